@@ -1,0 +1,134 @@
+"""CPU suite: the numpy oracle replayed against outputs of the reference itself
+(tests/golden/*.npz, produced by oracle/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+
+from oracle import nerf_oracle as orc
+
+
+def test_linspace_tables(golden):
+    fx = golden("sample_coarse")
+    assert np.array_equal(orc.linspace_f32(0, 1, 64), fx["t_vals"])
+    assert np.array_equal(orc.linspace_f32(0, 1, 64), golden("sample_pdf")["u_det"])
+
+
+@pytest.mark.parametrize("lindisp", [0, 1])
+@pytest.mark.parametrize("perturb", [0, 1])
+def test_sample_coarse_bit_exact(golden, lindisp, perturb):
+    fx = golden("sample_coarse")
+    key = "lindisp%d_perturb%d" % (lindisp, perturb)
+    z = orc.sample_coarse(fx[key + "_rays"], fx["t_vals"], fx["t_rand"] if perturb else None, bool(lindisp))
+    assert np.array_equal(z, fx[key + "_z"])
+
+
+@pytest.mark.parametrize("dist", ["uniform", "peaky", "sparse", "zeros"])
+@pytest.mark.parametrize("mode", ["det", "rand"])
+def test_sample_pdf_bit_exact(golden, dist, mode):
+    fx = golden("sample_pdf")
+    u = fx["u_det"] if mode == "det" else fx["u_rand"]
+    out = orc.sample_pdf(fx["bins"], fx["w_" + dist], u)
+    tag = "%s_%s" % (dist, mode)
+    assert np.array_equal(out["cdf"], fx["cdf_" + tag])
+    assert np.array_equal(out["inds"], fx["inds_" + tag])
+    assert out["inds"].dtype == np.int64
+    assert np.array_equal(out["samples"], fx["samples_" + tag])
+
+
+def test_searchsorted_ties():
+    # torch.searchsorted(right=True) == numpy side='right' == upper_bound
+    cdf = np.array([0, .25, .25, .5, 1], dtype=np.float32)
+    u = np.array([0, .25, .3, .5, .999, 1, 1.5], dtype=np.float32)
+    assert list(np.searchsorted(cdf, u, side="right")) == [1, 3, 3, 4, 4, 5, 5]
+
+
+def test_merge(golden):
+    fx = golden("merge")
+    w = np.zeros((fx["z"].shape[0], 64), np.float32)
+    merged = np.sort(np.concatenate([fx["z"], fx["z_samples"]], -1), -1)
+    assert np.array_equal(merged, fx["merged"])
+    zstd = np.std(fx["z_samples"].astype(np.float64), -1)
+    np.testing.assert_allclose(zstd, fx["z_std"], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("S", [64, 128])
+@pytest.mark.parametrize("white", [0, 1])
+@pytest.mark.parametrize("use_noise", [0, 1])
+def test_raw2outputs_forward(golden, S, white, use_noise):
+    fx = golden("raw2outputs")
+    tag = "S%d_w%d_n%d" % (S, white, use_noise)
+    noise = fx["S%d_noise" % S] if use_noise else None
+    out = orc.raw2outputs(fx["S%d_raw" % S], fx["S%d_z" % S], fx["S%d_rays_d" % S], noise, bool(white))
+    for k, name in [("rgb_map", "rgb"), ("acc_map", "acc"), ("weights", "weights"), ("depth_map", "depth"),
+                    ("alpha", "alpha"), ("disp_map", "disp")]:
+        ref = fx[tag + "_" + name]
+        got = out[k]
+        assert np.array_equal(np.isnan(ref), np.isnan(got)), k
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True, err_msg=k)
+    if not use_noise:
+        assert np.isnan(out["disp_map"][0])      # the all-sigma<=0 ray keeps its NaN (reference behaviour)
+
+
+@pytest.mark.parametrize("S", [64, 128])
+@pytest.mark.parametrize("white", [0, 1])
+@pytest.mark.parametrize("use_noise", [0, 1])
+def test_raw2outputs_backward(golden, S, white, use_noise):
+    fx = golden("raw2outputs")
+    tag = "S%d_w%d_n%d" % (S, white, use_noise)
+    noise = fx["S%d_noise" % S] if use_noise else None
+    d_raw = orc.raw2outputs_backward(fx["S%d_raw" % S], fx["S%d_z" % S], fx["S%d_rays_d" % S], noise, bool(white),
+                                     fx[tag + "_g_rgb"], fx[tag + "_g_disp"], fx[tag + "_g_acc"],
+                                     fx[tag + "_g_depth"], fx[tag + "_g_weights"])
+    ref = fx[tag + "_d_raw"]
+    scale = np.abs(ref).max()
+    assert np.abs(d_raw - ref).max() <= 2e-5 * scale
+
+
+def test_embed_and_mlp(golden):
+    fx = golden("nerf_mlp")
+    p = orc.init_params(int(fx["param_seed"]))
+    x = np.concatenate([orc.embed(fx["pts"], 10), orc.embed(fx["viewdirs"], 4)], -1)
+    assert x.shape[1] == 90
+    np.testing.assert_allclose(x, fx["embedded"], atol=2e-6, rtol=0)
+    out, saved = orc.nerf_forward(p, fx["embedded"], keep=True)
+    np.testing.assert_allclose(out, fx["out"], atol=2e-5, rtol=1e-5)
+    g = orc.nerf_backward(p, saved, fx["d_out"])
+    n = 0
+    for k in g:
+        ref = fx["grad." + k]
+        assert np.abs(g[k] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+        n += ref.size
+    assert n == 595844       # params per network
+
+
+def test_normal_map(golden):
+    fx = golden("normal_map")
+    K = fx["K"]
+    n = orc.normal_from_depth(fx["depth"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], k=31)
+    np.testing.assert_allclose(n, fx["normal_f64"], atol=1e-9)
+    np.testing.assert_allclose(n, fx["normal_f32"], atol=2e-4)          # reference fp32 unfold+inv path
+    gd = orc.normal_from_depth_backward(fx["depth"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], fx["g_normal_f64"], k=31)
+    np.testing.assert_allclose(gd, fx["d_depth_f64"], atol=1e-9 * max(1.0, np.abs(fx["d_depth_f64"]).max()))
+
+
+def test_render_rays_end_to_end(golden):
+    fx = golden("render_e2e")
+    pc = orc.init_params(int(fx["coarse_seed"]))
+    pf = orc.init_params(int(fx["fine_seed"]))
+    rays = orc.make_ray_batch(fx["rays_o"], fx["rays_d"], fx["near"], fx["far"])
+    t_vals = orc.linspace_f32(0, 1, 64)
+    # render kwargs (perturb=0, noise=0)
+    out = orc.render_rays(rays, pc, pf, t_vals, lindisp=True, white_bkgd=True)
+    np.testing.assert_allclose(out["rgb0"], fx["test_rgb0"], atol=2e-5)
+    np.testing.assert_allclose(out["rgb_map"], fx["test_rgb"], atol=5e-5)
+    np.testing.assert_allclose(out["depth_map"], fx["test_depth"], rtol=2e-4)
+    np.testing.assert_allclose(out["acc_map"], fx["test_acc"], atol=2e-5)
+    # fine z_vals follow the coarse weights: fp32 MLP rounding differences (BLAS order) may move a sample
+    # across a bin edge, so compare the bulk
+    close = np.isclose(out["z_vals"], fx["test_z_vals"], atol=1e-3)
+    assert close.mean() > 0.995
+    # train kwargs with the pytest=True streams
+    out = orc.render_rays(rays, pc, pf, t_vals, t_rand=fx["train_t_rand"], u=fx["train_u"],
+                          noise0=fx["train_noise0"], noise1=fx["train_noise1"], lindisp=True, white_bkgd=True)
+    np.testing.assert_allclose(out["rgb0"], fx["train_rgb0"], atol=2e-5)
+    np.testing.assert_allclose(out["rgb_map"], fx["train_rgb"], atol=5e-5)
+    np.testing.assert_allclose(out["disp_map"], fx["train_disp"], rtol=2e-4)
