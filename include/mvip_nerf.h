@@ -1,0 +1,160 @@
+/*
+ * mvip_nerf.h — C ABI of libmvip_nerf.so: the B200 (sm_100a) implementation of MVIP-NeRF's
+ * volume-rendering hot path.
+ *
+ * The reference has no FFI on this path (it is Python calling torch ops); the only FFI precedent in
+ * its tree is DS_NeRF/torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:9-20 (caller
+ * pre-allocates outputs, tensors must be CUDA + contiguous, library allocates nothing).  This header
+ * keeps that contract and adds an explicit stream.  Each entry point names the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as "host array";
+ *   - all buffers (inputs, outputs, stash, workspace) are owned by the caller; the library never
+ *     allocates or frees device memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 = OK, negative = error (MVIP_E_*); mvip_last_error() gives a thread-local
+ *     message.  There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - tensors are row-major and contiguous unless a stride parameter is given (strides in elements).
+ */
+#ifndef MVIP_NERF_H_
+#define MVIP_NERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVIP_ABI_VERSION 1
+
+#define MVIP_OK 0
+#define MVIP_E_INVALID (-1)     /* null / misaligned / out-of-range argument              */
+#define MVIP_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                */
+#define MVIP_E_CUDA (-3)        /* CUDA runtime error (launch failure, no device, ...)     */
+
+int mvip_abi_version(void);
+const char* mvip_last_error(void);
+/* compute capability of the current device as major*10+minor (e.g. 100), or <0 on error */
+int mvip_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stratified sampling along rays.            replaces DS_NeRF/run.py:1759-1781 (render_rays)
+ *   rays    [n_rays, ray_stride] fp32: o(0:3) d(3:6) near(6) far(7) ...
+ *   t_vals  [n_samples]  the torch.linspace(0,1,n_samples) table, computed by the host
+ *   t_rand  [n_rays, n_samples] uniform randoms (perturb > 0) or NULL (perturb == 0)
+ *   z_out   [n_rays, n_samples]
+ * Bit-exact against the reference's CPU result (every op rounded to fp32, no FMA contraction).
+ */
+int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const float* t_vals,
+                       const float* t_rand, int n_samples, int lindisp, float* z_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inverse-CDF sampling.                      replaces DS_NeRF/run_nerf_helpers.py:304-347 (sample_pdf)
+ *   bins    [n_rows, n_bins], weights [n_rows, n_bins-1]
+ *   u       [n_rows, n_out] or, if u_is_row, one row [n_out] shared by every ray (det=True linspace)
+ *   samples [n_rows, n_out];  inds [n_rows, n_out] int64 = searchsorted(cdf, u, right=True) (nullable);
+ *   cdf     [n_rows, n_bins] (nullable).
+ * cdf / inds / samples are bit-exact against torch CPU for 8 <= n_bins-1 <= 512.
+ */
+int mvip_sample_pdf(const float* bins, const float* weights, const float* u, int u_is_row,
+                    int64_t n_rows, int n_bins, int n_out, float* samples, int64_t* inds, float* cdf,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hierarchical sampling step of render_rays. replaces DS_NeRF/run.py:1809-1816 and :1836
+ *   z_mid = .5*(z[1:]+z[:-1]); z_samples = sample_pdf(z_mid, weights[1:-1], n_out, u);
+ *   z_merged = sort(cat(z_vals, z_samples)); z_std = std(z_samples, unbiased=False)
+ *   z_vals, weights [n_rays, n_samples]; outputs z_samples [n_rays,n_out] (nullable),
+ *   inds int64 [n_rays,n_out] (nullable), z_merged [n_rays, n_samples+n_out], z_std [n_rays] (nullable).
+ */
+int mvip_sample_fine(const float* z_vals, const float* weights, const float* u, int u_is_row,
+                     int64_t n_rays, int n_samples, int n_out, float* z_samples, int64_t* inds,
+                     float* z_merged, float* z_std, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Alpha compositing.                         replaces DS_NeRF/run_nerf_helpers.py:350-404 (raw2outputs)
+ *   raw [n_rays, n_samples, 4], z_vals [n_rays, n_samples], rays_d [n_rays, rays_d_stride] (first 3 used)
+ *   noise [n_rays, n_samples] already multiplied by raw_noise_std, or NULL
+ *   outputs: rgb [n,3], disp [n], acc [n], weights [n,S], depth [n], alpha [n,S] (nullable)
+ */
+int mvip_composite_forward(const float* raw, const float* z_vals, const float* rays_d,
+                           int rays_d_stride, const float* noise, int64_t n_rays, int n_samples,
+                           int white_bkgd, float* rgb, float* disp, float* acc, float* weights,
+                           float* depth, float* alpha, void* stream);
+
+/* Hand-written backward of the above (what autograd computes for the reference function):
+ *   upstream g_rgb [n,3], g_disp [n], g_acc [n], g_depth [n] (each nullable = zeros),
+ *   g_weights [n,S] (nullable), g_alpha [n,S] (nullable);  d_raw [n,S,4] is overwritten.
+ *   No gradient is produced for z_vals / rays_d (they carry none in the reference: run.py:1812). */
+int mvip_composite_backward(const float* raw, const float* z_vals, const float* rays_d,
+                            int rays_d_stride, const float* noise, int64_t n_rays, int n_samples,
+                            int white_bkgd, int detach_weights, const float* g_rgb,
+                            const float* g_disp, const float* g_acc, const float* g_depth,
+                            const float* g_weights, const float* g_alpha, float* d_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depth -> least-squares plane normal.       replaces DS_NeRF/run.py:1909-1940
+ *   (depth2xyz_torch + depth2normal_geo, zero-padded k x k window, normal NOT normalised)
+ *   depth [H,W] -> normal [3,H,W].  workspace: mvip_normal_workspace_bytes(H,W) bytes.
+ */
+size_t mvip_normal_workspace_bytes(int H, int W);
+int mvip_normal_forward(const float* depth, int H, int W, float fx, float fy, float cx, float cy,
+                        int k, float* normal, void* workspace, void* stream);
+int mvip_normal_backward(const float* depth, int H, int W, float fx, float fy, float cx, float cy,
+                         int k, const float* g_normal, float* d_depth, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused positional encoding + 8x256 NeRF MLP (use_viewdirs, skip at 4).
+ *   replaces DS_NeRF/run.py:1108-1124 (run_network), run_nerf_helpers.py:22-52 (Embedder.embed) and
+ *   :104-127 (NeRF.forward); backward = autograd of the same.
+ *
+ * Parameters are passed as a host array of MVIP_MLP_NUM_PARAMS device pointers in this order
+ * (nn.Module names of run_nerf_helpers.py:86-100, fp32, [out,in] row-major):
+ *   0..15  pts_linears.{0..7}.{weight,bias}   16,17 views_linears.0.{weight,bias}
+ *   18,19  feature_linear.{weight,bias}       20,21 alpha_linear.{weight,bias}
+ *   22,23  rgb_linear.{weight,bias}
+ * mvip_mlp_pack_weights converts them to the bf16, pre-swizzled, TMA-friendly blob the kernels
+ * stream (re-run after every optimizer step).
+ */
+#define MVIP_MLP_NUM_PARAMS 24
+size_t mvip_mlp_packed_bytes(void);
+int mvip_mlp_pack_weights(const float* const* params /* host array */, void* packed, void* stream);
+
+/* Points are described either by rays + depths (pts = o + d*z, viewdir = rays[:, viewdir_offset:+3];
+ * n_points = n_rays*n_samples) or, when rays == NULL, directly by pts/dirs rows with strides
+ * (e.g. columns 0:3 and 63:66 of an already-embedded [P,90] tensor). */
+typedef struct mvip_points {
+  const float* rays;   int ray_stride;  int viewdir_offset;
+  const float* z_vals; int64_t n_rays;  int n_samples;
+  const float* pts;    int64_t pts_stride;
+  const float* dirs;   int64_t dirs_stride;
+  int64_t n_points;
+} mvip_points;
+
+/* stash: activations kept for the backward pass (NULL for inference); mvip_mlp_stash_bytes(n_points) bytes */
+size_t mvip_mlp_stash_bytes(int64_t n_points);
+int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw /* [n_points,4] */,
+                     void* stash, void* stream);
+
+/* workspace for the backward: mvip_mlp_backward_workspace_bytes(n_points) bytes.
+ * grads: host array of MVIP_MLP_NUM_PARAMS device pointers (same order/shapes as params), fp32;
+ * accumulate != 0 adds into them, otherwise they are overwritten. */
+size_t mvip_mlp_backward_workspace_bytes(int64_t n_points);
+int mvip_mlp_backward(const void* packed, const float* d_raw /* [n_points,4] */, int64_t n_points,
+                      const void* stash, void* workspace, float* const* grads /* host array */,
+                      int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Self tests of the tcgen05 building blocks (descriptor / layout conventions), used by tests/.
+ *   which: 0 = K-major A,B (forward / dgrad form)   1 = MN-major A,B (wgrad form)
+ *   a [M=128,K] , b [N,K] fp32 row-major for which==0;  a [K,128], b [K,N] for which==1
+ *   out [128, N] fp32 = A * B^T (bf16 inputs, fp32 accumulate).  K multiple of 64, N in {64,128,256}.
+ */
+int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVIP_NERF_H_ */

@@ -1,0 +1,257 @@
+// composite.cu — raw2outputs alpha compositing, forward and hand-written backward.
+//   replaces DS_NeRF/run_nerf_helpers.py:350-404; backward formula: SURVEY.md §8a'-3.
+//
+// One warp per ray.  Lane l owns C consecutive samples [l*C, l*C+C): raw is read as float4 per
+// sample (16 B, coalesced across the warp), the exclusive cumprod of (1-alpha+1e-10) is a local
+// product plus a 5-step multiplicative warp scan, and the five ray sums are warp-shuffle reductions.
+// HBM-bound: algorithmic bytes per ray = S*(16 raw + 4 z [+4 noise]) + 12 rays_d read,
+// S*4 weights [+S*4 alpha] + 24 written.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+
+template <int C>
+struct Fwd {
+  float a[C], q[C], T[C], w[C], zz[C], e[C], delta[C], sig[C];
+  float cr[C], cg[C], cb[C];
+  float D, A, R, G, Bc;  // ray sums: depth, acc, rgb
+};
+
+// loads one ray's samples and evaluates alpha / transmittance / weights / ray sums
+template <int C>
+__device__ __forceinline__ void eval_ray(Fwd<C>& f, const float4* __restrict__ raw, const float* __restrict__ z,
+                                         const float* __restrict__ noise, float norm, int S, int lane) {
+  const int base = lane * C;
+  float4 rw[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int i = base + k;
+    bool v = i < S;
+    rw[k] = v ? __ldg(raw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f.zz[k] = v ? __ldg(z + i) : 0.f;
+    float nz = (v && noise) ? __ldg(noise + i) : 0.f;
+    f.sig[k] = rw[k].w + nz;
+  }
+  float z_next_lane = __shfl_down_sync(FULL_MASK, f.zz[0], 1);
+  float prod = 1.f;
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int i = base + k;
+    float zn = (k + 1 < C) ? f.zz[(k + 1 < C) ? k + 1 : k] : z_next_lane;
+    float dist = (i + 1 < S) ? (zn - f.zz[k]) : 1e10f;
+    f.delta[k] = dist * norm;
+    float x = fmaxf(f.sig[k], 0.f) * f.delta[k];
+    f.e[k] = expf(-x);
+    f.a[k] = (i < S) ? (1.f - f.e[k]) : 0.f;
+    f.q[k] = (i < S) ? ((1.f - f.a[k]) + 1e-10f) : 1.f;
+    f.T[k] = prod;  // local exclusive product
+    prod *= f.q[k];
+    f.cr[k] = 1.f / (1.f + expf(-rw[k].x));
+    f.cg[k] = 1.f / (1.f + expf(-rw[k].y));
+    f.cb[k] = 1.f / (1.f + expf(-rw[k].z));
+  }
+  // exclusive multiplicative scan of the lane products
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float v = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float excl = __shfl_up_sync(FULL_MASK, incl, 1);
+  if (lane == 0) excl = 1.f;
+  float sD = 0.f, sA = 0.f, sR = 0.f, sG = 0.f, sB = 0.f;
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    f.T[k] *= excl;
+    f.w[k] = f.a[k] * f.T[k];
+    sD += f.w[k] * f.zz[k];
+    sA += f.w[k];
+    sR += f.w[k] * f.cr[k];
+    sG += f.w[k] * f.cg[k];
+    sB += f.w[k] * f.cb[k];
+  }
+  f.D = warp_sum(sD);
+  f.A = warp_sum(sA);
+  f.R = warp_sum(sR);
+  f.G = warp_sum(sG);
+  f.Bc = warp_sum(sB);
+}
+
+// lane-owned run of C floats -> global row (vectorised when the row layout keeps 16/8-byte alignment)
+template <int C>
+__device__ __forceinline__ void store_row(float* __restrict__ row, const float (&v)[C], int base, int S) {
+  if constexpr (C % 4 == 0) {
+    if ((S & 3) == 0 && base + C <= S) {
+#pragma unroll
+      for (int k = 0; k < C; k += 4) *reinterpret_cast<float4*>(row + base + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      return;
+    }
+  } else if constexpr (C == 2) {
+    if ((S & 1) == 0 && base + 2 <= S) {
+      *reinterpret_cast<float2*>(row + base) = make_float2(v[0], v[1]);
+      return;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < C; ++k)
+    if (base + k < S) row[base + k] = v[k];
+}
+
+__device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
+  float x = __ldg(d), y = __ldg(d + 1), z = __ldg(d + 2);
+  return sqrtf(x * x + y * y + z * z);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarps * 32)
+composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                     int d_stride, const float* __restrict__ noise, int64_t n_rays, int S, int white,
+                     float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
+                     float* __restrict__ weights, float* __restrict__ depth, float* __restrict__ alpha) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t ray = (int64_t)blockIdx.x * kWarps + warp; ray < n_rays; ray += (int64_t)gridDim.x * kWarps) {
+    Fwd<C> f;
+    float norm = ray_norm(rays_d + ray * d_stride);
+    eval_ray<C>(f, raw + ray * S, z + ray * S, noise ? noise + ray * S : nullptr, norm, S, lane);
+    const int base = lane * C;
+    store_row<C>(weights + ray * S, f.w, base, S);
+    if (alpha) store_row<C>(alpha + ray * S, f.a, base, S);
+    if (lane == 0) {
+      float r = f.D / f.A;
+      float m = (r != r) ? r : fmaxf(1e-10f, r);  // torch.max propagates NaN (0/0 when every sigma <= 0)
+      float bg = white ? (1.f - f.A) : 0.f;
+      rgb[ray * 3 + 0] = f.R + bg;
+      rgb[ray * 3 + 1] = f.G + bg;
+      rgb[ray * 3 + 2] = f.Bc + bg;
+      disp[ray] = 1.f / m;
+      acc[ray] = f.A;
+      depth[ray] = f.D;
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarps * 32)
+composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                     int d_stride, const float* __restrict__ noise, int64_t n_rays, int S, int white, int detach_w,
+                     const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
+                     const float* __restrict__ g_depth, const float* __restrict__ g_weights,
+                     const float* __restrict__ g_alpha, float4* __restrict__ d_raw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t ray = (int64_t)blockIdx.x * kWarps + warp; ray < n_rays; ray += (int64_t)gridDim.x * kWarps) {
+    Fwd<C> f;
+    float norm = ray_norm(rays_d + ray * d_stride);
+    eval_ray<C>(f, raw + ray * S, z + ray * S, noise ? noise + ray * S : nullptr, norm, S, lane);
+    float gR = 0.f, gG = 0.f, gB = 0.f;
+    if (g_rgb) { gR = __ldg(g_rgb + ray * 3); gG = __ldg(g_rgb + ray * 3 + 1); gB = __ldg(g_rgb + ray * 3 + 2); }
+    float gdisp = g_disp ? __ldg(g_disp + ray) : 0.f;
+    float gD = g_depth ? __ldg(g_depth + ray) : 0.f;
+    float gA = g_acc ? __ldg(g_acc + ray) : 0.f;
+    float r = f.D / f.A;
+    bool live = !(r <= 1e-10f);  // NaN keeps the path, as torch.max's backward does
+    if (live && g_disp) {
+      gD += -gdisp * f.A / (f.D * f.D);
+      gA += gdisp / f.D;
+    }
+    if (white) gA -= (gR + gG + gB);
+    const int base = lane * C;
+    float G[C], Gw[C];
+    float local = 0.f;
+#pragma unroll
+    for (int k = C - 1; k >= 0; --k) {
+      int i = base + k;
+      float g = f.zz[k] * gD + gA;
+      if (!detach_w) g += gR * f.cr[k] + gG * f.cg[k] + gB * f.cb[k];
+      if (g_weights && i < S) g += __ldg(g_weights + ray * S + i);
+      G[k] = g;
+      float gw = (i < S) ? g * f.w[k] : 0.f;
+      Gw[k] = local;  // local exclusive suffix
+      local += gw;
+    }
+    // exclusive suffix scan over lanes (sum of totals of higher lanes)
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float v = __shfl_down_sync(FULL_MASK, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    float excl = __shfl_down_sync(FULL_MASK, incl, 1);
+    if (lane == 31) excl = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      int i = base + k;
+      if (i < S) {
+        float suffix = Gw[k] + excl;
+        float dalpha = G[k] * f.T[k] - suffix / f.q[k];
+        if (g_alpha) dalpha += __ldg(g_alpha + ray * S + i);
+        float dsig = (f.sig[k] > 0.f) ? dalpha * f.delta[k] * f.e[k] : 0.f;
+        float wk = f.w[k];
+        float4 o;
+        o.x = wk * gR * f.cr[k] * (1.f - f.cr[k]);
+        o.y = wk * gG * f.cg[k] * (1.f - f.cg[k]);
+        o.z = wk * gB * f.cb[k] * (1.f - f.cb[k]);
+        o.w = dsig;
+        d_raw[ray * S + i] = o;
+      }
+    }
+  }
+}
+
+int grid_for_rays(int64_t n) {
+  int64_t blocks = (n + kWarps - 1) / kWarps;
+  int64_t cap = (int64_t)mvip_num_sms() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+#define DISPATCH_C(S, ...)                         \
+  do {                                             \
+    int c__ = ((S) + 31) / 32;                     \
+    if (c__ <= 1) { constexpr int C = 1; __VA_ARGS__; }       \
+    else if (c__ <= 2) { constexpr int C = 2; __VA_ARGS__; }  \
+    else if (c__ <= 4) { constexpr int C = 4; __VA_ARGS__; }  \
+    else if (c__ <= 8) { constexpr int C = 8; __VA_ARGS__; }  \
+    else { constexpr int C = 16; __VA_ARGS__; }               \
+  } while (0)
+
+extern "C" {
+
+int mvip_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                           const float* noise, int64_t n_rays, int n_samples, int white_bkgd, float* rgb, float* disp,
+                           float* acc, float* weights, float* depth, float* alpha, void* stream) {
+  MVIP_REQUIRE(raw && z_vals && rays_d && rgb && disp && acc && weights && depth, MVIP_E_INVALID,
+               "mvip_composite_forward: null pointer");
+  MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_forward: bad shape");
+  MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_forward: n_samples %d > 512", n_samples);
+  MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(weights, 16) && (!alpha || mvip_aligned(alpha, 16)),
+               MVIP_E_INVALID, "mvip_composite_forward: raw/weights/alpha must be 16-byte aligned");
+  if (n_rays == 0) return MVIP_OK;
+  DISPATCH_C(n_samples, (composite_fwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
+                            reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
+                            n_samples, white_bkgd, rgb, disp, acc, weights, depth, alpha)));
+  MVIP_LAUNCH_OK("composite_fwd_kernel");
+  return MVIP_OK;
+}
+
+int mvip_composite_backward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                            const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
+                            const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
+                            const float* g_weights, const float* g_alpha, float* d_raw, void* stream) {
+  MVIP_REQUIRE(raw && z_vals && rays_d && d_raw, MVIP_E_INVALID, "mvip_composite_backward: null pointer");
+  MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_backward: bad shape");
+  MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_backward: n_samples %d > 512", n_samples);
+  MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(d_raw, 16), MVIP_E_INVALID,
+               "mvip_composite_backward: raw/d_raw must be 16-byte aligned");
+  if (n_rays == 0) return MVIP_OK;
+  DISPATCH_C(n_samples, (composite_bwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
+                            reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
+                            n_samples, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha,
+                            reinterpret_cast<float4*>(d_raw))));
+  MVIP_LAUNCH_OK("composite_bwd_kernel");
+  return MVIP_OK;
+}
+
+}  // extern "C"

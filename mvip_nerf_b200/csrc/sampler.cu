@@ -1,0 +1,331 @@
+// sampler.cu — stratified sampling and hierarchical (inverse-CDF) sampling, bit-exact against the
+// reference's CPU path.  Compiled with -fmad=false; every rounding step below is explicit.
+//
+//   mvip_sample_coarse : DS_NeRF/run.py:1759-1781
+//   mvip_sample_pdf    : DS_NeRF/run_nerf_helpers.py:304-347
+//   mvip_sample_fine   : DS_NeRF/run.py:1809-1816, 1836
+//
+// Third-party rounding that is reproduced here (re-verified in oracle/nerf_oracle.py):
+//   torch.sum(x,-1) on CPU  = 8 SIMD lanes x 4 interleaved accumulators (aten_row_sum below)
+//   torch.cumsum on CPU     = fp64 accumulation, fp32 rounding per output
+//   torch.searchsorted(right=True) = upper bound, int64
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxBins = 256;  // n_bins (= N_samples-1 inside render_rays)
+constexpr int kMaxOut = 256;   // N_importance
+
+// ---------------------------------------------------------------------------------------------
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, int ray_stride, int64_t n_rays,
+                                     const float* __restrict__ t_vals, const float* __restrict__ t_rand, int S,
+                                     int lindisp, float* __restrict__ z_out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = n_rays * S;
+  if (idx >= total) return;
+  int64_t r = idx / S;
+  int i = (int)(idx - r * S);
+  float near = __ldg(rays + r * ray_stride + 6);
+  float far = __ldg(rays + r * ray_stride + 7);
+  float inv_near = 0.f, inv_far = 0.f;
+  if (lindisp) {
+    inv_near = __fdiv_rn(1.0f, near);
+    inv_far = __fdiv_rn(1.0f, far);
+  }
+  auto base = [&](int j) -> float {
+    float t = __ldg(t_vals + j);
+    float omt = __fsub_rn(1.0f, t);
+    if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+    float den = __fadd_rn(__fmul_rn(inv_near, omt), __fmul_rn(inv_far, t));
+    return __fdiv_rn(1.0f, den);
+  };
+  float z = base(i);
+  if (t_rand != nullptr) {
+    float lower = z, upper = z;
+    if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(z, base(i - 1)));
+    if (i < S - 1) upper = __fmul_rn(0.5f, __fadd_rn(base(i + 1), z));
+    float tr = __ldg(t_rand + idx);
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+  }
+  z_out[idx] = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// torch.sum over K contiguous floats in ATen's CPU order; every lane returns the same value.
+__device__ float aten_row_sum(const float* x, int K, int lane) {
+  const int nv = K >> 3;
+  const int nfull = (nv >> 2) << 2;
+  float t = 0.f;
+  if (lane < 8) {
+    float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+    for (int v = 0; v < nfull; v += 4) {
+      float a0 = x[8 * v + lane], a1 = x[8 * (v + 1) + lane], a2 = x[8 * (v + 2) + lane], a3 = x[8 * (v + 3) + lane];
+      if (v == 0) {
+        ps0 = a0; ps1 = a1; ps2 = a2; ps3 = a3;
+      } else {
+        ps0 = __fadd_rn(ps0, a0); ps1 = __fadd_rn(ps1, a1); ps2 = __fadd_rn(ps2, a2); ps3 = __fadd_rn(ps3, a3);
+      }
+    }
+    for (int v = nfull; v < nv; ++v) {
+      float a = x[8 * v + lane];
+      ps0 = (v == 0) ? a : __fadd_rn(ps0, a);
+    }
+    t = ps0;
+    if (nfull > 0) t = __fadd_rn(__fadd_rn(__fadd_rn(ps0, ps1), ps2), ps3);
+  }
+  float acc = 0.f;
+  for (int k = 8 * nv; k < K; ++k) acc = __fadd_rn(acc, x[k]);
+  if (nv > 0) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc = __fadd_rn(acc, __shfl_sync(FULL_MASK, t, l));
+  }
+  return acc;
+}
+
+// One warp turns (bins[B], w[K=B-1] (already +1e-5)) into cdf[B] in shared memory.
+// The fp64 warp scan is exact (hence order-independent, == the sequential CPU scan) whenever every
+// pdf value is > 0 and >= 2^-27; otherwise lane 0 falls back to the sequential scan.
+__device__ void warp_build_cdf(float* w, float* cdf, int K, int lane) {
+  float s = aten_row_sum(w, K, lane);
+  bool ok = true;
+  for (int i = lane; i < K; i += 32) {
+    float p = __fdiv_rn(w[i], s);
+    w[i] = p;  // w now holds the pdf
+    ok = ok && (p >= 7.450580596923828e-09f) && (p <= 1.0f);
+  }
+  ok = __all_sync(FULL_MASK, ok);
+  __syncwarp();
+  if (ok) {
+    const int c = (K + 31) >> 5;
+    const int b = lane * c;
+    const int e = min(K, b + c);
+    double local = 0.0;
+    for (int i = b; i < e; ++i) local += (double)w[i];
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double v = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    double run = incl - local;
+    for (int i = b; i < e; ++i) {
+      run += (double)w[i];
+      cdf[i + 1] = (float)run;
+    }
+    if (lane == 0) cdf[0] = 0.f;
+  } else if (lane == 0) {
+    double run = 0.0;
+    cdf[0] = 0.f;
+    for (int i = 0; i < K; ++i) {
+      run += (double)w[i];
+      cdf[i + 1] = (float)run;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int upper_bound(const float* a, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int lower_bound(const float* a, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int B, float u, int* ind_out) {
+  int ind = upper_bound(cdf, B, u);
+  *ind_out = ind;
+  int below = max(0, ind - 1);
+  int above = min(B - 1, ind);
+  float cb = cdf[below];
+  float denom = __fsub_rn(cdf[above], cb);
+  if (denom < 1e-5f) denom = 1.0f;
+  float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  float bb = bins[below];
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bins[above], bb)));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_kernel(const float* __restrict__ bins_g, const float* __restrict__ weights_g, const float* __restrict__ u_g,
+                  int u_is_row, int64_t n_rows, int B, int M, float* __restrict__ samples_g,
+                  int64_t* __restrict__ inds_g, float* __restrict__ cdf_g) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = B - 1;
+  float* bins = smem + warp * (3 * B);
+  float* w = bins + B;
+  float* cdf = w + B;
+  for (int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + warp; row < n_rows;
+       row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    for (int i = lane; i < B; i += 32) bins[i] = __ldg(bins_g + row * B + i);
+    for (int i = lane; i < K; i += 32) w[i] = __fadd_rn(__ldg(weights_g + row * K + i), 1e-5f);
+    __syncwarp();
+    warp_build_cdf(w, cdf, K, lane);
+    if (cdf_g) for (int i = lane; i < B; i += 32) cdf_g[row * B + i] = cdf[i];
+    for (int j = lane; j < M; j += 32) {
+      float u = u_is_row ? __ldg(u_g + j) : __ldg(u_g + row * M + j);
+      int ind;
+      float smp = invert_cdf(cdf, bins, B, u, &ind);
+      samples_g[row * M + j] = smp;
+      if (inds_g) inds_g[row * M + j] = (int64_t)ind;
+    }
+    __syncwarp();
+  }
+}
+
+// bitonic sort of P2 (power of two) floats in shared memory by one warp, ascending
+__device__ void warp_bitonic_sort(float* a, int P2, int lane) {
+  for (int k = 2; k <= P2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P2; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          float x = a[i], y = a[ixj];
+          bool up = ((i & k) == 0);
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_fine_kernel(const float* __restrict__ z_g, const float* __restrict__ weights_g, const float* __restrict__ u_g,
+                   int u_is_row, int64_t n_rays, int S, int M, int P2, float* __restrict__ samples_g,
+                   int64_t* __restrict__ inds_g, float* __restrict__ merged_g, float* __restrict__ std_g) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = S - 1, K = S - 2, T = S + M;
+  const int per_warp = S + 3 * B + P2 + T;
+  float* z = smem + warp * per_warp;
+  float* bins = z + S;
+  float* w = bins + B;
+  float* cdf = w + B;
+  float* smp = cdf + B;   // P2 entries
+  float* out = smp + P2;  // T entries
+  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp; ray < n_rays;
+       ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    for (int i = lane; i < S; i += 32) z[i] = __ldg(z_g + ray * S + i);
+    for (int i = lane; i < K; i += 32) w[i] = __fadd_rn(__ldg(weights_g + ray * S + 1 + i), 1e-5f);
+    __syncwarp();
+    for (int i = lane; i < B; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(z[i + 1], z[i]));
+    __syncwarp();
+    warp_build_cdf(w, cdf, K, lane);
+    double sum = 0.0;
+    for (int j = lane; j < P2; j += 32) {
+      float v = CUDART_INF_F;
+      if (j < M) {
+        float u = u_is_row ? __ldg(u_g + j) : __ldg(u_g + ray * M + j);
+        int ind;
+        v = invert_cdf(cdf, bins, B, u, &ind);
+        if (samples_g) samples_g[ray * M + j] = v;
+        if (inds_g) inds_g[ray * M + j] = (int64_t)ind;
+        sum += (double)v;
+      }
+      smp[j] = v;
+    }
+    __syncwarp();
+    if (std_g) {  // torch.std(unbiased=False), run.py:1836 (tolerance-checked, not bit-exact)
+      double mean = warp_sum(sum) / (double)M;
+      double sq = 0.0;
+      for (int j = lane; j < M; j += 32) {
+        double d = (double)smp[j] - mean;
+        sq += d * d;
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) std_g[ray] = (float)sqrt(sq / (double)M);
+    }
+    bool sorted = true;
+    for (int j = lane; j + 1 < M; j += 32) sorted = sorted && (smp[j] <= smp[j + 1]);
+    if (!__all_sync(FULL_MASK, sorted)) warp_bitonic_sort(smp, P2, lane);
+    // merge two sorted runs by rank: z elements go before equal samples
+    for (int i = lane; i < S; i += 32) {
+      float v = z[i];
+      out[i + lower_bound(smp, M, v)] = v;
+    }
+    for (int j = lane; j < M; j += 32) {
+      float v = smp[j];
+      out[j + upper_bound(z, S, v)] = v;
+    }
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) merged_g[ray * T + i] = out[i];
+    __syncwarp();
+  }
+}
+
+int grid_for_rows(int64_t rows) {
+  int64_t blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = (int64_t)mvip_num_sms() * 16;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const float* t_vals, const float* t_rand,
+                       int n_samples, int lindisp, float* z_out, void* stream) {
+  MVIP_REQUIRE(rays && t_vals && z_out, MVIP_E_INVALID, "mvip_sample_coarse: null pointer");
+  MVIP_REQUIRE(ray_stride >= 8 && n_samples >= 1 && n_rays >= 0, MVIP_E_INVALID,
+               "mvip_sample_coarse: bad shape (ray_stride=%d n_samples=%d)", ray_stride, n_samples);
+  if (n_rays == 0) return MVIP_OK;
+  int64_t total = n_rays * n_samples;
+  int threads = 256;
+  int64_t blocks = (total + threads - 1) / threads;
+  MVIP_REQUIRE(blocks < (1ll << 31), MVIP_E_UNSUPPORTED, "mvip_sample_coarse: too many rays");
+  sample_coarse_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, t_vals, t_rand,
+                                                                               n_samples, lindisp, z_out);
+  MVIP_LAUNCH_OK("sample_coarse_kernel");
+  return MVIP_OK;
+}
+
+int mvip_sample_pdf(const float* bins, const float* weights, const float* u, int u_is_row, int64_t n_rows, int n_bins,
+                    int n_out, float* samples, int64_t* inds, float* cdf, void* stream) {
+  MVIP_REQUIRE(bins && weights && u && samples, MVIP_E_INVALID, "mvip_sample_pdf: null pointer");
+  MVIP_REQUIRE(n_rows >= 0 && n_out >= 1, MVIP_E_INVALID, "mvip_sample_pdf: bad shape");
+  MVIP_REQUIRE(n_bins - 1 >= 8 && n_bins <= kMaxBins && n_out <= kMaxOut, MVIP_E_UNSUPPORTED,
+               "mvip_sample_pdf: need 9 <= n_bins <= %d and n_out <= %d (got %d, %d); torch's CPU sum order is only "
+               "reproduced for that range", kMaxBins, kMaxOut, n_bins, n_out);
+  if (n_rows == 0) return MVIP_OK;
+  size_t smem = (size_t)kWarpsPerBlock * 3 * n_bins * sizeof(float);
+  sample_pdf_kernel<<<grid_for_rows(n_rows), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      bins, weights, u, u_is_row, n_rows, n_bins, n_out, samples, inds, cdf);
+  MVIP_LAUNCH_OK("sample_pdf_kernel");
+  return MVIP_OK;
+}
+
+int mvip_sample_fine(const float* z_vals, const float* weights, const float* u, int u_is_row, int64_t n_rays,
+                     int n_samples, int n_out, float* z_samples, int64_t* inds, float* z_merged, float* z_std,
+                     void* stream) {
+  MVIP_REQUIRE(z_vals && weights && u && z_merged, MVIP_E_INVALID, "mvip_sample_fine: null pointer");
+  MVIP_REQUIRE(n_rays >= 0 && n_out >= 1, MVIP_E_INVALID, "mvip_sample_fine: bad shape");
+  MVIP_REQUIRE(n_samples - 2 >= 8 && n_samples - 1 <= kMaxBins && n_out <= kMaxOut, MVIP_E_UNSUPPORTED,
+               "mvip_sample_fine: need 10 <= n_samples <= %d and n_out <= %d (got %d, %d)", kMaxBins + 1, kMaxOut,
+               n_samples, n_out);
+  if (n_rays == 0) return MVIP_OK;
+  int P2 = 1;
+  while (P2 < n_out) P2 <<= 1;
+  int B = n_samples - 1;
+  size_t per_warp = (size_t)n_samples + 3 * B + P2 + (n_samples + n_out);
+  size_t smem = (size_t)kWarpsPerBlock * per_warp * sizeof(float);
+  sample_fine_kernel<<<grid_for_rows(n_rays), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      z_vals, weights, u, u_is_row, n_rays, n_samples, n_out, P2, z_samples, inds, z_merged, z_std);
+  MVIP_LAUNCH_OK("sample_fine_kernel");
+  return MVIP_OK;
+}
+
+}  // extern "C"

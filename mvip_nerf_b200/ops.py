@@ -1,0 +1,254 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mvip_nerf.h).
+
+PyTorch is plumbing only: it owns device memory and the stream; every computation below is one of
+our sm_100a kernels in libmvip_nerf.so.  Inputs must be CUDA tensors — there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PARAM_ORDER = (["pts_linears.%d.%s" % (i, k) for i in range(8) for k in ("weight", "bias")] +
+               ["views_linears.0.weight", "views_linears.0.bias", "feature_linear.weight", "feature_linear.bias",
+                "alpha_linear.weight", "alpha_linear.bias", "rgb_linear.weight", "rgb_linear.bias"])
+PARAM_SHAPES = ([(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (256,)] + [(256, 256), (256,)] * 2 +
+                [(128, 283), (128,), (256, 256), (256,), (1, 256), (1,), (3, 128), (3,)])
+
+# kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+_LAUNCHES = {"mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
+             "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4,
+             "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: mvip_nerf_b200 has no CPU fallback" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _call(name, *args):
+    global launch_count
+    lib = _lib.load()
+    rc = getattr(lib, name)(*args)
+    _lib.check(rc, name)
+    launch_count += _LAUNCHES.get(name, 1)
+
+
+# ---------------------------------------------------------------------------------------------- sampling
+def sample_coarse(rays, t_vals, t_rand=None, lindisp=False):
+    """rays [N,>=8] -> z_vals [N,S]   (run.py:1759-1781)"""
+    rays = _f32(rays, "rays")
+    t_vals = _f32(t_vals, "t_vals")
+    t_rand = _f32(t_rand, "t_rand")
+    N, S = rays.shape[0], t_vals.numel()
+    z = torch.empty((N, S), device=rays.device, dtype=torch.float32)
+    _call("mvip_sample_coarse", _ptr(rays), rays.shape[1], N, _ptr(t_vals), _ptr(t_rand), S, int(bool(lindisp)),
+          _ptr(z), _stream())
+    return z
+
+
+def _u_arg(u, n_rows):
+    u = _f32(u, "u")
+    if u.dim() == 1:
+        return u, 1, u.numel()
+    if u.shape[0] != n_rows:
+        raise RuntimeError("u has %d rows, expected %d" % (u.shape[0], n_rows))
+    return u, 0, u.shape[-1]
+
+
+def sample_pdf(bins, weights, u, want_inds=False, want_cdf=False):
+    """(run_nerf_helpers.py:304-347) bins [N,B], weights [N,B-1], u [N,M] or [M] -> samples [N,M] (+inds, +cdf)"""
+    bins = _f32(bins, "bins")
+    weights = _f32(weights, "weights")
+    N, B = bins.shape
+    if weights.shape != (N, B - 1):
+        raise RuntimeError("weights must be [N, n_bins-1]")
+    u, is_row, M = _u_arg(u, N)
+    samples = torch.empty((N, M), device=bins.device, dtype=torch.float32)
+    inds = torch.empty((N, M), device=bins.device, dtype=torch.int64) if want_inds else None
+    cdf = torch.empty((N, B), device=bins.device, dtype=torch.float32) if want_cdf else None
+    _call("mvip_sample_pdf", _ptr(bins), _ptr(weights), _ptr(u), is_row, N, B, M, _ptr(samples), _ptr(inds), _ptr(cdf),
+          _stream())
+    return samples, inds, cdf
+
+
+def sample_fine(z_vals, weights, u, want_samples=True, want_inds=False, want_std=True):
+    """(run.py:1809-1816,1836) -> dict(z_samples, inds, z_merged, z_std)"""
+    z_vals = _f32(z_vals, "z_vals")
+    weights = _f32(weights, "weights")
+    N, S = z_vals.shape
+    u, is_row, M = _u_arg(u, N)
+    dev = z_vals.device
+    z_samples = torch.empty((N, M), device=dev, dtype=torch.float32) if want_samples else None
+    inds = torch.empty((N, M), device=dev, dtype=torch.int64) if want_inds else None
+    z_std = torch.empty((N,), device=dev, dtype=torch.float32) if want_std else None
+    z_merged = torch.empty((N, S + M), device=dev, dtype=torch.float32)
+    _call("mvip_sample_fine", _ptr(z_vals), _ptr(weights), _ptr(u), is_row, N, S, M, _ptr(z_samples), _ptr(inds),
+          _ptr(z_merged), _ptr(z_std), _stream())
+    return {"z_samples": z_samples, "inds": inds, "z_merged": z_merged, "z_std": z_std}
+
+
+# ---------------------------------------------------------------------------------------------- compositing
+def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_alpha=False):
+    raw = _f32(raw, "raw")
+    z_vals = _f32(z_vals, "z_vals")
+    rays_d = _f32(rays_d, "rays_d")
+    noise = _f32(noise, "noise")
+    N, S = z_vals.shape
+    dev = raw.device
+    rgb = torch.empty((N, 3), device=dev, dtype=torch.float32)
+    disp = torch.empty((N,), device=dev, dtype=torch.float32)
+    acc = torch.empty((N,), device=dev, dtype=torch.float32)
+    depth = torch.empty((N,), device=dev, dtype=torch.float32)
+    weights = torch.empty((N, S), device=dev, dtype=torch.float32)
+    alpha = torch.empty((N, S), device=dev, dtype=torch.float32) if need_alpha else None
+    _call("mvip_composite_forward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), rays_d.shape[-1], _ptr(noise), N, S,
+          int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(weights), _ptr(depth), _ptr(alpha), _stream())
+    return rgb, disp, acc, weights, depth, alpha
+
+
+def composite_backward(raw, z_vals, rays_d, noise, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
+                       g_weights=None, g_alpha=None):
+    raw = _f32(raw, "raw")
+    z_vals = _f32(z_vals, "z_vals")
+    rays_d = _f32(rays_d, "rays_d")
+    N, S = z_vals.shape
+    d_raw = torch.empty((N, S, 4), device=raw.device, dtype=torch.float32)
+    args = [_f32(t, "grad") for t in (g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha)]
+    _call("mvip_composite_backward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), rays_d.shape[-1], _ptr(_f32(noise, "noise")),
+          N, S, int(bool(white_bkgd)), int(bool(detach_weights)), *[_ptr(a) for a in args], _ptr(d_raw), _stream())
+    return d_raw
+
+
+# ---------------------------------------------------------------------------------------------- normal map
+def _normal_ws(H, W, dev):
+    n = _lib.load().mvip_normal_workspace_bytes(H, W)
+    return torch.empty((n // 8,), device=dev, dtype=torch.float64)
+
+
+def normal_forward(depth, fx, fy, cx, cy, k=31):
+    depth = _f32(depth, "depth")
+    H, W = depth.shape
+    normal = torch.empty((3, H, W), device=depth.device, dtype=torch.float32)
+    ws = _normal_ws(H, W, depth.device)
+    _call("mvip_normal_forward", _ptr(depth), H, W, float(fx), float(fy), float(cx), float(cy), int(k), _ptr(normal),
+          _ptr(ws), _stream())
+    return normal
+
+
+def normal_backward(depth, fx, fy, cx, cy, g_normal, k=31):
+    depth = _f32(depth, "depth")
+    g_normal = _f32(g_normal, "g_normal")
+    H, W = depth.shape
+    d_depth = torch.empty((H, W), device=depth.device, dtype=torch.float32)
+    ws = _normal_ws(H, W, depth.device)
+    _call("mvip_normal_backward", _ptr(depth), H, W, float(fx), float(fy), float(cx), float(cy), int(k), _ptr(g_normal),
+          _ptr(d_depth), _ptr(ws), _stream())
+    return d_depth
+
+
+# ---------------------------------------------------------------------------------------------- MLP
+def _aligned_bytes(nbytes, dev):
+    """uint8 buffer whose data_ptr is 1024-byte aligned (torch's caching allocator gives >= 512)."""
+    buf = torch.empty((nbytes + 1024,), device=dev, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def mlp_pack(params, out=None):
+    """params: sequence of 24 fp32 CUDA tensors in PARAM_ORDER -> packed uint8 blob"""
+    lib = _lib.load()
+    ps = [_f32(p.detach(), "param") for p in params]
+    if len(ps) != _lib.MVIP_MLP_NUM_PARAMS:
+        raise RuntimeError("expected %d parameter tensors" % _lib.MVIP_MLP_NUM_PARAMS)
+    for t, shp, name in zip(ps, PARAM_SHAPES, PARAM_ORDER):
+        if tuple(t.shape) != shp:
+            raise RuntimeError("%s has shape %s, the fused kernels need %s (D=8, W=256, multires=10/4, skips=[4], "
+                               "use_viewdirs)" % (name, tuple(t.shape), shp))
+    if out is None:
+        out = _aligned_bytes(lib.mvip_mlp_packed_bytes(), ps[0].device)
+    arr = (ctypes.c_void_p * len(ps))(*[t.data_ptr() for t in ps])
+    _call("mvip_mlp_pack_weights", arr, _ptr(out), _stream())
+    return out
+
+
+def _points_struct(rays=None, z_vals=None, viewdir_offset=8, pts=None, dirs=None):
+    s = _lib.MvipPoints()
+    keep = []
+    if rays is not None:
+        rays = _f32(rays, "rays")
+        z_vals = _f32(z_vals, "z_vals")
+        keep += [rays, z_vals]
+        s.rays = rays.data_ptr()
+        s.ray_stride = rays.shape[1]
+        s.viewdir_offset = viewdir_offset
+        s.z_vals = z_vals.data_ptr()
+        s.n_rays = rays.shape[0]
+        s.n_samples = z_vals.shape[1]
+        s.n_points = rays.shape[0] * z_vals.shape[1]
+    else:
+        if pts.dtype != torch.float32 or dirs.dtype != torch.float32 or not pts.is_cuda:
+            raise RuntimeError("pts/dirs must be fp32 CUDA tensors")
+        if pts.stride(-1) != 1 or dirs.stride(-1) != 1:
+            pts, dirs = pts.contiguous(), dirs.contiguous()
+        keep += [pts, dirs]
+        s.rays = None
+        s.pts = pts.data_ptr()
+        s.pts_stride = pts.stride(0)
+        s.dirs = dirs.data_ptr()
+        s.dirs_stride = dirs.stride(0)
+        s.n_points = pts.shape[0]
+    return s, keep
+
+
+def mlp_forward(packed, rays=None, z_vals=None, viewdir_offset=8, pts=None, dirs=None, want_stash=False):
+    """-> raw [P,4] (and the stash buffer when want_stash)"""
+    lib = _lib.load()
+    s, keep = _points_struct(rays, z_vals, viewdir_offset, pts, dirs)
+    dev = keep[0].device
+    raw = torch.empty((s.n_points, 4), device=dev, dtype=torch.float32)
+    stash = _aligned_bytes(lib.mvip_mlp_stash_bytes(s.n_points), dev) if want_stash else None
+    _call("mvip_mlp_forward", _ptr(packed), ctypes.byref(s), _ptr(raw), _ptr(stash), _stream())
+    return (raw, stash) if want_stash else raw
+
+
+def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
+    """-> list of 24 fp32 gradient tensors in PARAM_ORDER"""
+    lib = _lib.load()
+    d_raw = _f32(d_raw, "d_raw").reshape(-1, 4)
+    P = d_raw.shape[0]
+    dev = d_raw.device
+    if grads is None:
+        grads = [torch.zeros(shp, device=dev, dtype=torch.float32) for shp in PARAM_SHAPES]
+        accumulate = False
+    ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
+    arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    _call("mvip_mlp_backward", _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr, int(bool(accumulate)),
+          _stream())
+    return grads
+
+
+def selftest_umma(which, a, b):
+    a = _f32(a, "a")
+    b = _f32(b, "b")
+    if which == 0:
+        K, N = a.shape[1], b.shape[0]
+    else:
+        K, N = a.shape[0], b.shape[1]
+    out = torch.empty((128, N), device=a.device, dtype=torch.float32)
+    _call("mvip_selftest_umma", int(which), _ptr(a), _ptr(b), N, K, _ptr(out), _stream())
+    return out

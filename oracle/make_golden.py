@@ -148,14 +148,14 @@ def main():
                 g_rgb = torch.randn(N, 3, generator=g); g_disp = torch.randn(N, generator=g)
                 g_acc = torch.randn(N, generator=g); g_depth = torch.randn(N, generator=g)
                 g_w = torch.randn(N, S, generator=g)
-                live = ~torch.isnan(disp)
-                loss = (rgb * g_rgb).sum() + (disp[live] * g_disp[live]).sum() + (acc * g_acc).sum() + \
+                # NaN disp rays stay in the graph: the reference then yields NaN grads for exactly those rays
+                loss = (rgb * g_rgb).sum() + (disp * g_disp).sum() + (acc * g_acc).sum() + \
                     (depth * g_depth).sum() + (wts * g_w).sum()
                 loss.backward()
                 fx[tag + "_rgb"] = rgb.detach().numpy(); fx[tag + "_disp"] = disp.detach().numpy()
                 fx[tag + "_acc"] = acc.detach().numpy(); fx[tag + "_weights"] = wts.detach().numpy()
                 fx[tag + "_depth"] = depth.detach().numpy(); fx[tag + "_alpha"] = alpha.detach().numpy()
-                fx[tag + "_g_rgb"] = g_rgb.numpy(); fx[tag + "_g_disp"] = (g_disp * live).numpy()
+                fx[tag + "_g_rgb"] = g_rgb.numpy(); fx[tag + "_g_disp"] = g_disp.numpy()
                 fx[tag + "_g_acc"] = g_acc.numpy(); fx[tag + "_g_depth"] = g_depth.numpy()
                 fx[tag + "_g_weights"] = g_w.numpy(); fx[tag + "_d_raw"] = r.grad.numpy()
         fx["S%d_raw" % S] = raw.numpy(); fx["S%d_z" % S] = zz.numpy()

@@ -49,6 +49,8 @@ def aten_sum_lastdim(x):
     Pins `torch.sum(weights, -1, keepdim=True)` of run_nerf_helpers.py:307."""
     x = np.ascontiguousarray(x, dtype=f32)
     K = x.shape[-1]
+    if 5 <= K <= 7 or K > 512:
+        raise ValueError("aten_sum_lastdim restatement verified only for K in [1,4] U [8,512] (got %d)" % K)
     lead = x.shape[:-1]
     x2 = x.reshape(-1, K)
     nv = K // 8
@@ -342,7 +344,7 @@ def raw2outputs_backward(raw, z_vals, rays_d, noise, white_bkgd,
     A = w.sum(-1)
     with np.errstate(divide="ignore", invalid="ignore"):
         r = Dm / A
-        live = (r > 1e-10)
+        live = ~(r <= 1e-10)      # torch.max(1e-10, r) backward: r==NaN keeps the grad path (-> NaN), like the reference
         gD = np.asarray(g_depth, dtype=dtype) + np.where(live, -np.asarray(g_disp, dtype=dtype) * A / (Dm * Dm), 0.0)
         gA = np.asarray(g_acc, dtype=dtype) + np.where(live, np.asarray(g_disp, dtype=dtype) / Dm, 0.0)
     g_rgb = np.asarray(g_rgb, dtype=dtype)

@@ -1,0 +1,210 @@
+"""GPU suite (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the
+golden vectors produced by the reference and against the numpy oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mvip_nerf_b200 import ops as o
+    return o
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("lindisp", [0, 1])
+@pytest.mark.parametrize("perturb", [0, 1])
+def test_sample_coarse_bit_exact_vs_reference(ops, golden, lindisp, perturb):
+    fx = golden("sample_coarse")
+    key = "lindisp%d_perturb%d" % (lindisp, perturb)
+    z = ops.sample_coarse(cu(fx[key + "_rays"]), cu(fx["t_vals"]), cu(fx["t_rand"]) if perturb else None, bool(lindisp))
+    assert np.array_equal(npy(z), fx[key + "_z"])
+
+
+@pytest.mark.parametrize("dist", ["uniform", "peaky", "sparse", "zeros"])
+@pytest.mark.parametrize("mode", ["det", "rand"])
+def test_sample_pdf_bit_exact_vs_reference(ops, golden, dist, mode):
+    fx = golden("sample_pdf")
+    u = fx["u_det"] if mode == "det" else fx["u_rand"]
+    samples, inds, cdf = ops.sample_pdf(cu(fx["bins"]), cu(fx["w_" + dist]), cu(u), want_inds=True, want_cdf=True)
+    tag = "%s_%s" % (dist, mode)
+    assert np.array_equal(npy(cdf), fx["cdf_" + tag])
+    assert inds.dtype == torch.int64
+    assert np.array_equal(npy(inds), fx["inds_" + tag])          # sample indices: bit-exact
+    assert np.array_equal(npy(samples), fx["samples_" + tag])
+
+
+def test_sample_pdf_large_random_vs_oracle(ops):
+    rng = np.random.RandomState(7)
+    N = 20000
+    z = np.sort(1.2 + 6.5 * rng.rand(N, 64).astype(np.float32), -1)
+    bins = (0.5 * (z[:, 1:] + z[:, :-1])).astype(np.float32)
+    w = (rng.rand(N, 62) ** 8).astype(np.float32)
+    w[::7] *= (rng.rand(*w[::7].shape) > 0.9)
+    w[::13] = 0
+    w[5::17] *= 1e-12                                   # tiny pdf entries exercise the sequential-scan fallback
+    w[5::17, 3] = 1.0
+    u = rng.rand(N, 64).astype(np.float32)
+    u[:, 0] = 0.0
+    u[:, 1] = 1.0
+    want = orc.sample_pdf(bins, w, u)
+    samples, inds, cdf = ops.sample_pdf(cu(bins), cu(w), cu(u), want_inds=True, want_cdf=True)
+    assert np.array_equal(npy(cdf), want["cdf"])
+    assert np.array_equal(npy(inds), want["inds"])
+    assert np.array_equal(npy(samples), want["samples"])
+
+
+def test_sample_fine_merge_vs_reference(ops, golden):
+    fx = golden("merge")
+    sp = golden("sample_pdf")
+    N = fx["z"].shape[0]
+    w = np.zeros((N, 64), np.float32)
+    w[:, 1:-1] = sp["w_peaky"]
+    out = ops.sample_fine(cu(fx["z"]), cu(w), cu(sp["u_rand"]), want_inds=True)
+    assert np.array_equal(npy(out["z_samples"]), fx["z_samples"])
+    assert np.array_equal(npy(out["z_merged"]), fx["merged"])       # == torch.sort(cat) of the reference
+    np.testing.assert_allclose(npy(out["z_std"]), fx["z_std"], rtol=2e-5, atol=1e-6)
+    # det mode: u row shared by all rays, samples already sorted
+    out = ops.sample_fine(cu(fx["z"]), cu(w), cu(sp["u_det"]), want_inds=True)
+    want = orc.fine_samples(fx["z"], w, sp["u_det"])
+    assert np.array_equal(npy(out["z_merged"]), want["z_merged"])
+    assert np.array_equal(npy(out["inds"]), want["inds"])
+
+
+def test_sample_shapes_rejected(ops):
+    z = torch.zeros(4, 8, device="cuda")
+    with pytest.raises(RuntimeError, match="n_samples"):
+        ops.sample_fine(z, z, torch.linspace(0, 1, 8, device="cuda"))
+    assert ops.sample_coarse(torch.zeros(0, 11, device="cuda"), torch.linspace(0, 1, 64, device="cuda")).shape == (0, 64)
+
+
+# ------------------------------------------------------------------------------------------ compositing
+@pytest.mark.parametrize("S", [64, 128])
+@pytest.mark.parametrize("white", [0, 1])
+@pytest.mark.parametrize("use_noise", [0, 1])
+def test_composite_forward_vs_reference(ops, golden, S, white, use_noise):
+    fx = golden("raw2outputs")
+    tag = "S%d_w%d_n%d" % (S, white, use_noise)
+    noise = cu(fx["S%d_noise" % S]) if use_noise else None
+    rgb, disp, acc, w, depth, alpha = ops.composite_forward(cu(fx["S%d_raw" % S]), cu(fx["S%d_z" % S]),
+                                                            cu(fx["S%d_rays_d" % S]), noise, bool(white), need_alpha=True)
+    for got, name in [(rgb, "rgb"), (acc, "acc"), (w, "weights"), (depth, "depth"), (alpha, "alpha"), (disp, "disp")]:
+        ref = fx[tag + "_" + name]
+        got = npy(got)
+        assert np.array_equal(np.isnan(ref), np.isnan(got)), name
+        # fp32 compositing: 1e-5 relative (north_star); atol covers entries that are ~0
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True, err_msg=name)
+
+
+@pytest.mark.parametrize("S", [64, 128])
+@pytest.mark.parametrize("white", [0, 1])
+@pytest.mark.parametrize("use_noise", [0, 1])
+def test_composite_backward_vs_reference_autograd(ops, golden, S, white, use_noise):
+    fx = golden("raw2outputs")
+    tag = "S%d_w%d_n%d" % (S, white, use_noise)
+    noise = cu(fx["S%d_noise" % S]) if use_noise else None
+    d_raw = ops.composite_backward(cu(fx["S%d_raw" % S]), cu(fx["S%d_z" % S]), cu(fx["S%d_rays_d" % S]), noise,
+                                   bool(white), False, cu(fx[tag + "_g_rgb"]), cu(fx[tag + "_g_disp"]),
+                                   cu(fx[tag + "_g_acc"]), cu(fx[tag + "_g_depth"]), cu(fx[tag + "_g_weights"]))
+    ref = fx[tag + "_d_raw"]
+    got = npy(d_raw)
+    assert np.array_equal(np.isnan(ref), np.isnan(got))
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() <= 2e-5 * np.abs(ref[ok]).max()
+
+
+@pytest.mark.parametrize("S", [1, 7, 33, 48, 200])
+def test_composite_ragged_sample_counts_vs_oracle(ops, S):
+    rng = np.random.RandomState(S)
+    N = 37
+    raw = rng.randn(N, S, 4).astype(np.float32)
+    z = np.sort(1 + 5 * rng.rand(N, S).astype(np.float32), -1)
+    rd = rng.randn(N, 3).astype(np.float32)
+    want = orc.raw2outputs(raw, z, rd, None, True)
+    rgb, disp, acc, w, depth, _ = ops.composite_forward(cu(raw), cu(z), cu(rd), None, True)
+    np.testing.assert_allclose(npy(w), want["weights"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(rgb), want["rgb_map"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(depth), want["depth_map"], rtol=1e-5, atol=1e-6)
+    g = [rng.randn(N, 3), rng.randn(N), rng.randn(N), rng.randn(N), rng.randn(N, S)]
+    g = [x.astype(np.float32) for x in g]
+    want_b = orc.raw2outputs_backward(raw, z, rd, None, True, *g)
+    got_b = npy(ops.composite_backward(cu(raw), cu(z), cu(rd), None, True, False, *[cu(x) for x in g]))
+    assert np.abs(got_b - want_b).max() <= 3e-5 * np.abs(want_b).max()
+
+
+def test_composite_linearity_at_full_size(ops):
+    # size-independent property at the cfg-3 chunk size: rgb_map is linear in sigmoid(rgb) for fixed sigma,
+    # acc + transmittance of the last sample == 1, weights >= 0
+    N, S = 32768, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    raw = torch.randn(N, S, 4, device="cuda", generator=g)
+    z = torch.sort(1.2 + 6.5 * torch.rand(N, S, device="cuda", generator=g), -1)[0]
+    rd = torch.randn(N, 3, device="cuda", generator=g)
+    rgb, disp, acc, w, depth, alpha = ops.composite_forward(raw, z, rd, None, False, need_alpha=True)
+    assert float(w.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    raw2 = raw.clone()
+    raw2[..., :3] = 50.0                                  # sigmoid -> 1: rgb_map == acc
+    rgb2, _, acc2, _, _, _ = ops.composite_forward(raw2, z, rd, None, False)
+    torch.testing.assert_close(rgb2, acc2[:, None].expand(-1, 3), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(acc2, acc)
+    torch.testing.assert_close(depth, (w * z).sum(-1), rtol=2e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ normal map
+def test_normal_map_vs_reference(ops, golden):
+    fx = golden("normal_map")
+    K = fx["K"]
+    args = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+    n = npy(ops.normal_forward(cu(fx["depth"]), *args, k=31))
+    # the reference's own fp32 path differs from its fp64 path by ~1e-5; tolerance 1e-4 abs
+    np.testing.assert_allclose(n, fx["normal_f32"], atol=1e-4)
+    np.testing.assert_allclose(n, fx["normal_f64"], atol=2e-5)
+    gd = npy(ops.normal_backward(cu(fx["depth"]), *args, cu(fx["g_normal_f64"].astype(np.float32)), k=31))
+    ref = fx["d_depth_f64"]
+    assert np.abs(gd - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_normal_map_plane_property(ops):
+    # a fronto-parallel plane z = c has normal M^-1 s = (0, 0, 1/c) everywhere, any window, any size
+    H, W = 512, 512
+    depth = torch.full((H, W), 4.0, device="cuda")
+    n = ops.normal_forward(depth, 500.0, 500.0, W / 2, H / 2, k=31)
+    torch.testing.assert_close(n[2], torch.full((H, W), 0.25, device="cuda"), atol=1e-5, rtol=0)
+    assert float(n[:2].abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 building blocks
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (128, 128), (64, 64)])
+def test_umma_k_major(ops, N, K):
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    a = torch.randn(128, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    out = ops.selftest_umma(0, a, b)
+    ref = a.bfloat16().float() @ b.bfloat16().float().t()
+    torch.testing.assert_close(out, ref, atol=1e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 128), (64, 64), (128, 256)])
+def test_umma_mn_major(ops, N, K):
+    g = torch.Generator(device="cuda").manual_seed(N + K + 1)
+    a = torch.randn(K, 128, device="cuda", generator=g)
+    b = torch.randn(K, N, device="cuda", generator=g)
+    ref = a.bfloat16().float().t() @ b.bfloat16().float()
+    out1 = ops.selftest_umma(1, a, b)
+    err1 = float((out1 - ref).abs().max())
+    if err1 > 1e-2:                                      # diagnostic: which LBO/SBO convention the hardware uses
+        out2 = ops.selftest_umma(2, a, b)
+        err2 = float((out2 - ref).abs().max())
+        pytest.fail("MN-major convention 1 wrong (err %.3g); swapped convention err %.3g" % (err1, err2))
