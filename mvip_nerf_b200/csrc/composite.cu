@@ -222,7 +222,7 @@ extern "C" {
 int mvip_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
                            const float* noise, int64_t n_rays, int n_samples, int white_bkgd, float* rgb, float* disp,
                            float* acc, float* weights, float* depth, float* alpha, void* stream) {
-  MVIP_REQUIRE(raw && z_vals && rays_d && rgb && disp && acc && weights && depth, MVIP_E_INVALID,
+  MVIP_REQUIRE(n_rays == 0 || (raw && z_vals && rays_d && rgb && disp && acc && weights && depth), MVIP_E_INVALID,
                "mvip_composite_forward: null pointer");
   MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_forward: bad shape");
   MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_forward: n_samples %d > 512", n_samples);
@@ -240,7 +240,7 @@ int mvip_composite_backward(const float* raw, const float* z_vals, const float* 
                             const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
                             const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
                             const float* g_weights, const float* g_alpha, float* d_raw, void* stream) {
-  MVIP_REQUIRE(raw && z_vals && rays_d && d_raw, MVIP_E_INVALID, "mvip_composite_backward: null pointer");
+  MVIP_REQUIRE(n_rays == 0 || (raw && z_vals && rays_d && d_raw), MVIP_E_INVALID, "mvip_composite_backward: null pointer");
   MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_backward: bad shape");
   MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_backward: n_samples %d > 512", n_samples);
   MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(d_raw, 16), MVIP_E_INVALID,

@@ -1,9 +1,686 @@
-// mlp_backward.cu — placeholder until the dgrad-chain / wgrad kernels land.
+// mlp_backward.cu — backward of the fused NeRF MLP (what autograd computes for NeRF.forward,
+// DS_NeRF/run_nerf_helpers.py:104-127), from the activation stash written by mlp_forward.cu.
+//
+// Four launches per call:
+//   1. dgrad_chain_kernel  tcgen05, tile-major like the forward: d_raw -> d hidden_pre -> d feature ->
+//                          dZ_7 .. dZ_0 (grad w.r.t. each layer's pre-activation), transposed weights
+//                          streamed by TMA, ReLU masks from the stash; every dZ tile image is bulk-stored.
+//   2. wgrad_kernel        tcgen05 with MN-major operands: dW_l = dZ_l^T X_l, K = points.  The stash
+//                          images are used as-is (the bytes of a K-major [points x features] tile are an
+//                          MN-major operand when points are the contraction).  Persistent CTAs own a
+//                          contiguous, cost-balanced range of (layer, tile) work; accumulators stay in
+//                          TMEM over the whole range and are flushed once as fp32 partials.  Four spare
+//                          warps sum the dZ columns (bias grads) from the staged operand.
+//   3. head_grads_kernel   CUDA cores: alpha_linear / rgb_linear weight + bias grads (N = 1 and 3).
+//   4. reduce_kernel       deterministic (fixed-order) sum of the partials into the caller's grad tensors.
+// No gradient flows to pts / viewdirs (none is required by the reference: z_samples is detached, run.py:1812).
 #include "mlp_common.cuh"
+
+namespace {
+using namespace mlp;
+
+// =================================================================================================
+// 1. dgrad chain
+// =================================================================================================
+constexpr int kCThreads = 384;
+constexpr int kCStages = 3;
+constexpr uint32_t kCSmemAct = 0;                        // act[2]: 2 x 64 KB
+constexpr uint32_t kCSmemW = 2 * 4 * kActChunk;          // weight ring 3 x 32 KB
+constexpr uint32_t kCSmemBytes = kCSmemW + kCStages * kW256;  // 229,376
+constexpr int kCSteps = 9;
+
+struct ChainParams {
+  const uint8_t* packed;
+  const float4* d_raw;
+  const uint8_t* stash;
+  uint8_t* dz;
+  int64_t n_points;
+  int64_t n_tiles;
+};
+
+__device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
+
+__global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[kCStages], bar_empty[kCStages], bar_acc[2], bar_act[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const uint8_t* wT = p.packed + kFwdBytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < kCStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
+        int cidx = 0;
+        for (int s = 0; s < kCSteps; ++s) {
+          const int nch = chain_nchunks(s);
+          for (int slot = 0; slot < 2; ++slot) {
+            for (int ci = 0; ci < nch; ++ci) {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&bar_full[stage], kW256);
+              tma_load_1d(smem + kCSmemW + stage * kW256, wT + (size_t)(cidx + ci) * kW256, kW256, &bar_full[stage]);
+              if (++stage == kCStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          cidx += nch;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; uint32_t act_phase[2] = {0, 0};
+      const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
+        for (int s = 0; s < kCSteps; ++s) {
+          const int nch = chain_nchunks(s);
+          for (int slot = 0; slot < 2; ++slot) {
+            mbar_wait(&bar_act[slot], act_phase[slot]);
+            act_phase[slot] ^= 1;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            for (int ci = 0; ci < nch; ++ci) {
+              const uint32_t a_addr = smem_u32(smem) + kCSmemAct + slot * 4 * kActChunk + ci * kActChunk;
+              const uint32_t b_addr = smem_u32(smem) + kCSmemW + stage * kW256;
+              mbar_wait(&bar_full[stage], phase);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+                uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+              }
+              umma_commit(&bar_empty[stage]);
+              if (++stage == kCStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&bar_acc[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int slot = (warp - 4) >> 2;
+    const int r = tid - 128 - slot * 128;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t bar_id = 1 + slot;
+    uint8_t* act = smem + kCSmemAct + slot * 4 * kActChunk;
+    const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
+    uint32_t acc_phase = 0;
+
+    for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
+      const int64_t tile = 2 * it + slot;
+      const bool tile_valid = tile < p.n_tiles;
+      const int64_t g = tile * kTile + r;
+      const bool valid = tile_valid && g < p.n_points;
+      const uint8_t* stash_tile = p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes;
+      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
+
+      // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0]  -> A operand of step 0
+      float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r == 0) tma_store_wait_read0();
+      named_bar_sync(bar_id, 128);
+      {
+        const uint4 m4 = *reinterpret_cast<const uint4*>(masks + ((size_t)8 * 128 + r) * 8);
+        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          float v[32];
+          const uint32_t m = valid ? mw[c0 >> 5] : 0u;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + c0) + j4);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 128 + c0) + j4);
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 256 + c0) + j4);
+            v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+            v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+            v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+            v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+          uint8_t* img = act + (c0 >> 6) * kActChunk;
+          const int g0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
+                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(bar_id, 128);
+      if (r == 0) {
+        mbar_arrive(&bar_act[slot]);
+        if (tile_valid) {
+          for (int j = 0; j < 2; ++j)
+            tma_store_1d(dz_tile + (size_t)(kDzHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
+          tma_store_commit();
+        }
+      }
+
+      for (int s = 0; s < kCSteps; ++s) {
+        mbar_wait(&bar_acc[slot], acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (r == 0) tma_store_wait_read0();
+        named_bar_sync(bar_id, 128);
+        // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
+        uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        if (s >= 1) {
+          const uint4* mp = reinterpret_cast<const uint4*>(masks + ((size_t)(8 - s) * 128 + r) * 8);
+          const uint4 a = mp[0], b = mp[1];
+          mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
+        }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+          const int c0 = cb * 32;
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_base + slot * 256 + c0, acc);
+          tmem_ld_wait();
+          float v[32];
+          const uint32_t m = valid ? mw[cb] : 0u;
+          if (s == 1) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(small + kSmWAlpha + c0) + j4);
+              v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + dr.w * w.x;
+              v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + dr.w * w.y;
+              v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + dr.w * w.z;
+              v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + dr.w * w.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+          uint8_t* img = act + (c0 >> 6) * kActChunk;
+          const int g0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
+                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (r == 0) {
+          if (s < kCSteps - 1) mbar_arrive(&bar_act[slot]);
+          if (tile_valid) {
+            const int first = (s == 0) ? kDzFeat : kDzTrunk + 4 * (s - 1);
+            for (int j = 0; j < 4; ++j)
+              tma_store_1d(dz_tile + (size_t)(first + j) * kActChunk, act + j * kActChunk, kActChunk);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (r == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// 2. wgrad
+// =================================================================================================
+constexpr int kWThreads = 256;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 bias sums + drain
+constexpr int kWStages = 3;
+constexpr uint32_t kHalf = kActChunk / 2;                // 64 points of a chunk image
+constexpr uint32_t kWStageA = 0, kWStageB = 4 * kHalf;   // A: <=4 half chunks, B: <=5 half chunks
+constexpr uint32_t kWStageBytes = 9 * kHalf;             // 72 KB
+constexpr uint32_t kWSmemBytes = kWStages * kWStageBytes;  // 216 KB
+constexpr int kNumItems = 11;
+constexpr size_t kPartialSlotBytes = (size_t)256 * 320 * sizeof(float);
+constexpr int kMaxCtas = 160;
+
+struct WItem {
+  int a_chunk;      // first dZ-stash chunk of the M side
+  int m_blocks;     // 1 (128 output rows) or 2 (256)
+  int nb;           // number of 64-wide B chunks
+  int b_chunk[5];   // forward-stash chunk index of each
+  int dst;          // parameter index of the weight
+  int ld;           // its leading dimension
+  int col[5];       // destination column of each B chunk
+  int valid[5];     // valid columns of each B chunk
+  int bias;         // parameter index of the bias grad computed with this item, or -1
+  int cost;         // 8 KB units per 64-point stage
+};
+
+__constant__ WItem kItems[kNumItems] = {
+    // views_linears.0: d hidden_pre^T [feature | PE(viewdir)]
+    {kDzHidden, 1, 5, {33, 34, 35, 36, 37}, kPViewsW, 283, {0, 64, 128, 192, 256}, {64, 64, 64, 64, 27}, kPViewsB, 7},
+    // feature_linear: d feature^T h8
+    {kDzFeat, 2, 4, {29, 30, 31, 32, 0}, kPFeatW, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, kPFeatB, 8},
+    // pts_linears 7, 6
+    {kDzTrunk + 0, 2, 4, {25, 26, 27, 28, 0}, 14, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 15, 8},
+    {kDzTrunk + 4, 2, 4, {21, 22, 23, 24, 0}, 12, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 13, 8},
+    // pts_linears 5: h part (columns 63..318) and PE part (columns 0..62)
+    {kDzTrunk + 8, 2, 4, {17, 18, 19, 20, 0}, 10, 319, {63, 127, 191, 255, 0}, {64, 64, 64, 64, 0}, 11, 8},
+    {kDzTrunk + 8, 2, 1, {0, 0, 0, 0, 0}, 10, 319, {0, 0, 0, 0, 0}, {63, 0, 0, 0, 0}, -1, 5},
+    // pts_linears 4..1
+    {kDzTrunk + 12, 2, 4, {13, 14, 15, 16, 0}, 8, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 9, 8},
+    {kDzTrunk + 16, 2, 4, {9, 10, 11, 12, 0}, 6, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 7, 8},
+    {kDzTrunk + 20, 2, 4, {5, 6, 7, 8, 0}, 4, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 5, 8},
+    {kDzTrunk + 24, 2, 4, {1, 2, 3, 4, 0}, 2, 256, {0, 64, 128, 192, 0}, {64, 64, 64, 64, 0}, 3, 8},
+    // pts_linears 0: dZ_0^T PE
+    {kDzTrunk + 28, 2, 1, {0, 0, 0, 0, 0}, 0, 63, {0, 0, 0, 0, 0}, {63, 0, 0, 0, 0}, 1, 5},
+};
+constexpr int kRealItems = kNumItems;
+
+struct Segment {
+  int item;       // -1 = empty
+  int t0, t1;     // tile range
+  int pad;
+};
+
+struct WParams {
+  const uint8_t* stash;
+  const uint8_t* dz;
+  int64_t n_tiles;
+  float* partials;        // [grid][2] slots of kPartialSlotBytes
+  float* bias_partials;   // [grid][2][256]
+  Segment* segs;          // [grid][2]
+};
+
+// Cost-balanced static schedule: CTA b owns the cost range [b*C/G, (b+1)*C/G) of the concatenated
+// (item, tile) list; boundaries are snapped to tiles.  Returns up to 2 segments.
+__device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, Segment* out) {
+  int64_t total = 0;
+  for (int i = 0; i < kRealItems; ++i) total += (int64_t)kItems[i].cost * n_tiles;
+  const int64_t lo = total * b / G, hi = total * (b + 1) / G;
+  int n = 0;
+  int64_t base = 0;
+  for (int i = 0; i < kRealItems && n < 2; ++i) {
+    const int64_t c = kItems[i].cost;
+    const int64_t end = base + c * n_tiles;
+    // tiles of item i whose start cost lies in [lo, hi)
+    int64_t t0 = lo <= base ? 0 : (lo - base + c - 1) / c;
+    int64_t t1 = hi >= end ? n_tiles : (hi - base + c - 1) / c;
+    if (t0 < 0) t0 = 0;
+    if (t1 > n_tiles) t1 = n_tiles;
+    if (t1 > t0 && hi > base && lo < end) {
+      out[n].item = i; out[n].t0 = (int)t0; out[n].t1 = (int)t1; out[n].pad = 0;
+      ++n;
+    }
+    base = end;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[kWStages], bar_empty[kWStages], bar_acc, bar_drained;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ Segment seg_s[2];
+  __shared__ int nseg_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1 + 4); }
+    mbar_init(&bar_acc, 1);
+    mbar_init(&bar_drained, 4);
+    mbar_fence_init();
+    Segment sg[2];
+    sg[0].item = sg[1].item = -1; sg[0].t0 = sg[0].t1 = sg[1].t0 = sg[1].t1 = 0; sg[0].pad = sg[1].pad = 0;
+    nseg_s = schedule(blockIdx.x, gridDim.x, p.n_tiles, sg);
+    seg_s[0] = sg[0]; seg_s[1] = sg[1];
+    p.segs[blockIdx.x * 2 + 0] = sg[0];
+    p.segs[blockIdx.x * 2 + 1] = sg[1];
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nseg = nseg_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const WItem& itm = kItems[seg_s[sg].item];
+        const int na = 2 * itm.m_blocks;
+        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+          const uint8_t* dz_tile = p.dz + (size_t)t * kDzTileBytes;
+          const uint8_t* st_tile = p.stash + (size_t)t * kStashTileBytes;
+          for (int h = 0; h < 2; ++h) {
+            uint8_t* sbase = smem + stage * kWStageBytes;
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(na + itm.nb) * kHalf);
+            for (int j = 0; j < na; ++j)
+              tma_load_1d(sbase + kWStageA + j * kHalf, dz_tile + (size_t)(itm.a_chunk + j) * kActChunk + h * kHalf, kHalf,
+                          &bar_full[stage]);
+            for (int j = 0; j < itm.nb; ++j)
+              tma_load_1d(sbase + kWStageB + j * kHalf, st_tile + (size_t)itm.b_chunk[j] * kActChunk + h * kHalf, kHalf,
+                          &bar_full[stage]);
+            if (++stage == kWStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; uint32_t drained_phase = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const WItem& itm = kItems[seg_s[sg].item];
+        const int ntot = 64 * itm.nb;                        // accumulator columns per M block
+        const int n_main = itm.nb > 4 ? 256 : ntot;
+        const uint32_t idesc_main = umma_idesc_bf16(128, n_main, 1, 1);
+        const uint32_t idesc_tail = umma_idesc_bf16(128, 64, 1, 1);
+        if (sg > 0) {  // previous segment's accumulators must have been drained
+          mbar_wait(&bar_drained, drained_phase);
+          drained_phase ^= 1;
+          tc_fence_after();
+        }
+        bool first = true;
+        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sbase = smem_u32(smem) + stage * kWStageBytes;
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {                 // 16 points per MMA
+              for (int m = 0; m < itm.m_blocks; ++m) {
+                const uint64_t da = umma_desc_sw128(sbase + kWStageA + (2 * m) * kHalf + ks * 2048, kHalf, 1024);
+                const uint64_t db = umma_desc_sw128(sbase + kWStageB + ks * 2048, kHalf, 1024);
+                const uint32_t d = tmem_base + m * ntot;
+                const uint32_t accum = (first && ks == 0) ? 0u : 1u;
+                umma_bf16(d, da, db, idesc_main, accum);
+                if (itm.nb > 4) {
+                  const uint64_t db2 = umma_desc_sw128(sbase + kWStageB + 4 * kHalf + ks * 2048, kHalf, 1024);
+                  umma_bf16(d + 256, da, db2, idesc_tail, accum);
+                }
+              }
+            }
+            first = false;
+            umma_commit(&bar_empty[stage]);
+            if (++stage == kWStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&bar_acc);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== bias column sums + accumulator drain =====================
+    const int t4 = tid - 128;                 // 0..127
+    const int w4 = warp - 4;
+    const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
+    int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const WItem& itm = kItems[seg_s[sg].item];
+      const int ntot = 64 * itm.nb;
+      const bool do_bias = itm.bias >= 0 && (t4 < 64 * itm.m_blocks);
+      // thread t4 owns dZ features 2*t4, 2*t4+1: chunk t4/32, 16-byte group (t4%32)/4, word (t4%4)
+      const uint32_t boff = (uint32_t)(t4 >> 5) * kHalf;
+      const int bg = (t4 & 31) >> 2;
+      const uint32_t bw = (uint32_t)(t4 & 3) * 4;
+      float b0 = 0.f, b1 = 0.f;
+      for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&bar_full[stage], phase);
+          if (do_bias) {
+            const uint8_t* a = smem + stage * kWStageBytes + kWStageA + boff;
+#pragma unroll 8
+            for (int row = 0; row < 64; ++row) {
+              const uint32_t pr = *reinterpret_cast<const uint32_t*>(a + chunk_off16(row, bg) + bw);
+              b0 += __uint_as_float(pr << 16);
+              b1 += __uint_as_float(pr & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_empty[stage]);
+          if (++stage == kWStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      float* bias_out = p.bias_partials + ((size_t)blockIdx.x * 2 + sg) * 256;
+      if (do_bias) { bias_out[2 * t4] = b0; bias_out[2 * t4 + 1] = b1; }
+      // drain: TMEM lane i of M block m = output row 128 m + i; columns = input features
+      mbar_wait(&bar_acc, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      float* part = p.partials + ((size_t)blockIdx.x * 2 + sg) * (kPartialSlotBytes / sizeof(float));
+      for (int m = 0; m < itm.m_blocks; ++m) {
+        float* prow = part + (size_t)(128 * m + t4) * ntot;
+        for (int c0 = 0; c0 < ntot; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_base + m * ntot + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                                                    __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_drained);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// 3. alpha / rgb head grads on CUDA cores
+// =================================================================================================
+constexpr int kHeadFloats = 256 + 4 + 384 + 4;   // dW_alpha, db_alpha(+pad), dW_rgb, db_rgb(+pad)
+
+__global__ void __launch_bounds__(256) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
+                                                         int64_t n_points, int64_t n_tiles, float* __restrict__ out) {
+  __shared__ float4 dr[kTile];
+  const int j = threadIdx.x;  // feature column
+  float a_alpha = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
+  float s_alpha = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
+  const int64_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(n_tiles, t0 + per);
+  for (int64_t t = t0; t < t1; ++t) {
+    __syncthreads();
+    if (j < kTile) {
+      const int64_t g = t * kTile + j;
+      dr[j] = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const uint8_t* tile = stash + (size_t)t * kStashTileBytes;
+    const uint8_t* h8 = tile + (size_t)(kStashH + 28 + (j >> 6)) * kActChunk + (j & 7) * 2;
+    const uint8_t* hid = tile + (size_t)(kStashHidden + ((j & 127) >> 6)) * kActChunk + (j & 7) * 2;
+    const int gcol = (j & 63) >> 3;
+#pragma unroll 4
+    for (int row = 0; row < kTile; ++row) {
+      const float4 d = dr[row];
+      const float hv = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(h8 + chunk_off16(row, gcol))) << 16);
+      a_alpha += d.w * hv;
+      if (j < 128) {
+        const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(hid + chunk_off16(row, gcol))) << 16);
+        a_r += d.x * x; a_g += d.y * x; a_b += d.z * x;
+      }
+      if (j == 255) { s_alpha += d.w; s_r += d.x; s_g += d.y; s_b += d.z; }
+    }
+  }
+  float* o = out + (size_t)blockIdx.x * kHeadFloats;
+  o[j] = a_alpha;
+  if (j < 128) { o[260 + j] = a_r; o[260 + 128 + j] = a_g; o[260 + 256 + j] = a_b; }
+  if (j == 255) { o[256] = s_alpha; o[644] = s_r; o[645] = s_g; o[646] = s_b; }
+}
+
+// =================================================================================================
+// 4. deterministic reduction of all partials into the gradient tensors
+// =================================================================================================
+struct ReduceParams {
+  const float* partials;
+  const float* bias_partials;
+  const Segment* segs;
+  int w_grid;
+  const float* head_partials;
+  int head_grid;
+  GradPtrs grads;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
+  __shared__ int slots[2 * kMaxCtas];
+  __shared__ int nslots;
+  const int item = blockIdx.y;
+  if (item == kRealItems) {
+    // heads: alpha_linear / rgb_linear
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kHeadFloats; e += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int b = 0; b < p.head_grid; ++b) s += p.head_partials[(size_t)b * kHeadFloats + e];
+      float* dst = nullptr;
+      if (e < 256) dst = p.grads.p[kPAlphaW] + e;
+      else if (e == 256) dst = p.grads.p[kPAlphaB];
+      else if (e >= 260 && e < 644) dst = p.grads.p[kPRgbW] + (e - 260);
+      else if (e >= 644 && e < 647) dst = p.grads.p[kPRgbB] + (e - 644);
+      if (dst) *dst = p.accumulate ? *dst + s : s;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < 2 * p.w_grid; ++i)
+      if (p.segs[i].item == item && p.segs[i].t1 > p.segs[i].t0) slots[n++] = i;
+    nslots = n;
+  }
+  __syncthreads();
+  const WItem& itm = kItems[item];
+  const int rows = 128 * itm.m_blocks, ntot = 64 * itm.nb;
+  const size_t slot_floats = kPartialSlotBytes / sizeof(float);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * ntot; e += gridDim.x * blockDim.x) {
+    const int row = e / ntot, n = e % ntot;
+    const int j = n >> 6, w = n & 63;
+    if (w >= itm.valid[j]) continue;
+    float s = 0.f;
+    for (int k = 0; k < nslots; ++k) s += p.partials[(size_t)slots[k] * slot_floats + e];
+    float* dst = p.grads.p[itm.dst] + (size_t)row * itm.ld + itm.col[j] + w;
+    *dst = p.accumulate ? *dst + s : s;
+  }
+  if (itm.bias >= 0) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows; e += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < nslots; ++k) s += p.bias_partials[(size_t)slots[k] * 256 + e];
+      float* dst = p.grads.p[itm.bias] + e;
+      *dst = p.accumulate ? *dst + s : s;
+    }
+  }
+}
+
+// workspace carve-up (all offsets 1024-aligned)
+struct Workspace {
+  size_t dz, partials, bias, segs, heads, total;
+};
+Workspace carve(int64_t n_points) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
+  w.dz = take((size_t)num_tiles(n_points) * kDzTileBytes);
+  w.partials = take((size_t)kMaxCtas * 2 * kPartialSlotBytes);
+  w.bias = take((size_t)kMaxCtas * 2 * 256 * sizeof(float));
+  w.segs = take((size_t)kMaxCtas * 2 * sizeof(Segment));
+  w.heads = take((size_t)kMaxCtas * kHeadFloats * sizeof(float));
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
 extern "C" {
-size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return (size_t)mlp::num_tiles(n_points) * mlp::kDzTileBytes; }
-int mvip_mlp_backward(const void*, const float*, int64_t, const void*, void*, float* const*, int, void*) {
-  mvip_set_error("mvip_mlp_backward: not implemented yet");
-  return MVIP_E_UNSUPPORTED;
+
+size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_points).total; }
+
+int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, const void* stash, void* workspace,
+                      float* const* grads, int accumulate, void* stream) {
+  MVIP_REQUIRE(n_points >= 0, MVIP_E_INVALID, "mvip_mlp_backward: negative n_points");
+  MVIP_REQUIRE(grads, MVIP_E_INVALID, "mvip_mlp_backward: null grads");
+  GradPtrs gp;
+  for (int i = 0; i < MVIP_MLP_NUM_PARAMS; ++i) {
+    MVIP_REQUIRE(grads[i], MVIP_E_INVALID, "mvip_mlp_backward: grads[%d] is null", i);
+    gp.p[i] = grads[i];
+  }
+  if (n_points == 0) return MVIP_OK;  // nothing to add (caller zero-initialises when not accumulating)
+  MVIP_REQUIRE(packed && d_raw && stash && workspace, MVIP_E_INVALID, "mvip_mlp_backward: null pointer");
+  MVIP_REQUIRE(mvip_aligned(packed, 1024) && mvip_aligned(stash, 1024) && mvip_aligned(workspace, 1024) &&
+                   mvip_aligned(d_raw, 16),
+               MVIP_E_INVALID, "mvip_mlp_backward: packed/stash/workspace need 1024-byte and d_raw 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Workspace ws = carve(n_points);
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  const int64_t n_tiles = num_tiles(n_points);
+  const int sms = mvip_num_sms() < kMaxCtas ? mvip_num_sms() : kMaxCtas;
+
+  // 1. dgrad chain
+  {
+    ChainParams cp;
+    cp.packed = static_cast<const uint8_t*>(packed);
+    cp.d_raw = reinterpret_cast<const float4*>(d_raw);
+    cp.stash = static_cast<const uint8_t*>(stash);
+    cp.dz = wsb + ws.dz;
+    cp.n_points = n_points;
+    cp.n_tiles = n_tiles;
+    const int64_t n_pairs = (n_tiles + 1) / 2;
+    const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+    const size_t smem = kCSmemBytes + 1024;
+    MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
+    MVIP_LAUNCH_OK("dgrad_chain_kernel");
+  }
+  // 2. wgrad
+  const int w_grid = sms;
+  {
+    WParams wp;
+    wp.stash = static_cast<const uint8_t*>(stash);
+    wp.dz = wsb + ws.dz;
+    wp.n_tiles = n_tiles;
+    wp.partials = reinterpret_cast<float*>(wsb + ws.partials);
+    wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
+    wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
+    const size_t smem = kWSmemBytes + 1024;
+    MVIP_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_kernel<<<w_grid, kWThreads, smem, st>>>(wp);
+    MVIP_LAUNCH_OK("wgrad_kernel");
+  }
+  // 3. heads
+  const int head_grid = (int)(n_tiles < sms ? n_tiles : sms);
+  head_grads_kernel<<<head_grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_raw), static_cast<const uint8_t*>(stash),
+                                               n_points, n_tiles, reinterpret_cast<float*>(wsb + ws.heads));
+  MVIP_LAUNCH_OK("head_grads_kernel");
+  // 4. reduce
+  {
+    ReduceParams rp;
+    rp.partials = reinterpret_cast<const float*>(wsb + ws.partials);
+    rp.bias_partials = reinterpret_cast<const float*>(wsb + ws.bias);
+    rp.segs = reinterpret_cast<const Segment*>(wsb + ws.segs);
+    rp.w_grid = w_grid;
+    rp.head_partials = reinterpret_cast<const float*>(wsb + ws.heads);
+    rp.head_grid = head_grid;
+    rp.grads = gp;
+    rp.accumulate = accumulate;
+    reduce_kernel<<<dim3(32, kRealItems + 1), 256, 0, st>>>(rp);
+    MVIP_LAUNCH_OK("reduce_kernel");
+  }
+  return MVIP_OK;
 }
-}
+
+}  // extern "C"

@@ -353,6 +353,8 @@ extern "C" {
 size_t mvip_mlp_stash_bytes(int64_t n_points) { return (size_t)mlp::num_tiles(n_points) * mlp::kStashTileBytes; }
 
 int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, void* stash, void* stream) {
+  MVIP_REQUIRE(pts, MVIP_E_INVALID, "mvip_mlp_forward: null mvip_points");
+  if (pts->n_points == 0) return MVIP_OK;
   MVIP_REQUIRE(packed && raw, MVIP_E_INVALID, "mvip_mlp_forward: null pointer");
   int rc = check_points("mvip_mlp_forward", pts);
   if (rc) return rc;

@@ -279,10 +279,10 @@ extern "C" {
 
 int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const float* t_vals, const float* t_rand,
                        int n_samples, int lindisp, float* z_out, void* stream) {
-  MVIP_REQUIRE(rays && t_vals && z_out, MVIP_E_INVALID, "mvip_sample_coarse: null pointer");
   MVIP_REQUIRE(ray_stride >= 8 && n_samples >= 1 && n_rays >= 0, MVIP_E_INVALID,
                "mvip_sample_coarse: bad shape (ray_stride=%d n_samples=%d)", ray_stride, n_samples);
-  if (n_rays == 0) return MVIP_OK;
+  if (n_rays == 0) return MVIP_OK;  // empty batch: nothing to do (pointers may be null)
+  MVIP_REQUIRE(rays && t_vals && z_out, MVIP_E_INVALID, "mvip_sample_coarse: null pointer");
   int64_t total = n_rays * n_samples;
   int threads = 256;
   int64_t blocks = (total + threads - 1) / threads;
@@ -295,8 +295,8 @@ int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const 
 
 int mvip_sample_pdf(const float* bins, const float* weights, const float* u, int u_is_row, int64_t n_rows, int n_bins,
                     int n_out, float* samples, int64_t* inds, float* cdf, void* stream) {
-  MVIP_REQUIRE(bins && weights && u && samples, MVIP_E_INVALID, "mvip_sample_pdf: null pointer");
   MVIP_REQUIRE(n_rows >= 0 && n_out >= 1, MVIP_E_INVALID, "mvip_sample_pdf: bad shape");
+  MVIP_REQUIRE(n_rows == 0 || (bins && weights && u && samples), MVIP_E_INVALID, "mvip_sample_pdf: null pointer");
   MVIP_REQUIRE(n_bins - 1 >= 8 && n_bins <= kMaxBins && n_out <= kMaxOut, MVIP_E_UNSUPPORTED,
                "mvip_sample_pdf: need 9 <= n_bins <= %d and n_out <= %d (got %d, %d); torch's CPU sum order is only "
                "reproduced for that range", kMaxBins, kMaxOut, n_bins, n_out);
@@ -311,8 +311,8 @@ int mvip_sample_pdf(const float* bins, const float* weights, const float* u, int
 int mvip_sample_fine(const float* z_vals, const float* weights, const float* u, int u_is_row, int64_t n_rays,
                      int n_samples, int n_out, float* z_samples, int64_t* inds, float* z_merged, float* z_std,
                      void* stream) {
-  MVIP_REQUIRE(z_vals && weights && u && z_merged, MVIP_E_INVALID, "mvip_sample_fine: null pointer");
   MVIP_REQUIRE(n_rays >= 0 && n_out >= 1, MVIP_E_INVALID, "mvip_sample_fine: bad shape");
+  MVIP_REQUIRE(n_rays == 0 || (z_vals && weights && u && z_merged), MVIP_E_INVALID, "mvip_sample_fine: null pointer");
   MVIP_REQUIRE(n_samples - 2 >= 8 && n_samples - 1 <= kMaxBins && n_out <= kMaxOut, MVIP_E_UNSUPPORTED,
                "mvip_sample_fine: need 10 <= n_samples <= %d and n_out <= %d (got %d, %d)", kMaxBins + 1, kMaxOut,
                n_samples, n_out);

@@ -35,7 +35,7 @@ def test_sizes_and_errors_without_gpu():
     assert lib.mvip_mlp_stash_bytes(129) == 2 * (40 * 16384 + 9 * 128 * 32)
     assert lib.mvip_normal_workspace_bytes(4, 5) == 2 * 9 * 20 * 8
     # argument validation happens before any CUDA call
-    rc = lib.mvip_sample_coarse(None, 11, 4, None, None, 64, 1, None, None)
+    rc = lib.mvip_sample_coarse(None, 11, 4, None, None, 64, 1, None, None)   # n_rays=4 with null buffers
     assert rc == -1 and b"null" in lib.mvip_last_error()
 
 

@@ -125,7 +125,7 @@ def test_composite_backward_vs_reference_autograd(ops, golden, S, white, use_noi
     assert np.abs(got[ok] - ref[ok]).max() <= 2e-5 * np.abs(ref[ok]).max()
 
 
-@pytest.mark.parametrize("S", [1, 7, 33, 48, 200])
+@pytest.mark.parametrize("S", [2, 7, 33, 48, 200])
 def test_composite_ragged_sample_counts_vs_oracle(ops, S):
     rng = np.random.RandomState(S)
     N = 37

@@ -103,3 +103,73 @@ def test_mlp_forward_is_deterministic_and_tile_independent(ops):
     sub = rng.permutation(P)[:2048]
     want = orc.nerf_forward(p, np.concatenate([orc.embed(pts[sub], 10), orc.embed(vd[sub], 4)], -1))
     assert np.abs(a.cpu().numpy()[sub] - want).max() < RAW_ATOL
+
+
+# bf16 activations and bf16 dZ feed the weight-gradient GEMMs (fp32 accumulate): stated tolerance on every
+# parameter gradient = 2% of that tensor's max-abs entry (random-init network).
+GRAD_RTOL = 2e-2
+
+
+def _check_grads(ops, got, want_by_name, P):
+    worst = 0.0
+    for g, name in zip(got, ops.PARAM_ORDER):
+        ref = want_by_name[name]
+        err = float(np.abs(g.cpu().numpy() - ref).max()) / max(float(np.abs(ref).max()), 1e-12)
+        worst = max(worst, err)
+        assert err < GRAD_RTOL, (name, err, P)
+    return worst
+
+
+def test_mlp_backward_vs_reference_autograd(ops, golden):
+    fx = golden("nerf_mlp")
+    p = orc.init_params(int(fx["param_seed"]))
+    blob = pack(ops, p)
+    emb = cu(fx["embedded"])
+    raw, stash = ops.mlp_forward(blob, pts=emb[:, 0:3], dirs=emb[:, 63:66], want_stash=True)
+    grads = ops.mlp_backward(blob, cu(fx["d_out"]), stash)
+    _check_grads(ops, grads, {n: fx["grad." + n] for n in ops.PARAM_ORDER}, emb.shape[0])
+    # accumulate=True adds on top
+    grads2 = ops.mlp_backward(blob, cu(fx["d_out"]), stash, grads=[g.clone() for g in grads], accumulate=True)
+    for a, b in zip(grads, grads2):
+        torch.testing.assert_close(b, 2 * a, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("P", [1, 129, 1000, 20000])
+def test_mlp_backward_ragged_sizes_vs_oracle(ops, P):
+    rng = np.random.RandomState(100 + P)
+    p = orc.init_params(21)
+    pts = ((rng.rand(P, 3) * 2 - 1) * 5).astype(np.float32)
+    vd = rng.randn(P, 3).astype(np.float32)
+    vd /= np.linalg.norm(vd, axis=-1, keepdims=True)
+    d_out = rng.randn(P, 4).astype(np.float32)
+    x = np.concatenate([orc.embed(pts, 10), orc.embed(vd, 4)], -1)
+    _, saved = orc.nerf_forward(p, x, keep=True, dtype=np.float64)
+    want = orc.nerf_backward(p, saved, d_out, dtype=np.float64)
+    want = {k.replace(".weight", ".weight").replace(".bias", ".bias"): v for k, v in want.items()}
+    blob = pack(ops, p)
+    raw, stash = ops.mlp_forward(blob, pts=cu(pts), dirs=cu(vd), want_stash=True)
+    grads = ops.mlp_backward(blob, cu(d_out), stash)
+    _check_grads(ops, grads, want, P)
+
+
+def test_mlp_backward_is_linear_and_deterministic_at_full_size(ops):
+    # cfg-2 coarse-pass size (4096 rays x 64): grads are linear in d_raw and bitwise reproducible
+    rng = np.random.RandomState(3)
+    P = 4096 * 64
+    p = orc.init_params(22)
+    blob = pack(ops, p)
+    pts = cu(((rng.rand(P, 3) * 2 - 1) * 4).astype(np.float32))
+    vd = cu(rng.randn(P, 3).astype(np.float32))
+    d1 = cu(rng.randn(P, 4).astype(np.float32))
+    raw, stash = ops.mlp_forward(blob, pts=pts, dirs=vd, want_stash=True)
+    g1 = ops.mlp_backward(blob, d1, stash)
+    g1b = ops.mlp_backward(blob, d1, stash)
+    for a, b in zip(g1, g1b):
+        assert torch.equal(a, b)
+    g2 = ops.mlp_backward(blob, 2 * d1, stash)
+    for a, b, name in zip(g1, g2, ops.PARAM_ORDER):
+        scale = float(a.abs().max())
+        assert float((b - 2 * a).abs().max()) <= 2e-2 * scale, name     # bf16 rounding of dZ is not exactly linear
+    # bias grad of rgb_linear is exactly the column sum of d_raw[:, :3]
+    torch.testing.assert_close(g1[23], d1[:, :3].sum(0), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(g1[21], d1[:, 3:].sum(0), rtol=1e-4, atol=1e-2)
