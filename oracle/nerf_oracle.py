@@ -467,3 +467,72 @@ def make_ray_batch(rays_o, rays_d, near, far):
     n = np.full_like(rays_d[:, :1], near)
     f = np.full_like(rays_d[:, :1], far)
     return np.concatenate([rays_o, rays_d, n, f, viewdirs], -1).astype(f32)
+
+
+# --------------------------------------------------------------------------------------
+# Model of the CUDA path's mixed precision (bf16 tensor-core operands, fp32/fp64 accumulate).
+# Not a restatement of the reference: it answers "is the kernel computing what it is specified
+# to compute" separately from "how far is bf16 from the reference's fp32" (ReLU-mask flips of
+# ~0.5% of units dominate the latter for gradients).
+# --------------------------------------------------------------------------------------
+def bf16_round(x):
+    """round-to-nearest-even float32 -> bfloat16 -> float64 (numpy bit arithmetic)."""
+    a = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    a = (a + 0x7FFF + ((a >> 16) & 1)) & 0xFFFF0000
+    return a.astype(np.uint32).view(np.float32).reshape(np.shape(x)).astype(np.float64)
+
+
+def nerf_forward_backward_bf16sim(p, pts, viewdirs, d_out=None, multires=10, multires_views=4):
+    """Forward (and, with d_out, backward) of the NeRF MLP with every tensor-core operand rounded to
+    bf16 exactly where the kernels round: MMA weights, PE inputs, each layer's activation, each dZ.
+    The alpha / rgb heads run on fp32 activations with fp32 weights, as in mlp_forward.cu."""
+    W = {k: (bf16_round(v) if (k.endswith("weight") and not k.startswith(("alpha", "rgb"))) else v.astype(np.float64))
+         for k, v in p.items()}
+    pe = bf16_round(embed(pts, multires))
+    vpe = bf16_round(embed(viewdirs, multires_views))
+    h = pe
+    ins, pre = [], []
+    h8_f = None
+    for i in range(8):
+        ins.append(h)
+        z = h @ W["pts_linears.%d.weight" % i].T + W["pts_linears.%d.bias" % i]
+        pre.append(z)
+        hf = np.maximum(z, 0)
+        h = bf16_round(hf)
+        if i == 7:
+            h8_f = hf
+        if i == 4:
+            h = np.concatenate([pe, h], -1)
+    h8 = h
+    alpha = h8_f @ W["alpha_linear.weight"].T + W["alpha_linear.bias"]
+    feat = bf16_round(h8 @ W["feature_linear.weight"].T + W["feature_linear.bias"])
+    hv_in = np.concatenate([feat, vpe], -1)
+    pre_v = hv_in @ W["views_linears.0.weight"].T + W["views_linears.0.bias"]
+    hv_f = np.maximum(pre_v, 0)
+    rgb = hv_f @ W["rgb_linear.weight"].T + W["rgb_linear.bias"]
+    out = np.concatenate([rgb, alpha], -1)
+    if d_out is None:
+        return out
+    g = {}
+    d_out = np.asarray(d_out, dtype=np.float64)
+    d_rgb, d_alpha = d_out[:, :3], d_out[:, 3:4]
+    hv = bf16_round(hv_f)
+    g["rgb_linear.weight"] = d_rgb.T @ hv
+    g["rgb_linear.bias"] = d_rgb.sum(0)
+    g["alpha_linear.weight"] = d_alpha.T @ h8
+    g["alpha_linear.bias"] = d_alpha.sum(0)
+    d_pre_v = bf16_round((d_rgb @ W["rgb_linear.weight"]) * (pre_v > 0))
+    g["views_linears.0.weight"] = d_pre_v.T @ hv_in
+    g["views_linears.0.bias"] = d_pre_v.sum(0)
+    d_feat = bf16_round((d_pre_v @ W["views_linears.0.weight"])[:, :256])
+    g["feature_linear.weight"] = d_feat.T @ h8
+    g["feature_linear.bias"] = d_feat.sum(0)
+    d_h = d_feat @ W["feature_linear.weight"] + d_alpha @ W["alpha_linear.weight"]
+    for i in reversed(range(8)):
+        if i == 4:
+            d_h = d_h[:, 63:]
+        d_pre = bf16_round(d_h * (pre[i] > 0))
+        g["pts_linears.%d.weight" % i] = d_pre.T @ ins[i]
+        g["pts_linears.%d.bias" % i] = d_pre.sum(0)
+        d_h = d_pre @ W["pts_linears.%d.weight" % i]
+    return out, g
