@@ -105,6 +105,19 @@ int mvip_normal_forward(const float* depth, int H, int W, float fx, float fy, fl
 int mvip_normal_backward(const float* depth, int H, int W, float fx, float fy, float cx, float cy,
                          int k, const float* g_normal, float* d_depth, void* workspace, void* stream);
 
+/* Same least-squares normal on an arbitrary point map xyz [3,H,W] (the argument depth2normal_geo takes in the
+ * reference, run.py:1924); backward returns d_xyz [3,H,W]. */
+int mvip_normal_forward_xyz(const float* xyz, int H, int W, int k, float* normal, void* workspace, void* stream);
+int mvip_normal_backward_xyz(const float* xyz, int H, int W, int k, const float* g_normal, float* d_xyz,
+                             void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone positional encoding.           replaces DS_NeRF/run_nerf_helpers.py:22-52 (Embedder.embed)
+ *   in [n, >=dims] with row stride in_stride -> out [n, dims*(1+2*num_freqs)]:
+ *   [x, sin(x*2^0), cos(x*2^0), ..., sin(x*2^(L-1)), cos(x*2^(L-1))]  (log-sampled bands, include_input)
+ */
+int mvip_embed(const float* in, int64_t in_stride, int64_t n, int dims, int num_freqs, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused positional encoding + 8x256 NeRF MLP (use_viewdirs, skip at 4).
  *   replaces DS_NeRF/run.py:1108-1124 (run_network), run_nerf_helpers.py:22-52 (Embedder.embed) and

@@ -14,10 +14,17 @@ namespace {
 
 struct Cam {
   float fx, fy, cx, cy;
+  const float* xyz;   // non-null: take (x,y,z) from three [H,W] planes instead of back-projecting the depth
+  size_t plane;
 };
 
 __device__ __forceinline__ void xyz_of(const float* __restrict__ depth, int W, int h, int w, const Cam& c, float& x,
                                        float& y, float& z) {
+  if (c.xyz) {
+    const size_t o = (size_t)h * W + w;
+    x = __ldg(c.xyz + o); y = __ldg(c.xyz + c.plane + o); z = __ldg(c.xyz + 2 * c.plane + o);
+    return;
+  }
   z = __ldg(depth + (size_t)h * W + w);
   x = __fdiv_rn(__fmul_rn((float)w - c.cx, z), c.fx);  // (w-cx)*z/fx   run.py:1918
   y = __fdiv_rn(__fmul_rn((float)h - c.cy, z), c.fy);  // (h-cy)*z/fy   run.py:1919
@@ -135,6 +142,11 @@ __global__ void normal_ddepth_kernel(const double* __restrict__ ws, const float*
   double dax = m[6] - (m[0] * x + m[1] * y + m[2] * z);
   double day = m[7] - (m[1] * x + m[3] * y + m[4] * z);
   double daz = m[8] - (m[2] * x + m[4] * y + m[5] * z);
+  if (cam.xyz) {  // gradient w.r.t. the xyz planes themselves
+    const size_t plane = (size_t)H * W, o = (size_t)h * W + w;
+    d_depth[o] = (float)dax; d_depth[plane + o] = (float)day; d_depth[2 * plane + o] = (float)daz;
+    return;
+  }
   double g = dax * ((double)w - cam.cx) / cam.fx + day * ((double)h - cam.cy) / cam.fy + daz;
   d_depth[(size_t)h * W + w] = (float)g;
 }
@@ -153,11 +165,42 @@ extern "C" {
 
 size_t mvip_normal_workspace_bytes(int H, int W) { return (size_t)2 * 9 * (size_t)H * (size_t)W * sizeof(double); }
 
+int mvip_normal_forward_xyz(const float* xyz, int H, int W, int k, float* normal, void* workspace, void* stream) {
+  int rc = check_args("mvip_normal_forward_xyz", xyz, H, W, k, normal, workspace);
+  if (rc) return rc;
+  Cam cam{1.f, 1.f, 0.f, 0.f, xyz, (size_t)H * W};
+  dim3 block(128), grid((W + 127) / 128, H);
+  double* ws = static_cast<double*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  moments_h_kernel<<<grid, block, 0, st>>>(xyz, H, W, cam, k / 2, ws);
+  normal_solve_kernel<<<grid, block, 0, st>>>(ws, H, W, k / 2, normal);
+  MVIP_LAUNCH_OK("normal_forward_xyz kernels");
+  return MVIP_OK;
+}
+
+int mvip_normal_backward_xyz(const float* xyz, int H, int W, int k, const float* g_normal, float* d_xyz, void* workspace,
+                             void* stream) {
+  int rc = check_args("mvip_normal_backward_xyz", xyz, H, W, k, d_xyz, workspace);
+  if (rc) return rc;
+  MVIP_REQUIRE(g_normal, MVIP_E_INVALID, "mvip_normal_backward_xyz: null g_normal");
+  Cam cam{1.f, 1.f, 0.f, 0.f, xyz, (size_t)H * W};
+  dim3 block(128), grid((W + 127) / 128, H);
+  double* ws0 = static_cast<double*>(workspace);
+  double* ws1 = ws0 + (size_t)9 * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  moments_h_kernel<<<grid, block, 0, st>>>(xyz, H, W, cam, k / 2, ws0);
+  normal_adjoint_kernel<<<grid, block, 0, st>>>(ws0, g_normal, H, W, k / 2, ws1);
+  box_h_kernel<<<grid, block, 0, st>>>(ws1, H, W, k / 2, ws0);
+  normal_ddepth_kernel<<<grid, block, 0, st>>>(ws0, xyz, H, W, cam, k / 2, d_xyz);
+  MVIP_LAUNCH_OK("normal_backward_xyz kernels");
+  return MVIP_OK;
+}
+
 int mvip_normal_forward(const float* depth, int H, int W, float fx, float fy, float cx, float cy, int k, float* normal,
                         void* workspace, void* stream) {
   int rc = check_args("mvip_normal_forward", depth, H, W, k, normal, workspace);
   if (rc) return rc;
-  Cam cam{fx, fy, cx, cy};
+  Cam cam{fx, fy, cx, cy, nullptr, 0};
   dim3 block(128), grid((W + 127) / 128, H);
   double* ws = static_cast<double*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
@@ -172,7 +215,7 @@ int mvip_normal_backward(const float* depth, int H, int W, float fx, float fy, f
   int rc = check_args("mvip_normal_backward", depth, H, W, k, d_depth, workspace);
   if (rc) return rc;
   MVIP_REQUIRE(g_normal, MVIP_E_INVALID, "mvip_normal_backward: null g_normal");
-  Cam cam{fx, fy, cx, cy};
+  Cam cam{fx, fy, cx, cy, nullptr, 0};
   dim3 block(128), grid((W + 127) / 128, H);
   double* ws0 = static_cast<double*>(workspace);
   double* ws1 = ws0 + (size_t)9 * H * W;

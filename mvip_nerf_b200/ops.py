@@ -18,7 +18,7 @@ PARAM_SHAPES = ([(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (2
 # kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_count = 0
 _LAUNCHES = {"mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
-             "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4,
+             "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
              "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
 
 
@@ -159,6 +159,43 @@ def normal_backward(depth, fx, fy, cx, cy, g_normal, k=31):
     _call("mvip_normal_backward", _ptr(depth), H, W, float(fx), float(fy), float(cx), float(cy), int(k), _ptr(g_normal),
           _ptr(d_depth), _ptr(ws), _stream())
     return d_depth
+
+
+def normal_forward_xyz(xyz, k=31):
+    """xyz [3,H,W] -> normal [3,H,W]   (depth2normal_geo, run.py:1924-1940)"""
+    xyz = _f32(xyz, "xyz")
+    _, H, W = xyz.shape
+    normal = torch.empty((3, H, W), device=xyz.device, dtype=torch.float32)
+    ws = _normal_ws(H, W, xyz.device)
+    _call("mvip_normal_forward_xyz", _ptr(xyz), H, W, int(k), _ptr(normal), _ptr(ws), _stream())
+    return normal
+
+
+def normal_backward_xyz(xyz, g_normal, k=31):
+    xyz = _f32(xyz, "xyz")
+    g_normal = _f32(g_normal, "g_normal")
+    _, H, W = xyz.shape
+    d_xyz = torch.empty((3, H, W), device=xyz.device, dtype=torch.float32)
+    ws = _normal_ws(H, W, xyz.device)
+    _call("mvip_normal_backward_xyz", _ptr(xyz), H, W, int(k), _ptr(g_normal), _ptr(d_xyz), _ptr(ws), _stream())
+    return d_xyz
+
+
+# ---------------------------------------------------------------------------------------------- embedding
+def embed(x, num_freqs):
+    """x [..., D] -> [..., D*(1+2L)]   (Embedder.embed, run_nerf_helpers.py:51-52)"""
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor: mvip_nerf_b200 has no CPU fallback")
+    D = x.shape[-1]
+    flat = x.reshape(-1, D)
+    if flat.dtype != torch.float32:
+        flat = flat.float()
+    if flat.stride(-1) != 1:
+        flat = flat.contiguous()
+    n = flat.shape[0]
+    out = torch.empty((n, D * (1 + 2 * num_freqs)), device=x.device, dtype=torch.float32)
+    _call("mvip_embed", _ptr(flat), flat.stride(0) if n > 0 else D, n, D, int(num_freqs), _ptr(out), _stream())
+    return out.reshape(*x.shape[:-1], out.shape[-1])
 
 
 # ---------------------------------------------------------------------------------------------- MLP

@@ -1,0 +1,66 @@
+"""CPU suite: world_size-2 gloo tests of the N>1 host logic (sharding, gather, gradient allreduce)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from mvip_nerf_b200 import dist as md
+    r, w, _ = md.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # --- ray sharding + single gather: rank-local "render" = a pure per-ray function
+    rays = torch.arange(n * 11, dtype=torch.float32).reshape(n, 11)
+
+    def fake_render(rows):
+        return {"rgb_map": rows[:, 0:3] * 2, "disp_map": rows[:, 3], "acc_map": rows[:, 4] + 1, "depth_map": rows[:, 5]}
+    out = md.render_sharded(fake_render, rays)
+    if rank == 0:
+        want = fake_render(rays)
+        for k in want:
+            assert torch.equal(out[k], want[k]), k
+    else:
+        assert out is None
+    lo, hi = md.shard_bounds(n)
+    assert hi - lo in (n // world, n // world + 1)
+    # --- gradient allreduce: each rank holds the gradient of its shard; the sum equals the full-batch gradient
+    torch.manual_seed(0)
+    lin_a, lin_b = torch.nn.Linear(11, 4), torch.nn.Linear(11, 2)
+    full = (lin_a(rays) ** 2).sum() / n + (lin_b(rays) ** 2).sum() / n
+    ga_full = torch.autograd.grad(full, list(lin_a.parameters()) + list(lin_b.parameters()))
+    mine = md.shard_rows(rays)
+    loss = (lin_a(mine) ** 2).sum() / n + (lin_b(mine) ** 2).sum() / n      # scaled by the GLOBAL count
+    loss.backward()
+    md.allreduce_grads([list(lin_a.parameters()), list(lin_b.parameters())])
+    for p, g in zip(list(lin_a.parameters()) + list(lin_b.parameters()), ga_full):
+        torch.testing.assert_close(p.grad, g, rtol=1e-5, atol=1e-5)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7])
+def test_world2_gloo_shard_gather_allreduce(n):
+    mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+def test_shard_bounds_cover_everything():
+    from mvip_nerf_b200 import dist as md
+    for n in (0, 1, 7, 8, 762048, 65536):
+        for w in (1, 2, 4, 8):
+            b = [md.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,210 @@
+"""GPU suite: the drop-in API (mvip_nerf_b200.run / run_nerf_helpers) against the reference's own render()
+outputs (tests/golden/render_e2e.npz, produced by oracle/make_golden.py) and against the oracle."""
+import argparse
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# stated tolerances for the bf16 tensor-core MLP on the random-init network
+RGB_ATOL = 2e-3
+DISP_ATOL = 5e-3
+DEPTH_RTOL = 1e-2
+ACC_ATOL = 1e-3
+
+
+def nerf_args(basedir, expname="exp", **over):
+    a = dict(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=64, N_samples=64,
+             netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, alpha_model_path=None,
+             no_coarse=False, lrate=5e-4, basedir=basedir, expname=expname, ft_path=None, no_reload=True, perturb=1.0,
+             white_bkgd=True, raw_noise_std=1.0, dataset_type="llff", no_ndc=True, lindisp=True, sigma_loss=False)
+    a.update(over)
+    return argparse.Namespace(**a)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def load_seeded(net, seed):
+    p = orc.init_params(seed)
+    sd = net.state_dict()
+    net.load_state_dict({k: torch.from_numpy(p[k.replace("module.", "")]) for k in sd})
+
+
+@pytest.fixture(scope="module")
+def nerf(golden):
+    from mvip_nerf_b200 import run
+    fx = golden("render_e2e")
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "exp"))
+        kw_train, kw_test, start, grad_vars, opt = run.create_nerf(nerf_args(td))
+    load_seeded(kw_train["network_fn"], int(fx["coarse_seed"]))
+    load_seeded(kw_train["network_fine"], int(fx["fine_seed"]))
+    return run, kw_train, kw_test, grad_vars, opt, fx
+
+
+def test_create_nerf_contract(nerf):
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    assert set(kw_train) == {"network_query_fn", "perturb", "N_importance", "network_fine", "N_samples", "network_fn",
+                             "use_viewdirs", "white_bkgd", "raw_noise_std", "ndc", "lindisp"}
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0.
+    assert sum(p.numel() for p in grad_vars) == 2 * 595844
+    keys = list(kw_train["network_fn"].state_dict())
+    assert keys[0] == "module.pts_linears.0.weight" and len(keys) == 24       # reference checkpoint key names
+    assert isinstance(opt, torch.optim.Adam)
+
+
+def test_render_test_kwargs_vs_reference(nerf):
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    rays = torch.stack([cu(fx["rays_o"]), cu(fx["rays_d"])], 0)
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=float(fx["near"]),
+                                                   far=float(fx["far"]), retraw=True, need_alpha=True, **kw_test)
+    assert rgb.shape == (64, 3) and extras["raw"].shape == (64, 128, 4) and extras["weights"].shape == (64, 128)
+    assert set(extras) == {"weights", "z_vals", "raw", "alpha", "alpha0", "rgb0", "disp0", "acc0", "z_std"}
+    np.testing.assert_allclose(extras["rgb0"].cpu().numpy(), fx["test_rgb0"], atol=RGB_ATOL)
+    np.testing.assert_allclose(rgb.cpu().numpy(), fx["test_rgb"], atol=RGB_ATOL)
+    np.testing.assert_allclose(acc.cpu().numpy(), fx["test_acc"], atol=ACC_ATOL)
+    np.testing.assert_allclose(disp.cpu().numpy(), fx["test_disp"], atol=DISP_ATOL)
+    np.testing.assert_allclose(depth.cpu().numpy(), fx["test_depth"], rtol=DEPTH_RTOL)
+    # the coarse half of the merged z_vals is bit-exact; fine samples follow the (bf16) coarse weights
+    z = extras["z_vals"].cpu().numpy()
+    assert np.all(np.diff(z, axis=-1) >= 0)
+    assert np.isclose(z, fx["test_z_vals"], atol=0.05).mean() > 0.98
+
+
+def test_render_train_kwargs_and_grads_vs_reference(nerf):
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    from mvip_nerf_b200.run_nerf_helpers import img2mse
+    rays = torch.stack([cu(fx["rays_o"]), cu(fx["rays_d"])], 0)
+    for v in grad_vars:
+        v.grad = None
+    rgb, disp, acc, depth, extras = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=float(fx["near"]),
+                                               far=float(fx["far"]), retraw=True, pytest=True, **kw_train)
+    np.testing.assert_allclose(extras["rgb0"].detach().cpu().numpy(), fx["train_rgb0"], atol=RGB_ATOL)
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), fx["train_rgb"], atol=RGB_ATOL)
+    np.testing.assert_allclose(disp.detach().cpu().numpy(), fx["train_disp"], atol=DISP_ATOL)
+    loss = img2mse(rgb, torch.full_like(rgb, 0.5)) + img2mse(extras["rgb0"], torch.full_like(rgb, 0.5)) + \
+        0.1 * img2mse(disp, torch.full_like(disp, 0.3))
+    assert abs(loss.item() - float(fx["train_loss"])) < 2e-3 * max(1.0, abs(float(fx["train_loss"])))
+    loss.backward()
+    # parameter gradients of a real loss vs the reference's autograd (64 rays): cosine >= 0.99 per tensor,
+    # max-abs error <= 25% of the tensor's max-abs entry (bf16 ReLU-mask flips; same stated tolerance as
+    # tests/test_gpu_mlp.py, where the kernels themselves are checked to 5e-3 teacher-forced)
+    for nm in ("coarse", "fine"):
+        net = kw_train["network_fn" if nm == "coarse" else "network_fine"]
+        for k, p in net.named_parameters():
+            ref = fx["train_grad.%s.%s" % (nm, k.replace("module.", ""))]
+            g = p.grad.cpu().numpy()
+            if g.ndim == 2 and g.shape[0] == 256 and g.shape[1] >= 256:
+                g = g[::8]
+            scale = np.abs(ref).max()
+            assert np.abs(g - ref).max() <= 0.25 * scale, (nm, k)
+            if g.size > 8:
+                cos = (g * ref).sum() / np.sqrt((g * g).sum() * (ref * ref).sum())
+                assert cos > 0.99, (nm, k, cos)
+
+
+def test_render_c2w_path_chunking_and_shapes(nerf):
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    c2w = torch.eye(4, device="cuda")[:3, :4]
+    H, W, focal = 24, 32, 30.0
+    with torch.no_grad():
+        a = run.render(H, W, focal, chunk=32768, c2w=c2w, near=1.2, far=7.7, **kw_test)
+        b = run.render(H, W, focal, chunk=200, c2w=c2w, near=1.2, far=7.7, **kw_test)       # ragged chunks
+    assert a[0].shape == (H, W, 3) and a[1].shape == (H, W) and a[4]["weights"].shape == (H, W, 128)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)            # "chunk ... does not affect final results" (run.py:1153)
+    # patch = sub-rectangle of the same rays
+    with torch.no_grad():
+        p = run.render(H, W, focal, chunk=32768, c2w=c2w, near=1.2, far=7.7, patch=(3, 5, 7, 9), **kw_test)
+    assert torch.equal(p[0], a[0][3:10, 5:14])
+
+
+def test_helpers_api(nerf):
+    from mvip_nerf_b200 import run_nerf_helpers as h
+    embed, dim = h.get_embedder(10, 0)
+    assert dim == 63
+    x = torch.randn(100, 3, device="cuda") * 3
+    e = embed(x)
+    want = orc.embed(x.cpu().numpy(), 10)
+    np.testing.assert_allclose(e.cpu().numpy(), want, atol=2e-6)
+    ident, d3 = h.get_embedder(10, -1)
+    assert d3 == 3 and isinstance(ident, torch.nn.Identity)
+    with pytest.raises(NotImplementedError):
+        h.NeRF(D=4, W=128, input_ch=63, input_ch_views=27, use_viewdirs=True)
+    # sample_pdf through the drop-in signature (det=True draws torch.linspace like the reference)
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "sample_pdf.npz"))
+    s = h.sample_pdf(cu(fx["bins"]), cu(fx["w_peaky"]), 64, det=True)
+    assert np.array_equal(s.cpu().numpy(), fx["samples_peaky_det"])
+    s, inds = h.sample_pdf(cu(fx["bins"]), cu(fx["w_peaky"]), 64, det=False, pytest=True, return_inds=True)
+    assert np.array_equal(s.cpu().numpy(), fx["samples_peaky_rand"])
+    assert np.array_equal(inds.cpu().numpy(), fx["inds_peaky_rand"])
+
+
+def test_raw2outputs_autograd_matches_reference(golden):
+    from mvip_nerf_b200 import run_nerf_helpers as h
+    fx = golden("raw2outputs")
+    tag = "S64_w1_n0"
+    raw = cu(fx["S64_raw"]).requires_grad_(True)
+    rgb, disp, acc, w, depth, alpha = h.raw2outputs(raw, cu(fx["S64_z"]), cu(fx["S64_rays_d"]), 0, True, need_alpha=True)
+    loss = (rgb * cu(fx[tag + "_g_rgb"])).sum() + (disp * cu(fx[tag + "_g_disp"])).sum() + \
+        (acc * cu(fx[tag + "_g_acc"])).sum() + (depth * cu(fx[tag + "_g_depth"])).sum() + (w * cu(fx[tag + "_g_weights"])).sum()
+    loss.backward()
+    ref = fx[tag + "_d_raw"]
+    got = raw.grad.cpu().numpy()
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(ref), np.isnan(got))
+    assert np.abs(got[ok] - ref[ok]).max() <= 2e-5 * np.abs(ref[ok]).max()
+    assert h.raw2outputs(raw, cu(fx["S64_z"]), cu(fx["S64_rays_d"]))[5] is None
+
+
+def test_normal_map_drop_in_names(golden):
+    from mvip_nerf_b200 import run
+    from mvip_nerf_b200.run_nerf_helpers import depth2normal
+    fx = golden("normal_map")
+    depth = cu(fx["depth"]).requires_grad_(True)
+    K = cu(fx["K"])
+    # the reference's call sequence (run.py:962-964)
+    xyz = run.depth2xyz_torch(depth, K)
+    n = run.depth2normal_geo(xyz.permute(2, 0, 1).unsqueeze(0), k=31)
+    np.testing.assert_allclose(n[0].detach().cpu().numpy(), fx["normal_f32"], atol=1e-4)
+    (n[0] * cu(fx["g_normal_f32"])).sum().backward()
+    ref = fx["d_depth_f32"]          # the reference's own fp32 autograd (through linalg.inv): noisy, 2% of max
+    assert np.abs(depth.grad.cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    # fused route
+    d2 = cu(fx["depth"]).requires_grad_(True)
+    n2 = depth2normal(d2, fx["K"], k=31)
+    np.testing.assert_allclose(n2[0].detach().cpu().numpy(), fx["normal_f64"], atol=2e-5)
+    (n2[0] * cu(fx["g_normal_f64"].astype(np.float32))).sum().backward()
+    assert np.abs(d2.grad.cpu().numpy() - fx["d_depth_f64"]).max() <= 1e-4 * np.abs(fx["d_depth_f64"]).max()
+
+
+def test_training_reduces_loss(nerf):
+    # a few Adam steps through the public API on a fixed batch: the loss must go down (packed weights are
+    # refreshed after every optimizer step)
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    from mvip_nerf_b200.run_nerf_helpers import img2mse
+    sd = [p.detach().clone() for p in grad_vars]
+    rays = torch.stack([cu(fx["rays_o"]), cu(fx["rays_d"])], 0)
+    target = torch.rand(64, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    losses = []
+    for it in range(12):
+        opt.zero_grad()
+        rgb, disp, acc, depth, extras = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=1.2, far=7.7369,
+                                                   **kw_test)
+        loss = img2mse(rgb, target) + img2mse(extras["rgb0"], target)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    with torch.no_grad():
+        for p, s in zip(grad_vars, sd):
+            p.copy_(s)
+    assert losses[-1] < 0.7 * losses[0], losses
