@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the NeRF volume-rendering hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+metric  : rays/s of one training step (BASELINE.json cfg 2): N_rand = 4096 rays per GPU, 64 coarse +
+          (64+64) fine samples, coarse+fine 8x256 MLP fwd+bwd, sample_pdf + raw2outputs, MSE loss on
+          rgb and rgb0, gradient allreduce (N>1), Adam step.  Weak scaling: 4096 rays per GPU.
+value   : whole-job rays/s with the ray batch already resident in HBM.
+e2e     : the same step through the public API (mvip_nerf_b200.run.render) with HOST buffers: rays + targets
+          copied from pinned memory every step, loss read back every step.
+render  : secondary number — rendered rays/s of BASELINE.json cfg 3 (1008x756 image, render kwargs),
+          rays sharded over the GPUs with one final gather.
+roofline: the kernel with the largest share of the step, timed with CUDA events inside the timed region.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, FOCAL, NEAR, FAR = 756, 1008, 767.2935, 1.2, 7.7369
+N_RAND = 4096
+METRIC = "rays/sec (train fwd+bwd, 64+64 samples)"
+FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 1186816, 1114112, 1185536       # per point, DESIGN.md §kernels
+
+
+def peaks():
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        d["_source"] = "measured"
+        return d
+    except Exception:
+        return fallback
+
+
+def nerf_args(basedir):
+    return argparse.Namespace(
+        multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=64, N_samples=64, netdepth=8,
+        netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, alpha_model_path=None, no_coarse=False,
+        lrate=5e-4, basedir=basedir, expname="bench", ft_path=None, no_reload=True, perturb=1.0, white_bkgd=True,
+        raw_noise_std=1.0, dataset_type="llff", no_ndc=True, lindisp=True, sigma_loss=False)
+
+
+def synth_rays_np(n, seed):
+    """cfg-2 rays: seeded random pixels of the 1008x756 pinhole grid, identity pose."""
+    rng = np.random.RandomState(seed)
+    idx = rng.randint(0, H * W, size=n)
+    i = (idx % W).astype(np.float32)
+    j = (idx // W).astype(np.float32)
+    d = np.stack([(i - W * .5) / FOCAL, -(j - H * .5) / FOCAL, -np.ones_like(i)], -1).astype(np.float32)
+    o = np.zeros_like(d)
+    target = rng.rand(n, 3).astype(np.float32)
+    return o, d, target
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================
+# reference arm: CPU port of the reference path on the host cores
+# =====================================================================================================
+def cpu_train_rays_per_s(n_rays, steps, warmup):
+    from oracle import nerf_oracle as orc
+    from oracle import torch_cpu_port as port
+    pc = port.params_from_numpy(orc.init_params(1), True)
+    pf = port.params_from_numpy(orc.init_params(2), True)
+    o, d, target = synth_rays_np(n_rays, 1)
+    rays = torch.from_numpy(orc.make_ray_batch(o, d, NEAR, FAR))
+    tv = torch.linspace(0., 1., 64)
+    g = torch.Generator().manual_seed(0)
+    args = (torch.rand(n_rays, 64, generator=g), torch.rand(n_rays, 64, generator=g),
+            torch.randn(n_rays, 64, generator=g), torch.randn(n_rays, 128, generator=g), torch.from_numpy(target))
+    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4)
+    for _ in range(warmup):
+        port.train_step(rays, pc, pf, tv, *args); opt.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        port.train_step(rays, pc, pf, tv, *args); opt.step()
+    dt = time.perf_counter() - t0
+    return n_rays * steps / dt, dt / steps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 512
+    steps = max(1, min(a.steps, 6))
+    warm = max(1, min(a.warmup, 1))
+    val, sec = cpu_train_rays_per_s(sample, steps, warm)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": a.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "cfg2 train step (N_rand=4096/GPU), timed on a %d-ray sample per step" % sample},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": "%d rays x %d steps, PyTorch-CPU port of the reference path (oracle/torch_cpu_port.py)"
+                                       % (sample, steps)},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def run_ours(a):
+    from mvip_nerf_b200 import dist as md
+    from mvip_nerf_b200 import ops, run
+    from mvip_nerf_b200.run_nerf_helpers import img2mse
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank, world, local = md.init_from_env()
+    dev = torch.device("cuda", local)
+    pk = peaks()
+
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "bench"))
+        torch.manual_seed(0)
+        kw_train, kw_test, _, grad_vars, _ = run.create_nerf(nerf_args(td))
+    coarse, fine = kw_train["network_fn"], kw_train["network_fine"]
+    optimizer = torch.optim.Adam(grad_vars, lr=5e-4, betas=(0.9, 0.999), fused=True)
+    groups = [list(fine.parameters()), list(coarse.parameters())]
+
+    o, d, target = synth_rays_np(N_RAND, 100 + rank)
+    pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
+    h_o, h_d, h_t = pin(o), pin(d), pin(target)
+    d_rays = torch.stack([h_o.to(dev), h_d.to(dev)], 0)
+    d_target = h_t.to(dev)
+    inv_world = 1.0 / world
+
+    def step(rays, tgt):
+        optimizer.zero_grad(set_to_none=True)
+        rgb, disp, acc, depth, extras = run.render(H, W, FOCAL, chunk=32768, rays=rays, near=NEAR, far=FAR, **kw_train)
+        loss = (img2mse(rgb, tgt) + img2mse(extras["rgb0"], tgt)) * inv_world     # mean over the GLOBAL batch
+        loss.backward()
+        md.allreduce_grads(groups)
+        optimizer.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ---------------------------------------------------------------------
+    for _ in range(a.warmup):
+        step(d_rays, d_target)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.kernel_timer.enable(True)
+    l0 = ops.launch_count
+    ms_total = timed(lambda: step(d_rays, d_target), a.steps)
+    launches = ops.launch_count - l0
+    ktimes = ops.kernel_timer.collect()
+    ops.kernel_timer.enable(False)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / a.steps
+    value = world * N_RAND / (ms_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers, H2D every step, loss read back every step -----------------------
+    def e2e_step():
+        rays = torch.stack([h_o.to(dev, non_blocking=True), h_d.to(dev, non_blocking=True)], 0)
+        tgt = h_t.to(dev, non_blocking=True)
+        return float(step(rays, tgt).item())
+    for _ in range(max(1, a.warmup // 2)):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps) / a.steps
+    e2e_value = world * N_RAND / (ms_e2e * 1e-3)
+
+    # ---- secondary: full-image render (cfg 3), rays sharded, one gather ------------------------------
+    n_img = H * W
+    c2w = torch.eye(4, device=dev)[:3, :4]
+    from mvip_nerf_b200.run_nerf_helpers import get_rays
+    ro, rd = get_rays(H, W, FOCAL, c2w)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    ones = torch.ones(n_img, 1, device=dev)
+    rays_flat = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), NEAR * ones, FAR * ones, vd.reshape(-1, 3)], -1).contiguous()
+    kw_r = {k: v for k, v in kw_test.items() if k not in ("ndc", "use_viewdirs")}
+
+    def render_image():
+        with torch.no_grad():
+            return md.render_sharded(lambda rows: run.batchify_rays(rows, 1 << 17, **kw_r), rays_flat)
+    render_image()
+    r_steps = 3
+    ms_render = timed(render_image, r_steps) / r_steps
+    render_value = n_img / (ms_render * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events around each launch, inside the timed region) -----
+    pts = {"coarse": N_RAND * 64, "fine": N_RAND * 128}
+    per_kernel = {}
+    tot_kernel_ms = sum(sum(v) for v in ktimes.values())
+    for name, vals in ktimes.items():
+        per_kernel[name] = {"launches_per_step": len(vals) / a.steps, "ms_per_step": sum(vals) / a.steps,
+                            "share_of_step": sum(vals) / a.steps / ms_step}
+    npts = pts["coarse"] + pts["fine"]
+    flops = {"mvip_mlp_forward": FLOP_FWD * npts, "dgrad_chain_kernel": FLOP_DGRAD * npts, "wgrad_kernel": FLOP_WGRAD * npts}
+    top = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    roofline = None
+    if top in flops:
+        ach = flops[top] / (per_kernel[top]["ms_per_step"] * 1e-3) / 1e12
+        roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["_source"],
+                    "share_of_step": per_kernel[top]["share_of_step"]}
+    for k in flops:
+        if k in per_kernel:
+            per_kernel[k]["tflops"] = flops[k] / (per_kernel[k]["ms_per_step"] * 1e-3) / 1e12
+            per_kernel[k]["frac_of_peak"] = per_kernel[k]["tflops"] / peak_tf
+
+    # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------------
+    cpu_base = None
+    if world == 1 and not a.no_cpu_baseline:
+        sample, csteps = 512, 4
+        cval, _ = cpu_train_rays_per_s(sample, csteps, 1)
+        cpu_base = {"value": cval, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": "%d rays x %d steps of the same train step, PyTorch-CPU port of the reference path" % (sample, csteps)}
+
+    bytes_in = (h_o.numel() + h_d.numel() + h_t.numel()) * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: one training step, N_rand=%d rays per GPU (global %d), N_samples=64, N_importance=64, "
+                               "coarse+fine 8x256 NeRF (random init), lindisp, white_bkgd, perturb=1, raw_noise_std=1, "
+                               "loss=mse(rgb)+mse(rgb0), grad allreduce, fused Adam" % (N_RAND, N_RAND * world),
+                   "parallelism": "rays sharded, dp%d" % world,
+                   "l2": "no explicit flush: each step streams ~8 GB of activation stash per GPU (>> 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "kernels": per_kernel,
+        "render": {"value": render_value, "unit": "rays/s", "ms_per_image": ms_render,
+                   "workload": "cfg3: 1008x756 image (762,048 rays), render kwargs, rays sharded over %d GPU(s), one gather" % world,
+                   "tflops": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12,
+                   "frac_of_peak": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12 / (peak_tf * world)},
+        "train_tflops": world * N_RAND * 192 * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) / (ms_step * 1e-3) / 1e12,
+    }
+    line["train_frac_of_peak"] = line["train_tflops"] / (peak_tf * world)
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

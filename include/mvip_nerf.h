@@ -159,6 +159,11 @@ int mvip_mlp_backward(const void* packed, const float* d_raw /* [n_points,4] */,
                       const void* stash, void* workspace, float* const* grads /* host array */,
                       int accumulate, void* stream);
 
+/* The same call split into its four launches (bit 0 dgrad chain, 1 wgrad, 2 head grads, 3 reduce) so a
+ * caller can bracket each kernel with its own events; phases must run in order on the same workspace. */
+int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_points, const void* stash,
+                             void* workspace, float* const* grads, int accumulate, int phase_mask, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Self tests of the tcgen05 building blocks (descriptor / layout conventions), used by tests/.
  *   which: 0 = K-major A,B (forward / dgrad form)   1 = MN-major A,B (wgrad form)

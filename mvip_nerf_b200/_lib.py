@@ -49,6 +49,8 @@ _SIGNATURES = {
     "mvip_mlp_backward_workspace_bytes": (c_size_t, [c_int64]),
     "mvip_mlp_backward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_void_p), c_int,
                                   c_void_p]),
+    "mvip_mlp_backward_phases": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_void_p), c_int,
+                                         c_int, c_void_p]),
     "mvip_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

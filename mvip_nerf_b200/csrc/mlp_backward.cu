@@ -488,42 +488,67 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
 // 3. alpha / rgb head grads on CUDA cores
 // =================================================================================================
 constexpr int kHeadFloats = 256 + 4 + 384 + 4;   // dW_alpha, db_alpha(+pad), dW_rgb, db_rgb(+pad)
+constexpr int kHeadMaxBlocks = 1184;             // 8 per SM
 
+__device__ __forceinline__ void unpack_bf16x8(const uint4 v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// dW_alpha[j] = sum_p d_alpha[p] h8[p][j];  dW_rgb[c][j] = sum_p d_rgb[p][c] hidden[p][j];  db = sum_p d_raw[p].
+// Thread (cg = tid%32, rg = tid/32) owns the 8 features [8cg, 8cg+8) of rows [16rg, 16rg+16) of every tile of
+// its block: one 16-byte load per (row, operand), eight lanes covering one 128-byte row segment.
 __global__ void __launch_bounds__(256) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
                                                          int64_t n_points, int64_t n_tiles, float* __restrict__ out) {
-  __shared__ float4 dr[kTile];
-  const int j = threadIdx.x;  // feature column
-  float a_alpha = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
-  float s_alpha = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
-  const int64_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(n_tiles, t0 + per);
-  for (int64_t t = t0; t < t1; ++t) {
-    __syncthreads();
-    if (j < kTile) {
-      const int64_t g = t * kTile + j;
-      dr[j] = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
+  __shared__ float red[8][kHeadFloats];
+  const int tid = threadIdx.x, cg = tid & 31, rg = tid >> 5;
+  float aa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float ar[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t h8_off = (uint32_t)(kStashH + 28 + (cg >> 3)) * kActChunk;
+  const uint32_t hid_off = (uint32_t)(kStashHidden + ((cg & 15) >> 3)) * kActChunk;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const uint8_t* tile = stash + (size_t)t * kStashTileBytes;
-    const uint8_t* h8 = tile + (size_t)(kStashH + 28 + (j >> 6)) * kActChunk + (j & 7) * 2;
-    const uint8_t* hid = tile + (size_t)(kStashHidden + ((j & 127) >> 6)) * kActChunk + (j & 7) * 2;
-    const int gcol = (j & 63) >> 3;
-#pragma unroll 4
-    for (int row = 0; row < kTile; ++row) {
-      const float4 d = dr[row];
-      const float hv = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(h8 + chunk_off16(row, gcol))) << 16);
-      a_alpha += d.w * hv;
-      if (j < 128) {
-        const float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(hid + chunk_off16(row, gcol))) << 16);
-        a_r += d.x * x; a_g += d.y * x; a_b += d.z * x;
+#pragma unroll 8
+    for (int i = 0; i < 16; ++i) {
+      const int row = rg * 16 + i;
+      const int64_t g = t * kTile + row;
+      const float4 d = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t o = chunk_off16(row, cg & 7);
+      float h[8];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(tile + h8_off + o)), h);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) aa[e] += d.w * h[e];
+      if (cg < 16) {
+        float x[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(tile + hid_off + o)), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ar[e] += d.x * x[e]; ag[e] += d.y * x[e]; ab[e] += d.z * x[e]; }
       }
-      if (j == 255) { s_alpha += d.w; s_r += d.x; s_g += d.y; s_b += d.z; }
+      if (cg == 31) { ds.x += d.x; ds.y += d.y; ds.z += d.z; ds.w += d.w; }
     }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[rg][cg * 8 + e] = aa[e];
+    if (cg < 16) {
+      red[rg][260 + cg * 8 + e] = ar[e];
+      red[rg][260 + 128 + cg * 8 + e] = ag[e];
+      red[rg][260 + 256 + cg * 8 + e] = ab[e];
+    }
+  }
+  if (cg == 31) { red[rg][256] = ds.w; red[rg][644] = ds.x; red[rg][645] = ds.y; red[rg][646] = ds.z; }
+  if (cg == 30) { red[rg][257] = red[rg][258] = red[rg][259] = 0.f; red[rg][647] = 0.f; }
+  __syncthreads();
   float* o = out + (size_t)blockIdx.x * kHeadFloats;
-  o[j] = a_alpha;
-  if (j < 128) { o[260 + j] = a_r; o[260 + 128 + j] = a_g; o[260 + 256 + j] = a_b; }
-  if (j == 255) { o[256] = s_alpha; o[644] = s_r; o[645] = s_g; o[646] = s_b; }
+  for (int e = tid; e < kHeadFloats; e += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][e];
+    o[e] = s;
+  }
 }
 
 // =================================================================================================
@@ -599,7 +624,7 @@ Workspace carve(int64_t n_points) {
   w.partials = take((size_t)kMaxCtas * 2 * kPartialSlotBytes);
   w.bias = take((size_t)kMaxCtas * 2 * 256 * sizeof(float));
   w.segs = take((size_t)kMaxCtas * 2 * sizeof(Segment));
-  w.heads = take((size_t)kMaxCtas * kHeadFloats * sizeof(float));
+  w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
   w.total = off;
   return w;
 }
@@ -612,6 +637,11 @@ size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_poin
 
 int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, const void* stash, void* workspace,
                       float* const* grads, int accumulate, void* stream) {
+  return mvip_mlp_backward_phases(packed, d_raw, n_points, stash, workspace, grads, accumulate, 15, stream);
+}
+
+int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_points, const void* stash,
+                             void* workspace, float* const* grads, int accumulate, int phase_mask, void* stream) {
   MVIP_REQUIRE(n_points >= 0, MVIP_E_INVALID, "mvip_mlp_backward: negative n_points");
   MVIP_REQUIRE(grads, MVIP_E_INVALID, "mvip_mlp_backward: null grads");
   GradPtrs gp;
@@ -631,7 +661,7 @@ int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, 
   const int sms = mvip_num_sms() < kMaxCtas ? mvip_num_sms() : kMaxCtas;
 
   // 1. dgrad chain
-  {
+  if (phase_mask & 1) {
     ChainParams cp;
     cp.packed = static_cast<const uint8_t*>(packed);
     cp.d_raw = reinterpret_cast<const float4*>(d_raw);
@@ -648,7 +678,7 @@ int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, 
   }
   // 2. wgrad
   const int w_grid = sms;
-  {
+  if (phase_mask & 2) {
     WParams wp;
     wp.stash = static_cast<const uint8_t*>(stash);
     wp.dz = wsb + ws.dz;
@@ -662,12 +692,15 @@ int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, 
     MVIP_LAUNCH_OK("wgrad_kernel");
   }
   // 3. heads
-  const int head_grid = (int)(n_tiles < sms ? n_tiles : sms);
-  head_grads_kernel<<<head_grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_raw), static_cast<const uint8_t*>(stash),
-                                               n_points, n_tiles, reinterpret_cast<float*>(wsb + ws.heads));
-  MVIP_LAUNCH_OK("head_grads_kernel");
+  const int head_cap = sms * 8 < kHeadMaxBlocks ? sms * 8 : kHeadMaxBlocks;
+  const int head_grid = (int)(n_tiles < head_cap ? n_tiles : head_cap);
+  if (phase_mask & 4) {
+    head_grads_kernel<<<head_grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_raw), static_cast<const uint8_t*>(stash),
+                                                 n_points, n_tiles, reinterpret_cast<float*>(wsb + ws.heads));
+    MVIP_LAUNCH_OK("head_grads_kernel");
+  }
   // 4. reduce
-  {
+  if (phase_mask & 8) {
     ReduceParams rp;
     rp.partials = reinterpret_cast<const float*>(wsb + ws.partials);
     rp.bias_partials = reinterpret_cast<const float*>(wsb + ws.bias);

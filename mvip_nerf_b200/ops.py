@@ -22,6 +22,30 @@ _LAUNCHES = {"mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 
              "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
 
 
+class _KernelTimer:
+    """Optional CUDA-event bracket around every library call (bench.py: per-kernel times inside the timed region)."""
+
+    def __init__(self):
+        self.on = False
+        self.recs = []
+
+    def enable(self, on):
+        self.on = bool(on)
+        if on:
+            self.recs = []
+
+    def collect(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.recs:
+            out.setdefault(name, []).append(e0.elapsed_time(e1))
+        self.recs = []
+        return out
+
+
+kernel_timer = _KernelTimer()
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -43,9 +67,19 @@ def _f32(t, name):
 def _call(name, *args):
     global launch_count
     lib = _lib.load()
-    rc = getattr(lib, name)(*args)
+    label = None
+    if isinstance(name, tuple):
+        name, label = name
+    if kernel_timer.on:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        kernel_timer.recs.append((label or name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     _lib.check(rc, name)
-    launch_count += _LAUNCHES.get(name, 1)
+    launch_count += 1 if label else _LAUNCHES.get(name, 1)
 
 
 # ---------------------------------------------------------------------------------------------- sampling
@@ -274,8 +308,13 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-    _call("mvip_mlp_backward", _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr, int(bool(accumulate)),
-          _stream())
+    if kernel_timer.on:   # one bracket per launch: dgrad chain, wgrad, head grads, reduce
+        for bit, label in ((1, "dgrad_chain_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
+            _call(("mvip_mlp_backward_phases", label), _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr,
+                  int(bool(accumulate)), bit, _stream())
+    else:
+        _call("mvip_mlp_backward", _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr, int(bool(accumulate)),
+              _stream())
     return grads
 
 

@@ -536,3 +536,48 @@ def nerf_forward_backward_bf16sim(p, pts, viewdirs, d_out=None, multires=10, mul
         g["pts_linears.%d.bias" % i] = d_pre.sum(0)
         d_h = d_pre @ W["pts_linears.%d.weight" % i]
     return out, g
+
+
+# --------------------------------------------------------------------------------------
+# One training step of the path (render_rays forward + backward of an MSE loss), used as the CPU
+# baseline by bench.py (`cpu_baseline` / `--impl reference`, kind "port") and by the e2e tests.
+# --------------------------------------------------------------------------------------
+def train_step(rays, p_coarse, p_fine, t_vals, t_rand, u, noise0, noise1, target_rgb, lindisp=True,
+               white_bkgd=True, dtype=f32):
+    """loss = mse(rgb, target) + mse(rgb0, target) (run.py:1000-1027 without the SDS / depth terms);
+    returns (loss, grads_coarse, grads_fine).  Follows autograd of the reference: z_samples detached."""
+    rays = np.asarray(rays, dtype=f32)
+    N = rays.shape[0]
+    viewdirs = rays[:, -3:]
+    z0 = sample_coarse(rays, t_vals, t_rand, lindisp)
+    raw0, saved0 = run_network(p_coarse, points(rays, z0), viewdirs, keep=True, dtype=dtype)
+    c0 = raw2outputs(raw0, z0, rays[:, 3:6], noise0, white_bkgd, dtype=dtype)
+    fs = fine_samples(z0, c0["weights"], u)
+    z1 = fs["z_merged"]
+    raw1, saved1 = run_network(p_fine, points(rays, z1), viewdirs, keep=True, dtype=dtype)
+    c1 = raw2outputs(raw1, z1, rays[:, 3:6], noise1, white_bkgd, dtype=dtype)
+    target = np.asarray(target_rgb, dtype=np.float64)
+    d1 = c1["rgb_map"].astype(np.float64) - target
+    d0 = c0["rgb_map"].astype(np.float64) - target
+    loss = float((d1 ** 2).mean() + (d0 ** 2).mean())
+    g_rgb1 = 2.0 * d1 / d1.size
+    g_rgb0 = 2.0 * d0 / d0.size
+    zeros = np.zeros(N)
+    d_raw1 = raw2outputs_backward(raw1, z1, rays[:, 3:6], noise1, white_bkgd, g_rgb1, zeros, zeros, zeros, dtype=np.float64)
+    d_raw0 = raw2outputs_backward(raw0, z0, rays[:, 3:6], noise0, white_bkgd, g_rgb0, zeros, zeros, zeros, dtype=np.float64)
+    g1 = nerf_backward(p_fine, saved1, d_raw1.reshape(-1, 4).astype(dtype), dtype=dtype)
+    g0 = nerf_backward(p_coarse, saved0, d_raw0.reshape(-1, 4).astype(dtype), dtype=dtype)
+    return loss, g0, g1
+
+
+def blas_threads():
+    """Number of threads numpy's BLAS uses (what `cores` means in bench.py's cpu_baseline)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    import os
+    return os.cpu_count() or 1

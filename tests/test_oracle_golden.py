@@ -134,3 +134,51 @@ def test_render_rays_end_to_end(golden):
     np.testing.assert_allclose(out["rgb0"], fx["train_rgb0"], atol=2e-5)
     np.testing.assert_allclose(out["rgb_map"], fx["train_rgb"], atol=5e-5)
     np.testing.assert_allclose(out["disp_map"], fx["train_disp"], rtol=2e-4)
+
+
+def test_torch_cpu_port_matches_reference_golden(golden):
+    # the bench's CPU baseline arm (oracle/torch_cpu_port.py) against the reference's own render() outputs
+    import torch
+    from oracle import torch_cpu_port as port
+    fx = golden("render_e2e")
+    pc = port.params_from_numpy(orc.init_params(int(fx["coarse_seed"])), True)
+    pf = port.params_from_numpy(orc.init_params(int(fx["fine_seed"])), True)
+    rays = torch.from_numpy(orc.make_ray_batch(fx["rays_o"], fx["rays_d"], fx["near"], fx["far"]))
+    tv = torch.linspace(0., 1., 64)
+    with torch.no_grad():
+        out = port.render_rays(rays, pc, pf, tv)
+    np.testing.assert_allclose(out["rgb_map"].numpy(), fx["test_rgb"], atol=1e-5)
+    np.testing.assert_allclose(out["z_vals"].numpy(), fx["test_z_vals"], atol=1e-5)
+    out = port.render_rays(rays, pc, pf, tv, torch.from_numpy(fx["train_t_rand"]), torch.from_numpy(fx["train_u"]),
+                           torch.from_numpy(fx["train_noise0"]), torch.from_numpy(fx["train_noise1"]))
+    np.testing.assert_allclose(out["rgb_map"].detach().numpy(), fx["train_rgb"], atol=1e-5)
+    loss = ((out["rgb_map"] - 0.5) ** 2).mean() + ((out["rgb0"] - 0.5) ** 2).mean() + 0.1 * ((out["disp_map"] - 0.3) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - float(fx["train_loss"])) < 1e-5
+    g = pf["pts_linears.0.weight"].grad.numpy()
+    ref = fx["train_grad.fine.pts_linears.0.weight"]
+    assert np.abs(g - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+def test_oracle_train_step_matches_torch_port():
+    import torch
+    from oracle import torch_cpu_port as port
+    rng = np.random.RandomState(0)
+    N = 24
+    ro, rd = orc.get_rays(756, 1008, 767.2935, np.eye(4, dtype=np.float32)[:3, :4])
+    idx = rng.permutation(756 * 1008)[:N]
+    rays = orc.make_ray_batch(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx], 1.2, 7.7369)
+    pcn, pfn = orc.init_params(1), orc.init_params(2)
+    tv = orc.linspace_f32(0, 1, 64)
+    r = [rng.rand(N, 64).astype(np.float32), rng.rand(N, 64).astype(np.float32),
+         rng.randn(N, 64).astype(np.float32), rng.randn(N, 128).astype(np.float32)]
+    target = rng.rand(N, 3).astype(np.float32)
+    loss, g0, g1 = orc.train_step(rays, pcn, pfn, tv, r[0], r[1], r[2], r[3], target, dtype=np.float64)
+    pc, pf = port.params_from_numpy(pcn, True), port.params_from_numpy(pfn, True)
+    lt = port.train_step(torch.from_numpy(rays), pc, pf, torch.from_numpy(tv), *[torch.from_numpy(x) for x in r],
+                         torch.from_numpy(target))
+    assert abs(loss - lt.item()) < 1e-5
+    for name in ("pts_linears.0.weight", "pts_linears.5.weight", "rgb_linear.weight", "alpha_linear.bias"):
+        for gn, pt in ((g0, pc), (g1, pf)):
+            ref = pt[name].grad.numpy()
+            assert np.abs(gn[name] - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1e-12), name
