@@ -304,7 +304,13 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
     P = d_raw.shape[0]
     dev = d_raw.device
     if grads is None:
-        grads = [torch.zeros(shp, device=dev, dtype=torch.float32) for shp in PARAM_SHAPES]
+        # one flat buffer, 24 views; the reduce kernel overwrites every element when accumulate == 0
+        sizes = [int(torch.Size(shp).numel()) for shp in PARAM_SHAPES]
+        flat = torch.empty((sum(sizes),), device=dev, dtype=torch.float32)
+        grads, off = [], 0
+        for shp, n in zip(PARAM_SHAPES, sizes):
+            grads.append(flat[off:off + n].view(shp))
+            off += n
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
