@@ -170,6 +170,10 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
  *   a [M=128,K] , b [N,K] fp32 row-major for which==0;  a [K,128], b [K,N] for which==1
  *   out [128, N] fp32 = A * B^T (bf16 inputs, fp32 accumulate).  K multiple of 64, N in {64,128,256}.
  */
+/* Debug aid: cycle counters recorded by CTA 0 of the last mvip_mlp_forward launch (host array of 16 u64;
+ * synchronises the device). */
+int mvip_debug_profile(unsigned long long* out16);
+
 int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
 
 #ifdef __cplusplus

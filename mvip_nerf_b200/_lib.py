@@ -51,6 +51,7 @@ _SIGNATURES = {
                                   c_void_p]),
     "mvip_mlp_backward_phases": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_void_p), c_int,
                                          c_int, c_void_p]),
+    "mvip_debug_profile": (c_int, [c_void_p]),
     "mvip_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,5 +1,6 @@
 // api.cu — error plumbing and device queries of the C ABI (include/mvip_nerf.h).
-#include "common.cuh"
+#include "mlp_common.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -21,6 +22,17 @@ int mvip_num_sms() {
   }
   return cached[dev];
 }
+
+namespace mlp {
+bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVIP_MLP_CTA_PAIRS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace mlp
 
 extern "C" {
 

@@ -68,4 +68,7 @@ constexpr size_t kDzTileBytes = (size_t)kDzChunks * kActChunk;
 
 inline int64_t num_tiles(int64_t n_points) { return (n_points + kTile - 1) / kTile; }
 
+// kernel variant switch (api.cu): CTA pairs (cta_group::2) unless MVIP_MLP_CTA_PAIRS=0
+bool use_cta_pairs();
+
 }  // namespace mlp

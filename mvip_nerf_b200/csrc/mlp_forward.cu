@@ -26,6 +26,10 @@ constexpr uint32_t kSmemW = kSmemPE + 2 * kActChunk;     // weight ring
 constexpr uint32_t kSmemBytes = kSmemW + kStages * kW256;  // 229,376
 constexpr int kNumSteps = 10;
 
+// cycle counters of CTA 0 (debug aid, read with mvip_debug_profile): [0] mma: act wait, [1] mma: weight wait,
+// [2] mma: total, [3] epi slot0: acc wait, [4] epi slot0: work, [5] epi slot0: total, [6] producer: empty wait
+__device__ unsigned long long g_prof[16];
+
 struct Params {
   const uint8_t* packed;
   mvip_points pts;
@@ -89,6 +93,196 @@ __device__ __forceinline__ void write_pe_row(uint8_t* img, int row, float x, flo
     }
     *reinterpret_cast<uint4*>(img + chunk_off16(row, g)) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// ===================== epilogue warpgroups (shared by the 1-CTA and the CTA-pair kernels) =====================
+// Warps 4..11: warpgroup `slot` owns tile slot `slot`; thread r <-> row r of the tile <-> TMEM lane r.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// small_smem != 0: the fp32 tail of the packed blob (biases, alpha / rgb heads) was staged in shared memory at
+// that shared-space address (CTA-pair kernel); otherwise it is read from global memory.
+template <bool kTrain, int kCta>
+__device__ __forceinline__ void forward_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
+                                                 uint32_t tmem_base, int warp, int tid, uint32_t cta_rank,
+                                                 int64_t first_it, int64_t n_iters, int64_t it_stride,
+                                                 uint32_t small_smem) {
+  auto small4 = [&](int float_index) -> float4 {   // 4 consecutive floats of the small-parameter block
+    if (kCta == 2) return lds_f4(small_smem + float_index * 4);
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.packed + kSmallOff) + float_index));
+  };
+  auto small1 = [&](int float_index) -> float {
+    if (kCta == 2) return lds_f1(small_smem + float_index * 4);
+    return __ldg(reinterpret_cast<const float*>(p.packed + kSmallOff) + float_index);
+  };
+  // "A operand ready + accumulator drained" goes to the MMA issuer: local barrier, or the leader CTA's in a pair
+  auto act_arrive = [&](uint64_t* bar) {
+    if (kCta == 1 || cta_rank == 0) mbar_arrive(bar);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+  };
+  {
+    const int slot = (warp - 4) >> 2;
+    const int r = tid - 128 - slot * 128;                     // row of the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t bar_id = 1 + slot;
+    uint8_t* act = smem + kSmemAct + slot * 4 * kActChunk;
+    uint8_t* pe = smem + kSmemPE + slot * kActChunk;
+    uint32_t acc_phase = 0;
+    long long t_accw = 0, t_work = 0, t_begin = clock64();
+
+    for (int64_t it = first_it; it < n_iters; it += it_stride) {
+      const int64_t tile = (kCta == 1) ? 2 * it + slot : 4 * it + 2 * slot + (int64_t)cta_rank;
+      const bool tile_valid = tile < p.n_tiles;
+      const int64_t g = tile * kTile + r;
+      const bool valid = tile_valid && g < p.pts.n_points;
+      uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
+
+      // ---- inputs: point and view direction of this row -----------------------------------
+      float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+      if (valid) {
+        if (p.pts.rays) {
+          const int64_t ray = g / p.pts.n_samples;
+          const float* rp = p.pts.rays + ray * p.pts.ray_stride;
+          const float zv = __ldg(p.pts.z_vals + g);
+          px = __fadd_rn(__ldg(rp + 0), __fmul_rn(__ldg(rp + 3), zv));   // pts = o + d*z   run.py:1783
+          py = __fadd_rn(__ldg(rp + 1), __fmul_rn(__ldg(rp + 4), zv));
+          pz = __fadd_rn(__ldg(rp + 2), __fmul_rn(__ldg(rp + 5), zv));
+          vx = __ldg(rp + p.pts.viewdir_offset);
+          vy = __ldg(rp + p.pts.viewdir_offset + 1);
+          vz = __ldg(rp + p.pts.viewdir_offset + 2);
+        } else {
+          const float* pp = p.pts.pts + g * p.pts.pts_stride;
+          const float* dp = p.pts.dirs + g * p.pts.dirs_stride;
+          px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+          vx = __ldg(dp); vy = __ldg(dp + 1); vz = __ldg(dp + 2);
+        }
+      }
+      if (kTrain) {
+        if (r == 0) tma_store_wait_read0();
+        named_bar_sync(bar_id, 128);
+      }
+      write_pe_row<10>(pe, r, px, py, pz);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(bar_id, 128);
+      if (r == 0) {
+        act_arrive(&bar_act[slot]);
+        if (kTrain && tile_valid) {
+          tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
+          tma_store_commit();
+        }
+      }
+
+      float alpha_acc = 0.f;
+      float rgb_acc[3] = {0.f, 0.f, 0.f};
+
+      for (int s = 0; s < kNumSteps; ++s) {
+        long long t0 = clock64();
+        mbar_wait(&bar_acc[slot], acc_phase);
+        long long t1 = clock64();
+        t_accw += t1 - t0;
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (kTrain) {
+          if (r == 0) tma_store_wait_read0();   // earlier bulk stores finished reading act / pe
+          named_bar_sync(bar_id, 128);
+        }
+        const int ncols = (s == 9) ? 128 : 256;
+        const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
+        uint32_t* mrow = kTrain ? reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff +
+                                                               ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32)
+                                : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_base + slot * 256 + c0, acc);
+          tmem_ld_wait();
+          float v[32];
+          uint32_t mword = 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = small4(bias_i + c0 + 4 * j4);
+            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
+            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
+            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
+            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
+          }
+          if (s != 8) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (kTrain) mword |= (v[j] > 0.f ? 1u : 0u) << j;
+              v[j] = fmaxf(v[j], 0.f);
+            }
+          }
+          if (kTrain && s != 8 && tile_valid) mrow[c0 >> 5] = mword;
+          if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w = small4(kSmWAlpha + c0 + 4 * j4);
+              alpha_acc += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
+            }
+          }
+          if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w = small4(kSmWRgb + ch * 128 + c0 + 4 * j4);
+                rgb_acc[ch] += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
+              }
+            }
+          }
+          if (s != 9 || kTrain) {
+            // next layer's A operand (and the stash image): 32 columns = 4 x 16-byte groups of chunk c0/64
+            uint8_t* img = act + (c0 >> 6) * kActChunk;
+            const int g0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
+                  make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            }
+          }
+        }
+        if (s == 8) write_pe_row<4>(pe, r, vx, vy, vz);  // PE(viewdir) replaces PE(pts): L5 has consumed it
+        if (s == 9 && valid) {
+          p.raw[g] = make_float4(rgb_acc[0] + small1(kSmBRgb), rgb_acc[1] + small1(kSmBRgb + 1),
+                                 rgb_acc[2] + small1(kSmBRgb + 2), alpha_acc + small1(kSmBAlpha));
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        t_work += clock64() - t1;
+        if (r == 0) {
+          if (s < 9) act_arrive(&bar_act[slot]);
+          if (kTrain && tile_valid) {
+            if (s < 8) {
+              for (int j = 0; j < 4; ++j)
+                tma_store_1d(stash_tile + (size_t)(kStashH + 4 * s + j) * kActChunk, act + j * kActChunk, kActChunk);
+            } else if (s == 8) {
+              for (int j = 0; j < 4; ++j)
+                tma_store_1d(stash_tile + (size_t)(kStashFeat + j) * kActChunk, act + j * kActChunk, kActChunk);
+              tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
+            } else {
+              for (int j = 0; j < 2; ++j)
+                tma_store_1d(stash_tile + (size_t)(kStashHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
+            }
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (kTrain && r == 0) tma_store_wait_all0();
+    if (blockIdx.x == 0 && tid == 128) { g_prof[3] = t_accw; g_prof[4] = t_work; g_prof[5] = clock64() - t_begin; }
   }
 }
 
@@ -175,160 +369,159 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warpgroups =====================
-    const int slot = (warp - 4) >> 2;
-    const int r = tid - 128 - slot * 128;                     // row of the tile == TMEM lane
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t bar_id = 1 + slot;
-    uint8_t* act = smem + kSmemAct + slot * 4 * kActChunk;
-    uint8_t* pe = smem + kSmemPE + slot * kActChunk;
-    const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
-    uint32_t acc_phase = 0;
-
-    for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-      const int64_t tile = 2 * it + slot;
-      const bool tile_valid = tile < p.n_tiles;
-      const int64_t g = tile * kTile + r;
-      const bool valid = tile_valid && g < p.pts.n_points;
-      uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
-
-      // ---- inputs: point and view direction of this row -----------------------------------
-      float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
-      if (valid) {
-        if (p.pts.rays) {
-          const int64_t ray = g / p.pts.n_samples;
-          const float* rp = p.pts.rays + ray * p.pts.ray_stride;
-          const float zv = __ldg(p.pts.z_vals + g);
-          px = __fadd_rn(__ldg(rp + 0), __fmul_rn(__ldg(rp + 3), zv));   // pts = o + d*z   run.py:1783
-          py = __fadd_rn(__ldg(rp + 1), __fmul_rn(__ldg(rp + 4), zv));
-          pz = __fadd_rn(__ldg(rp + 2), __fmul_rn(__ldg(rp + 5), zv));
-          vx = __ldg(rp + p.pts.viewdir_offset);
-          vy = __ldg(rp + p.pts.viewdir_offset + 1);
-          vz = __ldg(rp + p.pts.viewdir_offset + 2);
-        } else {
-          const float* pp = p.pts.pts + g * p.pts.pts_stride;
-          const float* dp = p.pts.dirs + g * p.pts.dirs_stride;
-          px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
-          vx = __ldg(dp); vy = __ldg(dp + 1); vz = __ldg(dp + 2);
-        }
-      }
-      if (kTrain) {
-        if (r == 0) tma_store_wait_read0();
-        named_bar_sync(bar_id, 128);
-      }
-      write_pe_row<10>(pe, r, px, py, pz);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(bar_id, 128);
-      if (r == 0) {
-        mbar_arrive(&bar_act[slot]);
-        if (kTrain && tile_valid) {
-          tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
-          tma_store_commit();
-        }
-      }
-
-      float alpha_acc = 0.f;
-      float rgb_acc[3] = {0.f, 0.f, 0.f};
-
-      for (int s = 0; s < kNumSteps; ++s) {
-        mbar_wait(&bar_acc[slot], acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (kTrain) {
-          if (r == 0) tma_store_wait_read0();   // earlier bulk stores finished reading act / pe
-          named_bar_sync(bar_id, 128);
-        }
-        const int ncols = (s == 9) ? 128 : 256;
-        const float* bias = small + (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
-        uint32_t* mrow = kTrain ? reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff +
-                                                               ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32)
-                                : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + lane_base + slot * 256 + c0, acc);
-          tmem_ld_wait();
-          float v[32];
-          uint32_t mword = 0;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j4);
-            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
-            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
-            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
-            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
-          }
-          if (s != 8) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (kTrain) mword |= (v[j] > 0.f ? 1u : 0u) << j;
-              v[j] = fmaxf(v[j], 0.f);
-            }
-          }
-          if (kTrain && s != 8 && tile_valid) mrow[c0 >> 5] = mword;
-          if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(small + kSmWAlpha + c0) + j4);
-              alpha_acc += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
-            }
-          }
-          if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + ch * 128 + c0) + j4);
-                rgb_acc[ch] += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
-              }
-            }
-          }
-          if (s != 9 || kTrain) {
-            // next layer's A operand (and the stash image): 32 columns = 4 x 16-byte groups of chunk c0/64
-            uint8_t* img = act + (c0 >> 6) * kActChunk;
-            const int g0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
-                  make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-            }
-          }
-        }
-        if (s == 8) write_pe_row<4>(pe, r, vx, vy, vz);  // PE(viewdir) replaces PE(pts): L5 has consumed it
-        if (s == 9 && valid) {
-          p.raw[g] = make_float4(rgb_acc[0] + __ldg(small + kSmBRgb), rgb_acc[1] + __ldg(small + kSmBRgb + 1),
-                                 rgb_acc[2] + __ldg(small + kSmBRgb + 2), alpha_acc + __ldg(small + kSmBAlpha));
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (r == 0) {
-          if (s < 9) mbar_arrive(&bar_act[slot]);
-          if (kTrain && tile_valid) {
-            if (s < 8) {
-              for (int j = 0; j < 4; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashH + 4 * s + j) * kActChunk, act + j * kActChunk, kActChunk);
-            } else if (s == 8) {
-              for (int j = 0; j < 4; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashFeat + j) * kActChunk, act + j * kActChunk, kActChunk);
-              tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
-            } else {
-              for (int j = 0; j < 2; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
-            }
-            tma_store_commit();
-          }
-        }
-      }
-    }
-    if (kTrain && r == 0) tma_store_wait_all0();
+    forward_epilogue<kTrain, 1>(p, smem, bar_acc, bar_act, tmem_base, warp, tid, 0, blockIdx.x, n_pairs, gridDim.x, 0u);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
+// =================================================================================================
+// CTA-pair variant (cta_group::2): two SMs of a cluster cooperate on 256-point MMAs.
+//   * each CTA keeps its own two 128-point tile slots, TMEM accumulators and epilogue warps;
+//   * a weight chunk is split by output rows: each CTA streams only its half (16 KB) into a 3-stage ring,
+//     and a staged chunk is used by BOTH tile slots before it is released -> 1/4 of the L2->smem weight
+//     traffic of the 1-CTA kernel, with 2x the prefetch depth;
+//   * slot 0 runs up to 2 chunks ahead of slot 1 ("A0 A1 B0 A2 B1 A3 B2 B3"), so one slot's epilogue still
+//     overlaps the other slot's MMAs;
+//   * only the leader CTA (rank 0) issues tcgen05.mma.cta_group::2; its barriers collect the peer's
+//     "weights landed" (relay warp) and "A operand ready" (remote mbarrier arrive) signals, and
+//     tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
+// =================================================================================================
+constexpr int kStages2 = 3;
+constexpr int kLead2 = kStages2 - 1;                              // chunks slot 0 may run ahead of slot 1
+constexpr uint32_t kHalfW256 = kW256 / 2;
+constexpr uint32_t kSmemSmall2 = kSmemW + kStages2 * kHalfW256;   // fp32 tail of the packed blob (12,320 B)
+constexpr uint32_t kSmemBytes2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // 225,280
+
+template <bool kTrain>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_forward_pair_kernel(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[kStages2], bar_empty[kStages2], bar_acc[2], bar_act[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t n_quads = (p.n_tiles + 3) / 4;
+  const int64_t first_it = blockIdx.x >> 1, it_stride = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&bar_full[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
+      mbar_init(&bar_empty[i], 1);                  // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 2); }   // act: one arrive per CTA
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(&tmem_base_s, 512);
+  {  // biases + alpha / rgb heads -> shared memory (read ~10^3 times per tile by the epilogue warps)
+    const float4* src = reinterpret_cast<const float4*>(p.packed + kSmallOff);
+    float4* dst = reinterpret_cast<float4*>(smem + kSmemSmall2);
+    for (int i = tid; i < kSmallFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's half of every chunk, each chunk once per quad =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t it = first_it; it < n_quads; it += it_stride) {
+        for (int c = 0; c < kFwdChunks; ++c) {
+          const uint32_t half = fwd_chunk_bytes(c) / 2;
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], half);
+          tma_load_1d(smem + kSmemW + stage * kHalfW256, p.packed + fwd_chunk_off(c) + rank * half, half, &bar_full[stage]);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (rank == 1) {
+        // ===================== relay: tell the leader that this CTA's half has landed =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t it = first_it; it < n_quads; it += it_stride) {
+          for (int c = 0; c < kFwdChunks; ++c) {
+            mbar_wait(&bar_full[stage], phase);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[stage]), 0));
+            if (++stage == kStages2) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        // ===================== MMA issuer (leader CTA) =====================
+        uint32_t act_phase[2] = {0, 0};
+        uint32_t gchunk = 0;   // running chunk counter -> ring stage and phase
+        long long t_act = 0, t_full = 0, t_begin = clock64();
+        const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0);
+        const uint32_t idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        for (int64_t it = first_it; it < n_quads; it += it_stride) {
+          for (int s = 0; s < kNumSteps; ++s) {
+            const int n = step_nchunks(s);
+            const uint32_t idesc = (s == 9) ? idesc128 : idesc256;
+            int ia = 0, ib = 0;
+            while (ib < n) {
+              const bool do_a = (ia < n) && (ia - ib < kLead2);
+              const int slot = do_a ? 0 : 1;
+              const int ci = do_a ? ia : ib;
+              const uint32_t g = gchunk + (uint32_t)ci;
+              const uint32_t stage = g % kStages2, phase = (g / kStages2) & 1u;
+              if (ci == 0) {
+                long long t0 = clock64();
+                mbar_wait_cluster(&bar_act[slot], act_phase[slot]);
+                t_act += clock64() - t0;
+                act_phase[slot] ^= 1;
+                tc_fence_after();
+              }
+              if (do_a) {   // first use of the chunk: both halves must have landed
+                long long t0 = clock64();
+                mbar_wait_cluster(&bar_full[stage], phase);
+                t_full += clock64() - t0;
+                tc_fence_after();
+              }
+              const int src = step_asrc(s, ci);
+              const uint32_t a_addr = sbase + (src == 0 ? kSmemPE + slot * kActChunk
+                                                        : kSmemAct + slot * 4 * kActChunk + (src - 1) * kActChunk);
+              const uint32_t b_addr = sbase + kSmemW + stage * kHalfW256;
+              const int ksteps = (s == 9 && ci == 4) ? 2 : 4;
+              const uint32_t d_tmem = tmem_base + slot * 256;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < ksteps) {
+                  uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+                  uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                  umma_bf16_2cta(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                }
+              }
+              if (do_a) {
+                if (++ia == n) umma_commit_2cta(&bar_acc[0], 3);
+              } else {
+                umma_commit_2cta(&bar_empty[stage], 3);     // second (last) use: free the stage in both CTAs
+                if (++ib == n) umma_commit_2cta(&bar_acc[1], 3);
+              }
+            }
+            gchunk += (uint32_t)n;
+          }
+        }
+        if (blockIdx.x == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
+      }
+    }
+  } else if (warp >= 4) {
+    forward_epilogue<kTrain, 2>(p, smem, bar_acc, bar_act, tmem_base, warp, tid, rank, first_it, n_quads, it_stride,
+                                smem_u32(smem + kSmemSmall2));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still signal our barriers / read our smem until it is done too
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 int check_points(const char* who, const mvip_points* pts) {
@@ -350,6 +543,12 @@ int check_points(const char* who, const mvip_points* pts) {
 
 extern "C" {
 
+int mvip_debug_profile(unsigned long long* out16) {
+  MVIP_CUDA_OK(cudaDeviceSynchronize());
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
+  return MVIP_OK;
+}
+
 size_t mvip_mlp_stash_bytes(int64_t n_points) { return (size_t)mlp::num_tiles(n_points) * mlp::kStashTileBytes; }
 
 int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, void* stash, void* stream) {
@@ -367,6 +566,21 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
   p.raw = reinterpret_cast<float4*>(raw);
   p.stash = static_cast<uint8_t*>(stash);
   p.n_tiles = mlp::num_tiles(pts->n_points);
+  if (mlp::use_cta_pairs()) {
+    const int64_t n_quads = (p.n_tiles + 3) / 4;
+    const int max_clusters = mvip_num_sms() / 2;
+    const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
+    const size_t smem2 = kSmemBytes2 + 1024;
+    if (stash) {
+      MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mlp_forward_pair_kernel<true><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(p);
+    } else {
+      MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mlp_forward_pair_kernel<false><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(p);
+    }
+    MVIP_LAUNCH_OK("mlp_forward_pair_kernel");
+    return MVIP_OK;
+  }
   const int64_t n_pairs = (p.n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < mvip_num_sms() ? n_pairs : mvip_num_sms());
   const size_t smem = kSmemBytes + 1024;
