@@ -41,14 +41,29 @@ struct ChainParams {
 __device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
 
 __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[kCStages], bar_empty[kCStages], bar_acc[2], bar_act[2];
-  __shared__ uint32_t tmem_base_s;
+  // No static shared memory in this kernel: the dynamic segment then starts 1024-byte aligned (checked below),
+  // which the 128-byte-swizzled operand tiles need, and every byte of the 227 KB is usable:
+  //   [act 128 KB][weight ring 96 KB][w_alpha, W_rgb fp32 2.5 KB][mbarriers]
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* heads_s = reinterpret_cast<float*>(smem + kCSmemBytes);          // read per row by every epilogue thread
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kCSmemBytes + 2560);
+  uint64_t* bar_empty = bar_full + kCStages;
+  uint64_t* bar_acc = bar_empty + kCStages;
+  uint64_t* bar_act = bar_acc + 2;
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bar_act + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) printf("mvip: dgrad_chain_kernel dynamic smem base %u not 1024-aligned\n", smem_u32(smem));
+    __trap();
+  }
   const int64_t n_pairs = (p.n_tiles + 1) / 2;
   const uint8_t* wT = p.packed + kFwdBytes;
+  {
+    const float* sm = reinterpret_cast<const float*>(p.packed + kSmallOff);
+    for (int i = tid; i < 256; i += kCThreads) heads_s[i] = __ldg(sm + kSmWAlpha + i);
+    for (int i = tid; i < 384; i += kCThreads) heads_s[256 + i] = __ldg(sm + kSmWRgb + i);
+  }
 
   if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0; uint32_t act_phase[2] = {0, 0};
       const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
       for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
@@ -97,16 +112,20 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
               const uint32_t b_addr = smem_u32(smem) + kCSmemW + stage * kW256;
               mbar_wait(&bar_full[stage], phase);
               tc_fence_after();
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+                  uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                  umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&bar_empty[stage]);
               }
-              umma_commit(&bar_empty[stage]);
+              __syncwarp();
               if (++stage == kCStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&bar_acc[slot]);
+            if (elect_one_sync()) umma_commit(&bar_acc[slot]);
+            __syncwarp();
           }
         }
       }
@@ -117,7 +136,6 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t bar_id = 1 + slot;
     uint8_t* act = smem + kCSmemAct + slot * 4 * kActChunk;
-    const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
     uint32_t acc_phase = 0;
 
     for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
@@ -142,16 +160,16 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
           const uint32_t m = valid ? mw[c0 >> 5] : 0u;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + c0) + j4);
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 128 + c0) + j4);
-            const float4 w2 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 256 + c0) + j4);
+            const float4 w0 = *(reinterpret_cast<const float4*>(heads_s + 256 + c0) + j4);
+            const float4 w1 = *(reinterpret_cast<const float4*>(heads_s + 256 + 128 + c0) + j4);
+            const float4 w2 = *(reinterpret_cast<const float4*>(heads_s + 256 + 256 + c0) + j4);
             v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
             v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
             v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
             v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> mask_bit_of_column(j)) & 1u) ? v[j] : 0.f;
           uint8_t* img = act + (c0 >> 6) * kActChunk;
           const int g0 = (c0 & 63) >> 3;
 #pragma unroll
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
           if (s == 1) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(small + kSmWAlpha + c0) + j4);
+              const float4 w = *(reinterpret_cast<const float4*>(heads_s + c0) + j4);
               v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + dr.w * w.x;
               v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + dr.w * w.y;
               v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + dr.w * w.z;
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> mask_bit_of_column(j)) & 1u) ? v[j] : 0.f;
           uint8_t* img = act + (c0 >> 6) * kActChunk;
           const int g0 = (c0 & 63) >> 3;
 #pragma unroll
@@ -380,8 +398,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (all lanes run the loop, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0; uint32_t drained_phase = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const WItem& itm = kItems[seg_s[sg].item];
@@ -400,6 +418,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
             const uint32_t sbase = smem_u32(smem) + stage * kWStageBytes;
             mbar_wait(&bar_full[stage], phase);
             tc_fence_after();
+            if (elect_one_sync()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {                 // 16 points per MMA
               for (int m = 0; m < itm.m_blocks; ++m) {
@@ -414,12 +433,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
                 }
               }
             }
-            first = false;
             umma_commit(&bar_empty[stage]);
+            }
+            __syncwarp();
+            first = false;
             if (++stage == kWStages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&bar_acc);
+        if (elect_one_sync()) umma_commit(&bar_acc);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -671,7 +693,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     cp.n_tiles = n_tiles;
     const int64_t n_pairs = (n_tiles + 1) / 2;
     const int grid = (int)(n_pairs < sms ? n_pairs : sms);
-    const size_t smem = kCSmemBytes + 1024;
+    const size_t smem = kCSmemBytes + 2560 + 128;
     MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
     MVIP_LAUNCH_OK("dgrad_chain_kernel");

@@ -66,6 +66,10 @@ constexpr int kDzChunks = 38;
 constexpr int kDzHidden = 0, kDzFeat = 2, kDzTrunk = 6;
 constexpr size_t kDzTileBytes = (size_t)kDzChunks * kActChunk;
 
+// ReLU mask word layout: bit of column j (0..31) inside its 32-column mask word.  The forward epilogue derives
+// the bits from packed bf16 pairs of two 16-column blocks, hence the interleave.
+__host__ __device__ inline int mask_bit_of_column(int j) { return 16 * (j & 1) + 8 * (j >> 4) + ((j & 15) >> 1); }
+
 inline int64_t num_tiles(int64_t n_points) { return (n_points + kTile - 1) / kTile; }
 
 // kernel variant switch (api.cu): CTA pairs (cta_group::2) unless MVIP_MLP_CTA_PAIRS=0

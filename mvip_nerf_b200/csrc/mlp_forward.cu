@@ -96,6 +96,48 @@ __device__ __forceinline__ void write_pe_row(uint8_t* img, int row, float x, flo
   }
 }
 
+
+// one half (4 of the 8 sixteen-byte groups) of a PE row; `half` is warp-uniform
+template <int L>
+__device__ __forceinline__ void write_pe_half(uint8_t* img, int row, float x, float y, float z, int half) {
+  float s[3][10], c[3][10];
+  pe_axis(x, L, s[0], c[0]);
+  pe_axis(y, L, s[1], c[1]);
+  pe_axis(z, L, s[2], c[2]);
+  const float in[3] = {x, y, z};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h == half) {
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        const int g = 4 * h + gg;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = g * 8 + e;
+          float val = 0.f;
+          if (i < 3) val = in[i];
+          else if (i < 3 + 6 * L) {
+            const int t = i - 3, k = t / 6, r6 = t % 6, d = r6 % 3;
+            val = (r6 >= 3) ? c[d][k] : s[d][k];
+          }
+          v[e] = val;
+        }
+        *reinterpret_cast<uint4*>(img + chunk_off16(row, g)) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
+    }
+  }
+}
+
+// bf16x2 pack with fused ReLU (negative -> +0)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+
 // ===================== epilogue warpgroups (shared by the 1-CTA and the CTA-pair kernels) =====================
 // Warps 4..11: warpgroup `slot` owns tile slot `slot`; thread r <-> row r of the tile <-> TMEM lane r.
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -219,7 +261,7 @@ __device__ __forceinline__ void forward_epilogue(const Params& p, uint8_t* smem,
           if (s != 8) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (kTrain) mword |= (v[j] > 0.f ? 1u : 0u) << j;
+              if (kTrain) mword |= (v[j] > 0.f ? 1u : 0u) << mask_bit_of_column(j);
               v[j] = fmaxf(v[j], 0.f);
             }
           }
@@ -331,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0; uint32_t act_phase[2] = {0, 0};
       const uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
       const uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
@@ -352,18 +394,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
               const int ksteps = (s == 9 && ci == 4) ? 2 : 4;  // viewdir PE has 27 (<32) channels
               mbar_wait(&bar_full[stage], phase);
               tc_fence_after();
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (kk < ksteps) {
-                  uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                  uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                  umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < ksteps) {
+                    uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+                    uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                    umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                  }
                 }
+                umma_commit(&bar_empty[stage]);
               }
-              umma_commit(&bar_empty[stage]);
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&bar_acc[slot]);
+            if (elect_one_sync()) umma_commit(&bar_acc[slot]);
+            __syncwarp();
           }
         }
       }
@@ -390,14 +436,202 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
 //     "weights landed" (relay warp) and "A operand ready" (remote mbarrier arrive) signals, and
 //     tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
 // =================================================================================================
+
+// ===================== CTA-pair epilogue: 8 warps per tile slot =====================
+// Warp e = warp-4: slot = e/8, TMEM lane quarter q = e%4 (must equal warp%4), column half hcol = (e%8)/4.
+// Thread (q, lane, hcol) owns row r = 32q+lane and output columns [hcol*W/2, (hcol+1)*W/2) of every layer;
+// TMEM loads are double-buffered (the next 32 columns are in flight while the current ones are processed).
+constexpr int kThreads2 = 640;
 constexpr int kStages2 = 3;
 constexpr int kLead2 = kStages2 - 1;                              // chunks slot 0 may run ahead of slot 1
 constexpr uint32_t kHalfW256 = kW256 / 2;
 constexpr uint32_t kSmemSmall2 = kSmemW + kStages2 * kHalfW256;   // fp32 tail of the packed blob (12,320 B)
-constexpr uint32_t kSmemBytes2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // 225,280
+constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
+constexpr uint32_t kSmemBytes2 = kSmemXch2 + 2 * 2048;            // 229,376
 
 template <bool kTrain>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_forward_pair_kernel(const Params p) {
+__device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
+                                              uint32_t tmem_base, int warp, int lane, uint32_t cta_rank,
+                                              int64_t first_it, int64_t n_iters, int64_t it_stride) {
+  const int e = warp - 4, slot = e >> 3, q = e & 3, hcol = (e & 7) >> 2;
+  const int r = q * 32 + lane;
+  const bool leader = (e & 7) == 0 && lane == 0;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t bar_id = 1 + slot;
+  uint8_t* act = smem + kSmemAct + slot * 4 * kActChunk;
+  uint8_t* pe = smem + kSmemPE + slot * kActChunk;
+  const uint32_t small_s = smem_u32(smem + kSmemSmall2);
+  float4* xch = reinterpret_cast<float4*>(smem + kSmemXch2 + slot * 2048) + r;
+  uint32_t acc_phase = 0;
+  long long t_accw = 0, t_work = 0, t_loop = 0, t_ldw = 0, t_begin = clock64();
+
+  auto act_arrive = [&]() {
+    if (cta_rank == 0) mbar_arrive(&bar_act[slot]);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[slot]), 0));
+  };
+
+  for (int64_t it = first_it; it < n_iters; it += it_stride) {
+    const int64_t tile = 4 * it + 2 * slot + (int64_t)cta_rank;
+    const bool tile_valid = tile < p.n_tiles;
+    const int64_t g = tile * kTile + r;
+    const bool valid = tile_valid && g < p.pts.n_points;
+    uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
+
+    float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (valid) {
+      if (p.pts.rays) {
+        const int64_t ray = g / p.pts.n_samples;
+        const float* rp = p.pts.rays + ray * p.pts.ray_stride;
+        const float zv = __ldg(p.pts.z_vals + g);
+        px = __fadd_rn(__ldg(rp + 0), __fmul_rn(__ldg(rp + 3), zv));   // pts = o + d*z   run.py:1783
+        py = __fadd_rn(__ldg(rp + 1), __fmul_rn(__ldg(rp + 4), zv));
+        pz = __fadd_rn(__ldg(rp + 2), __fmul_rn(__ldg(rp + 5), zv));
+        vx = __ldg(rp + p.pts.viewdir_offset);
+        vy = __ldg(rp + p.pts.viewdir_offset + 1);
+        vz = __ldg(rp + p.pts.viewdir_offset + 2);
+      } else {
+        const float* pp = p.pts.pts + g * p.pts.pts_stride;
+        const float* dp = p.pts.dirs + g * p.pts.dirs_stride;
+        px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+        vx = __ldg(dp); vy = __ldg(dp + 1); vz = __ldg(dp + 2);
+      }
+    }
+    if (kTrain) {
+      if (leader) tma_store_wait_read0();
+      named_bar_sync(bar_id, 256);
+    }
+    write_pe_half<10>(pe, r, px, py, pz, hcol);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(bar_id, 256);
+    if (leader) {
+      act_arrive();
+      if (kTrain && tile_valid) {
+        tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
+        tma_store_commit();
+      }
+    }
+
+    float alpha_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+
+    for (int s = 0; s < kNumSteps; ++s) {
+      long long t0 = clock64();
+      mbar_wait(&bar_acc[slot], acc_phase);
+      long long t1 = clock64();
+      t_accw += t1 - t0;
+      acc_phase ^= 1;
+      tc_fence_after();
+      if (kTrain) {
+        if (leader) tma_store_wait_read0();   // earlier bulk stores finished reading act / pe
+        named_bar_sync(bar_id, 256);
+      }
+      const int half_cols = (s == 9) ? 64 : 128;
+      const int nblk = half_cols >> 4;                        // 16-column blocks: 8, or 4 for the views layer
+      const int col_base = hcol * half_cols;
+      const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
+      const uint32_t t_addr = tmem_base + lane_base + slot * 256 + col_base;
+      uint32_t buf[2][16];
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      tmem_ld16(t_addr, buf[0]);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < nblk) {
+          uint32_t (&acc)[16] = buf[b & 1];
+          long long tw0 = clock64();
+          tmem_ld_wait_on16(acc);
+          t_ldw += clock64() - tw0;
+          if (b + 1 < nblk) tmem_ld16(t_addr + 16 * (b + 1), buf[(b + 1) & 1]);
+          const int c0 = col_base + 16 * b;
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = lds_f4(small_s + (bias_i + c0 + 4 * j4) * 4);
+            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + bb.x;
+            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + bb.y;
+            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + bb.z;
+            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + bb.w;
+          }
+          if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w = lds_f4(small_s + (kSmWAlpha + c0 + 4 * j4) * 4);
+              alpha_part += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y +
+                            fmaxf(v[4 * j4 + 2], 0.f) * w.z + fmaxf(v[4 * j4 + 3], 0.f) * w.w;
+            }
+          }
+          if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w = lds_f4(small_s + (kSmWRgb + ch * 128 + c0 + 4 * j4) * 4);
+                rgb_part[ch] += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y +
+                                fmaxf(v[4 * j4 + 2], 0.f) * w.z + fmaxf(v[4 * j4 + 3], 0.f) * w.w;
+              }
+            }
+          }
+          if (s != 9 || kTrain) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pk[i] = (s == 8) ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+            if (kTrain && s != 8) {
+              // ReLU mask bits of these 16 columns (non-zero bf16 halves), layout: mask_bit_of_column() in mlp_common.cuh
+              uint32_t m = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) m |= (((pk[i] + 0x7FFF7FFFu) >> 15) & 0x00010001u) << i;
+              mw[b >> 1] |= m << (8 * (b & 1));
+            }
+            // next layer's A operand (and the stash image): 16 columns = 2 x 16-byte groups of chunk c0/64
+            uint8_t* img = act + (c0 >> 6) * kActChunk;
+            const int g0 = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      if (kTrain && s != 8 && tile_valid) {
+        uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32);
+        if (s == 9) *reinterpret_cast<uint2*>(mrow + 2 * hcol) = make_uint2(mw[0], mw[1]);
+        else *reinterpret_cast<uint4*>(mrow + 4 * hcol) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+      }
+      if (s == 8) write_pe_half<4>(pe, r, vx, vy, vz, hcol);  // PE(viewdir) replaces PE(pts): L5 has consumed it
+      if (s == 9 && hcol == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
+      t_loop += clock64() - t1;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 256);
+      t_work += clock64() - t1;
+      if (s == 9 && hcol == 0 && valid) {
+        const float4 o = *xch;
+        p.raw[g] = make_float4(rgb_part[0] + o.x + lds_f1(small_s + kSmBRgb * 4), rgb_part[1] + o.y + lds_f1(small_s + (kSmBRgb + 1) * 4),
+                               rgb_part[2] + o.z + lds_f1(small_s + (kSmBRgb + 2) * 4), alpha_part + o.w + lds_f1(small_s + kSmBAlpha * 4));
+      }
+      if (leader) {
+        if (s < 9) act_arrive();
+        if (kTrain && tile_valid) {
+          if (s < 8) {
+            for (int j = 0; j < 4; ++j)
+              tma_store_1d(stash_tile + (size_t)(kStashH + 4 * s + j) * kActChunk, act + j * kActChunk, kActChunk);
+          } else if (s == 8) {
+            for (int j = 0; j < 4; ++j)
+              tma_store_1d(stash_tile + (size_t)(kStashFeat + j) * kActChunk, act + j * kActChunk, kActChunk);
+            tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
+          } else {
+            for (int j = 0; j < 2; ++j)
+              tma_store_1d(stash_tile + (size_t)(kStashHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+  }
+  if (kTrain && leader) tma_store_wait_all0();
+  if (blockIdx.x == 0 && warp == 4 && lane == 0) { g_prof[3] = t_accw; g_prof[4] = t_work; g_prof[5] = clock64() - t_begin; g_prof[7] = t_loop; g_prof[8] = t_ldw; }
+}
+
+template <bool kTrain>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_forward_pair_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar_full[kStages2], bar_empty[kStages2], bar_acc[2], bar_act[2];
@@ -420,7 +654,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_for
   {  // biases + alpha / rgb heads -> shared memory (read ~10^3 times per tile by the epilogue warps)
     const float4* src = reinterpret_cast<const float4*>(p.packed + kSmallOff);
     float4* dst = reinterpret_cast<float4*>(smem + kSmemSmall2);
-    for (int i = tid; i < kSmallFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kSmallFloats / 4; i += kThreads2) dst[i] = __ldg(src + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -443,8 +677,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_for
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      if (rank == 1) {
+    {
+      if (rank == 1 && lane != 0) {
+        // only lane 0 relays
+      } else if (rank == 1) {
         // ===================== relay: tell the leader that this CTA's half has landed =====================
         int stage = 0; uint32_t phase = 0;
         for (int64_t it = first_it; it < n_quads; it += it_stride) {
@@ -475,14 +711,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_for
               const uint32_t stage = g % kStages2, phase = (g / kStages2) & 1u;
               if (ci == 0) {
                 long long t0 = clock64();
-                mbar_wait_cluster(&bar_act[slot], act_phase[slot]);
+                mbar_wait(&bar_act[slot], act_phase[slot]);
                 t_act += clock64() - t0;
                 act_phase[slot] ^= 1;
                 tc_fence_after();
               }
               if (do_a) {   // first use of the chunk: both halves must have landed
                 long long t0 = clock64();
-                mbar_wait_cluster(&bar_full[stage], phase);
+                mbar_wait(&bar_full[stage], phase);
                 t_full += clock64() - t0;
                 tc_fence_after();
               }
@@ -492,30 +728,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_for
               const uint32_t b_addr = sbase + kSmemW + stage * kHalfW256;
               const int ksteps = (s == 9 && ci == 4) ? 2 : 4;
               const uint32_t d_tmem = tmem_base + slot * 256;
+              if (do_a) ++ia; else ++ib;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (kk < ksteps) {
-                  uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                  uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                  umma_bf16_2cta(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < ksteps) {
+                    uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+                    uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                    umma_bf16_2cta(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                  }
+                }
+                if (do_a) {
+                  if (ia == n) umma_commit_2cta(&bar_acc[0], 3);
+                } else {
+                  umma_commit_2cta(&bar_empty[stage], 3);     // second (last) use: free the stage in both CTAs
+                  if (ib == n) umma_commit_2cta(&bar_acc[1], 3);
                 }
               }
-              if (do_a) {
-                if (++ia == n) umma_commit_2cta(&bar_acc[0], 3);
-              } else {
-                umma_commit_2cta(&bar_empty[stage], 3);     // second (last) use: free the stage in both CTAs
-                if (++ib == n) umma_commit_2cta(&bar_acc[1], 3);
-              }
+              __syncwarp();
             }
             gchunk += (uint32_t)n;
           }
         }
-        if (blockIdx.x == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
+        if (blockIdx.x == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
       }
     }
   } else if (warp >= 4) {
-    forward_epilogue<kTrain, 2>(p, smem, bar_acc, bar_act, tmem_base, warp, tid, rank, first_it, n_quads, it_stride,
-                                smem_u32(smem + kSmemSmall2));
+    pair_epilogue<kTrain>(p, smem, bar_acc, bar_act, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
   }
 
   tc_fence_before();
@@ -573,10 +812,10 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
     const size_t smem2 = kSmemBytes2 + 1024;
     if (stash) {
       MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mlp_forward_pair_kernel<true><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(p);
+      mlp_forward_pair_kernel<true><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
     } else {
       MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      mlp_forward_pair_kernel<false><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(p);
+      mlp_forward_pair_kernel<false><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
     }
     MVIP_LAUNCH_OK("mlp_forward_pair_kernel");
     return MVIP_OK;

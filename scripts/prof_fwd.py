@@ -20,4 +20,5 @@ for stash in (False, True):
     n = pts.shape[0]
     print("stash=%s P=%d  %.3f ms  %.1f TF" % (stash, n, a.elapsed_time(b), n * 1186816 / a.elapsed_time(b) / 1e9))
     print("  mma: act-wait %.1f%%  weight-wait %.1f%%  total %d cyc" % (100 * v[0] / max(v[2], 1), 100 * v[1] / max(v[2], 1), v[2]))
+    print("  epi loop-only per step %.0f cyc, of which tmem-ld wait %.0f cyc" % (v[7] / max(1, (n / 128 / 4 / 74) * 10), v[8] / max(1, (n / 128 / 4 / 74) * 10)))
     print("  epi(slot0): acc-wait %.1f%%  work %.1f%%  total %d cyc;  work per layer-step %.0f cyc" % (100 * v[3] / max(v[5], 1), 100 * v[4] / max(v[5], 1), v[5], v[4] / max(1, (n / 128 / 4 / 74) * 10)))

@@ -147,7 +147,9 @@ def decode_stash(stash, P):
         out["vpe"].append(dec[37])
         out["hidden"].append(np.concatenate(list(dec[38:40]), -1))
         m = tb[40 * 16384:].view(np.uint32).reshape(9, 128, 8)
-        bits = ((m[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(9, 128, 256)
+        j = np.arange(32)
+        bitpos = (16 * (j & 1) + 8 * (j >> 4) + ((j & 15) >> 1)).astype(np.uint32)     # mask_bit_of_column (mlp_common.cuh)
+        bits = ((m[..., None] >> bitpos) & 1).astype(bool).reshape(9, 128, 256)
         out["mask"].append(bits)
     res = {"pe": np.concatenate(out["pe"], 0)[:P], "feat": np.concatenate(out["feat"], 0)[:P],
            "vpe": np.concatenate(out["vpe"], 0)[:P], "hidden": np.concatenate(out["hidden"], 0)[:P],
