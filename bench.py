@@ -68,7 +68,7 @@ def synth_rays_np(n, seed):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -89,7 +89,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: samples before this instant are ignored"""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -101,7 +105,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t_end = time.time()
+        t0 = getattr(self, "t0", 0.0)
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t_end:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -222,6 +230,10 @@ def run_ours(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(3):                         # nvidia-smi needs ~100 ms to start streaming: keep the GPUs busy meanwhile
+        step(d_rays, d_target)                 # (all ranks: the step contains a collective)
+    torch.cuda.synchronize()
+    clocks.mark()
     ops.kernel_timer.enable(True)
     l0 = ops.launch_count
     ms_total = timed(lambda: step(d_rays, d_target), a.steps)
@@ -329,7 +341,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
