@@ -444,6 +444,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
 constexpr int kThreads2 = 640;
 constexpr int kStages2 = 3;
 constexpr int kLead2 = kStages2 - 1;                              // chunks slot 0 may run ahead of slot 1
+#ifndef MVIP_PAIR_SHARE
+#define MVIP_PAIR_SHARE 0
+#endif
+constexpr bool kShare2 = MVIP_PAIR_SHARE != 0;   // share a staged weight chunk between the two tile slots (skewed order)
 constexpr uint32_t kHalfW256 = kW256 / 2;
 constexpr uint32_t kSmemSmall2 = kSmemW + kStages2 * kHalfW256;   // fp32 tail of the packed blob (12,320 B)
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
@@ -532,20 +536,33 @@ __device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, ui
       const uint32_t t_addr = tmem_base + lane_base + slot * 256 + col_base;
       uint32_t buf[2][16];
       uint32_t mw[4] = {0u, 0u, 0u, 0u};
+#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 2
+      const int c0_dummy = (int)acc_phase + r;
+#else
       tmem_ld16(t_addr, buf[0]);
+#endif
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
         if (b < nblk) {
           uint32_t (&acc)[16] = buf[b & 1];
+#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 2
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = (uint32_t)(c0_dummy + i);
+#else
           long long tw0 = clock64();
           tmem_ld_wait_on16(acc);
           t_ldw += clock64() - tw0;
           if (b + 1 < nblk) tmem_ld16(t_addr + 16 * (b + 1), buf[(b + 1) & 1]);
+#endif
           const int c0 = col_base + 16 * b;
           float v[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
+#ifdef MVIP_EXP_NOBIAS
+            const float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
             const float4 bb = lds_f4(small_s + (bias_i + c0 + 4 * j4) * 4);
+#endif
             v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + bb.x;
             v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + bb.y;
             v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + bb.z;
@@ -570,11 +587,26 @@ __device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, ui
               }
             }
           }
+#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 1
+          {  // experiment: TMEM drain only
+            uint32_t x = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x ^= acc[i];
+            if (x == 0x12345678u) mw[0] ^= x;
+          }
+          if (false) {
+            uint32_t pk[8];
+#else
           if (s != 9 || kTrain) {
             uint32_t pk[8];
+#endif
 #pragma unroll
             for (int i = 0; i < 8; ++i)
+#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 4
+              pk[i] = __float_as_uint(v[2 * i]) ^ __float_as_uint(v[2 * i + 1]);
+#else
               pk[i] = (s == 8) ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+#endif
             if (kTrain && s != 8) {
               // ReLU mask bits of these 16 columns (non-zero bf16 halves), layout: mask_bit_of_column() in mlp_common.cuh
               uint32_t m = 0;
@@ -585,8 +617,13 @@ __device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, ui
             // next layer's A operand (and the stash image): 16 columns = 2 x 16-byte groups of chunk c0/64
             uint8_t* img = act + (c0 >> 6) * kActChunk;
             const int g0 = (c0 & 63) >> 3;
+#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 3
+            if ((pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]) == 0x12345678u) mw[0] ^= 1u;
+            if (mw[0] == 0x9999u) *reinterpret_cast<uint4*>(img + chunk_off16(r, g0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#else
             *reinterpret_cast<uint4*>(img + chunk_off16(r, g0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#endif
           }
         }
       }
@@ -667,12 +704,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t it = first_it; it < n_quads; it += it_stride) {
-        for (int c = 0; c < kFwdChunks; ++c) {
-          const uint32_t half = fwd_chunk_bytes(c) / 2;
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], half);
-          tma_load_1d(smem + kSmemW + stage * kHalfW256, p.packed + fwd_chunk_off(c) + rank * half, half, &bar_full[stage]);
-          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        int cbase = 0;
+        for (int s = 0; s < kNumSteps; ++s) {
+          const int n = step_nchunks(s);
+          for (int pass = 0; pass < (kShare2 ? 1 : 2); ++pass) {     // unshared: once per tile slot
+            for (int ci = 0; ci < n; ++ci) {
+              const int c = cbase + ci;
+              const uint32_t half = fwd_chunk_bytes(c) / 2;
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&bar_full[stage], half);
+              tma_load_1d(smem + kSmemW + stage * kHalfW256, p.packed + fwd_chunk_off(c) + rank * half, half, &bar_full[stage]);
+              if (++stage == kStages2) { stage = 0; phase ^= 1; }
+            }
+          }
+          cbase += n;
         }
       }
     }
@@ -684,7 +729,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
         // ===================== relay: tell the leader that this CTA's half has landed =====================
         int stage = 0; uint32_t phase = 0;
         for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          for (int c = 0; c < kFwdChunks; ++c) {
+          for (int c = 0; c < (kShare2 ? kFwdChunks : 2 * kFwdChunks); ++c) {
             mbar_wait(&bar_full[stage], phase);
             mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[stage]), 0));
             if (++stage == kStages2) { stage = 0; phase ^= 1; }
@@ -704,10 +749,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
             const uint32_t idesc = (s == 9) ? idesc128 : idesc256;
             int ia = 0, ib = 0;
             while (ib < n) {
-              const bool do_a = (ia < n) && (ia - ib < kLead2);
+              const bool do_a = (ia < n) && (kShare2 ? (ia - ib < kLead2) : true);
               const int slot = do_a ? 0 : 1;
               const int ci = do_a ? ia : ib;
-              const uint32_t g = gchunk + (uint32_t)ci;
+              const uint32_t g = gchunk + (uint32_t)ci + ((!kShare2 && !do_a) ? (uint32_t)n : 0u);
               const uint32_t stage = g % kStages2, phase = (g / kStages2) & 1u;
               if (ci == 0) {
                 long long t0 = clock64();
@@ -716,7 +761,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
                 act_phase[slot] ^= 1;
                 tc_fence_after();
               }
-              if (do_a) {   // first use of the chunk: both halves must have landed
+              if (do_a || !kShare2) {   // first use of the staged chunk: both halves must have landed
                 long long t0 = clock64();
                 mbar_wait(&bar_full[stage], phase);
                 t_full += clock64() - t0;
@@ -738,16 +783,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
                     umma_bf16_2cta(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
                   }
                 }
+                if (!do_a || !kShare2) umma_commit_2cta(&bar_empty[stage], 3);   // last use: free the stage in both CTAs
                 if (do_a) {
                   if (ia == n) umma_commit_2cta(&bar_acc[0], 3);
                 } else {
-                  umma_commit_2cta(&bar_empty[stage], 3);     // second (last) use: free the stage in both CTAs
                   if (ib == n) umma_commit_2cta(&bar_acc[1], 3);
                 }
               }
               __syncwarp();
             }
-            gchunk += (uint32_t)n;
+            gchunk += (uint32_t)(kShare2 ? n : 2 * n);
           }
         }
         if (blockIdx.x == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
