@@ -522,7 +522,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 v, float (&f)[8]) {
 // dW_alpha[j] = sum_p d_alpha[p] h8[p][j];  dW_rgb[c][j] = sum_p d_rgb[p][c] hidden[p][j];  db = sum_p d_raw[p].
 // Thread (cg = tid%32, rg = tid/32) owns the 8 features [8cg, 8cg+8) of rows [16rg, 16rg+16) of every tile of
 // its block: one 16-byte load per (row, operand), eight lanes covering one 128-byte row segment.
-__global__ void __launch_bounds__(256) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
+__global__ void __launch_bounds__(256, 2) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
                                                          int64_t n_points, int64_t n_tiles, float* __restrict__ out) {
   __shared__ float red[8][kHeadFloats];
   const int tid = threadIdx.x, cg = tid & 31, rg = tid >> 5;
@@ -533,23 +533,30 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const float4* __restric
   const uint32_t hid_off = (uint32_t)(kStashHidden + ((cg & 15) >> 3)) * kActChunk;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const uint8_t* tile = stash + (size_t)t * kStashTileBytes;
-#pragma unroll 8
+    // all loads of the tile first (32 independent 16-byte requests per thread), then the FMAs
+    uint4 hv[16], xv[16];
+    float4 dv[16];
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int row = rg * 16 + i;
-      const int64_t g = t * kTile + row;
-      const float4 d = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
       const uint32_t o = chunk_off16(row, cg & 7);
-      float h[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(tile + h8_off + o)), h);
+      hv[i] = __ldg(reinterpret_cast<const uint4*>(tile + h8_off + o));
+      xv[i] = (cg < 16) ? __ldg(reinterpret_cast<const uint4*>(tile + hid_off + o)) : make_uint4(0u, 0u, 0u, 0u);
+      const int64_t g = t * kTile + row;
+      dv[i] = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) aa[e] += d.w * h[e];
-      if (cg < 16) {
-        float x[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(tile + hid_off + o)), x);
+    for (int i = 0; i < 16; ++i) {
+      const float4 d = dv[i];
+      float h[8], x[8];
+      unpack_bf16x8(hv[i], h);
+      unpack_bf16x8(xv[i], x);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ar[e] += d.x * x[e]; ag[e] += d.y * x[e]; ab[e] += d.z * x[e]; }
+      for (int e = 0; e < 8; ++e) {
+        aa[e] += d.w * h[e];
+        ar[e] += d.x * x[e]; ag[e] += d.y * x[e]; ab[e] += d.z * x[e];
       }
-      if (cg == 31) { ds.x += d.x; ds.y += d.y; ds.z += d.z; ds.w += d.w; }
+      ds.x += d.x; ds.y += d.y; ds.z += d.z; ds.w += d.w;
     }
   }
 #pragma unroll
