@@ -425,61 +425,152 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
 
 
 // =================================================================================================
-// CTA-pair variant (cta_group::2): two SMs of a cluster cooperate on 256-point MMAs.
-//   * each CTA keeps its own two 128-point tile slots, TMEM accumulators and epilogue warps;
-//   * a weight chunk is split by output rows: each CTA streams only its half (16 KB) into a 3-stage ring,
-//     and a staged chunk is used by BOTH tile slots before it is released -> 1/4 of the L2->smem weight
-//     traffic of the 1-CTA kernel, with 2x the prefetch depth;
-//   * slot 0 runs up to 2 chunks ahead of slot 1 ("A0 A1 B0 A2 B1 A3 B2 B3"), so one slot's epilogue still
-//     overlaps the other slot's MMAs;
-//   * only the leader CTA (rank 0) issues tcgen05.mma.cta_group::2; its barriers collect the peer's
-//     "weights landed" (relay warp) and "A operand ready" (remote mbarrier arrive) signals, and
-//     tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs.
+// CTA-pair kernel (cta_group::2), activations resident in TENSOR MEMORY ("TS" MMAs: A from TMEM, B from smem).
+//
+// Measured on B200 (scripts/ubench/umma_bench.cu): a 128xNx16 bf16 MMA with A in shared memory takes 171 cycles at N = 256
+// (75 % of the tensor-pipe floor, the cuBLAS level) and 107 at N = 128; with A in TMEM it takes 138 / 74 cycles (93 % / 87 %).
+// So the layer outputs never go to shared memory: the epilogue packs them to bf16 and writes them straight back
+// to TMEM as the next layer's A operand.
+//
+//   * a cluster of two CTAs works on four 128-point tiles: each CTA owns two tile slots X, Y and the MMAs are
+//     256 (2 x 128 points) x 128 x 16: one N-half of a layer at a time;
+//   * TMEM per CTA (512 columns): slot T at column 256 T: [0,128) = A operand (256 bf16 features, two per column),
+//     [128,256) = fp32 accumulator of one N-half (128 output features);
+//   * issue order per layer: X.h0, Y.h0, X.h1, Y.h1.  While the tensor pipe works on Y, X's eight epilogue warps
+//     drain X's accumulator half (tcgen05.ld -> +bias, ReLU, bf16 pack).  The h0 result is HELD IN REGISTERS
+//     (32 per thread) because X.h1 still reads the old A operand; after X.h1 completes both halves are written
+//     to the A columns (tcgen05.st) and X's next layer can start: no tensor-pipe bubble as long as
+//     the drain of one half (~600 cycles) fits into the MMAs of the other slot's half (~1200 cycles);
+//   * weights: a ring stage holds this CTA's 64 rows of one (layer, N-half, 64-wide K chunk) = 8 KB; a stage
+//     is used by X and then Y before it is released, so every weight byte is fetched once per four tiles
+//     (1/4 of the L2 -> smem traffic of the 1-CTA kernel) and the ring is 12 deep;
+//   * PE(pts) / PE(viewdir) live in shared memory (one 16 KB image per slot) and enter L0, L5 and the views layer as
+//     ordinary smem-A MMAs accumulating into the same TMEM columns;
+//   * training: the packed bf16 rows are additionally staged in shared memory (32 KB per slot) and bulk-stored to the
+//     activation stash; ReLU masks are derived from the packed words.
+//   * only the leader CTA (rank 0) issues MMAs; its barriers collect the peer's "weights landed" (relay warp)
+//     and "A operand ready / accumulator drained" (remote mbarrier arrive) signals, and tcgen05.commit
+//     multicasts "stage free" / "accumulator full" to both CTAs.
 // =================================================================================================
-
-// ===================== CTA-pair epilogue: 8 warps per tile slot =====================
-// Warp e = warp-4: slot = e/8, TMEM lane quarter q = e%4 (must equal warp%4), column half hcol = (e%8)/4.
-// Thread (q, lane, hcol) owns row r = 32q+lane and output columns [hcol*W/2, (hcol+1)*W/2) of every layer;
-// TMEM loads are double-buffered (the next 32 columns are in flight while the current ones are processed).
 constexpr int kThreads2 = 640;
-constexpr int kStages2 = 3;
-constexpr int kLead2 = kStages2 - 1;                              // chunks slot 0 may run ahead of slot 1
-#ifndef MVIP_PAIR_SHARE
-#define MVIP_PAIR_SHARE 0
-#endif
-constexpr bool kShare2 = MVIP_PAIR_SHARE != 0;   // share a staged weight chunk between the two tile slots (skewed order)
-constexpr uint32_t kHalfW256 = kW256 / 2;
-constexpr uint32_t kSmemSmall2 = kSmemW + kStages2 * kHalfW256;   // fp32 tail of the packed blob (12,320 B)
+constexpr int kStages2 = 12;
+constexpr uint32_t kStageBytes2 = 64 * 128;                              // 64 weight rows x 64 k (bf16)
+constexpr uint32_t kSmemPE2 = 0;                                         // pe[2]: 2 x 16 KB
+constexpr uint32_t kSmemW2 = 2 * kActChunk;                              // weight ring
+constexpr uint32_t kSmemSmall2 = kSmemW2 + kStages2 * kStageBytes2;      // fp32 tail of the packed blob (12,320 B)
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
-constexpr uint32_t kSmemBytes2 = kSmemXch2 + 2 * 2048;            // 229,376
+constexpr uint32_t kSmemStg2 = kSmemXch2 + 2 * 2048;                     // stash staging: 2 slots x 2 chunk images (train)
+constexpr uint32_t kSmemBytes2Infer = kSmemStg2;
+constexpr uint32_t kSmemBytes2Train = kSmemStg2 + 4 * kActChunk;         // 214,016
+constexpr int kFillsPerIter2 = 2 * (1 + 4 * 4 + 5 + 2 * 4 + 4) + 5;      // ring stages consumed per tile quad = 73
+
+// One accumulator half (this thread: row r, 64 of its 128 columns) -> +bias, (ReLU), bf16 pairs in pk[32].
+// kStep: 0 = trunk layer (ReLU), 1 = layer 7 (ReLU + alpha head), 2 = feature layer (no ReLU), 3 = views layer (ReLU + rgb head)
+template <bool kTrain, int kKind, int kHalf>
+__device__ __forceinline__ void drain_half(uint32_t tD, uint32_t small_s, int bias_i, int col0, uint32_t (&pk)[32],
+                                           uint32_t (&mw)[4], float& alpha_part, float (&rgb_part)[3]) {
+  uint32_t buf[2][16];
+  tmem_ld16(tD, buf[0]);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    uint32_t (&acc)[16] = buf[b & 1];
+    tmem_ld_wait_on16(acc);
+    if (b + 1 < 4) tmem_ld16(tD + 16 * (b + 1), buf[(b + 1) & 1]);
+    const int c0 = col0 + 16 * b;
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 bb = lds_f4(small_s + (bias_i + c0 + 4 * j4) * 4);
+      v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + bb.x;
+      v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + bb.y;
+      v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + bb.z;
+      v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + bb.w;
+    }
+    if (kKind == 1) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 w = lds_f4(small_s + (kSmWAlpha + c0 + 4 * j4) * 4);
+        alpha_part += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y + fmaxf(v[4 * j4 + 2], 0.f) * w.z +
+                      fmaxf(v[4 * j4 + 3], 0.f) * w.w;
+      }
+    }
+    if (kKind == 3) {  // rgb head (run_nerf_helpers.py:122)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w = lds_f4(small_s + (kSmWRgb + ch * 128 + c0 + 4 * j4) * 4);
+          rgb_part[ch] += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y + fmaxf(v[4 * j4 + 2], 0.f) * w.z +
+                          fmaxf(v[4 * j4 + 3], 0.f) * w.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[8 * b + i] = (kKind == 2) ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (kTrain && kKind != 2) {
+      // ReLU mask bits of these 16 columns (non-zero bf16 halves), layout: mask_bit_of_column() in mlp_common.cuh
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m |= (((pk[8 * b + i] + 0x7FFF7FFFu) >> 15) & 0x00010001u) << i;
+      mw[2 * kHalf + (b >> 1)] |= m << (8 * (b & 1));
+    }
+  }
+}
 
 template <bool kTrain>
-__device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
-                                              uint32_t tmem_base, int warp, int lane, uint32_t cta_rank,
-                                              int64_t first_it, int64_t n_iters, int64_t it_stride) {
-  const int e = warp - 4, slot = e >> 3, q = e & 3, hcol = (e & 7) >> 2;
+__device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
+                                            uint32_t tmem_base, int warp, int lane, uint32_t cta_rank,
+                                            int64_t first_it, int64_t n_iters, int64_t it_stride) {
+  // warp e = warp-4: slot T = e/8, TMEM lane quarter q = e%4 (== warp%4), column half ch = (e%8)/4 of every accumulator half
+  const int e = warp - 4, T = e >> 3, q = e & 3, ch = (e & 7) >> 2;
   const int r = q * 32 + lane;
   const bool leader = (e & 7) == 0 && lane == 0;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  const uint32_t bar_id = 1 + slot;
-  uint8_t* act = smem + kSmemAct + slot * 4 * kActChunk;
-  uint8_t* pe = smem + kSmemPE + slot * kActChunk;
+  const uint32_t tA = tmem_base + lane_base + T * 256;    // A operand: 128 columns = 256 bf16 features
+  const uint32_t tD = tA + 128 + ch * 64;                  // this thread's 64 accumulator columns
+  const uint32_t bar_id = 1 + T;
+  uint8_t* pe = smem + kSmemPE2 + T * kActChunk;
+  uint8_t* stg_slot = smem + kSmemStg2 + T * 2 * kActChunk;
+  uint8_t* stg = stg_slot + ch * kActChunk;
   const uint32_t small_s = smem_u32(smem + kSmemSmall2);
-  float4* xch = reinterpret_cast<float4*>(smem + kSmemXch2 + slot * 2048) + r;
+  float4* xch = reinterpret_cast<float4*>(smem + kSmemXch2 + T * 2048) + r;
   uint32_t acc_phase = 0;
-  long long t_accw = 0, t_work = 0, t_loop = 0, t_ldw = 0, t_begin = clock64();
+  long long t_accw = 0, t_begin = clock64();
 
   auto act_arrive = [&]() {
-    if (cta_rank == 0) mbar_arrive(&bar_act[slot]);
-    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[slot]), 0));
+    if (cta_rank == 0) mbar_arrive(&bar_act[T]);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
+  };
+  auto wait_acc = [&]() {
+    long long t0 = clock64();
+    mbar_wait(&bar_acc[T], acc_phase);
+    t_accw += clock64() - t0;
+    acc_phase ^= 1;
+    tc_fence_after();
   };
 
   for (int64_t it = first_it; it < n_iters; it += it_stride) {
-    const int64_t tile = 4 * it + 2 * slot + (int64_t)cta_rank;
+    const int64_t tile = 4 * it + 2 * T + (int64_t)cta_rank;
     const bool tile_valid = tile < p.n_tiles;
     const int64_t g = tile * kTile + r;
     const bool valid = tile_valid && g < p.pts.n_points;
     uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
+
+    // packed bf16 rows of both column halves -> staging images -> one 32 KB bulk store into the stash
+    auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32]) {
+      if (leader) tma_store_wait_read0();       // the previous bulk store has finished reading the staging images
+      named_bar_sync(bar_id, 256);
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq)
+        *reinterpret_cast<uint4*>(stg + chunk_off16(r, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 256);
+      if (leader && tile_valid) {
+        tma_store_1d(stash_tile + (size_t)first_chunk * kActChunk, stg_slot, 2 * kActChunk);
+        tma_store_commit();
+      }
+    };
 
     float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
     if (valid) {
@@ -501,15 +592,15 @@ __device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, ui
       }
     }
     if (kTrain) {
-      if (leader) tma_store_wait_read0();
+      if (leader) tma_store_wait_read0();      // PE(viewdir) of the previous tile has been stored
       named_bar_sync(bar_id, 256);
     }
-    write_pe_half<10>(pe, r, px, py, pz, hcol);
+    write_pe_half<10>(pe, r, px, py, pz, ch);
     fence_proxy_async_smem();
     tc_fence_before();
     named_bar_sync(bar_id, 256);
     if (leader) {
-      act_arrive();
+      act_arrive();                            // L0 may start: PE ready, accumulator free
       if (kTrain && tile_valid) {
         tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
         tma_store_commit();
@@ -518,153 +609,74 @@ __device__ __forceinline__ void pair_epilogue(const Params& p, uint8_t* smem, ui
 
     float alpha_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
 
-    for (int s = 0; s < kNumSteps; ++s) {
-      long long t0 = clock64();
-      mbar_wait(&bar_acc[slot], acc_phase);
-      long long t1 = clock64();
-      t_accw += t1 - t0;
-      acc_phase ^= 1;
-      tc_fence_after();
-      if (kTrain) {
-        if (leader) tma_store_wait_read0();   // earlier bulk stores finished reading act / pe
-        named_bar_sync(bar_id, 256);
-      }
-      const int half_cols = (s == 9) ? 64 : 128;
-      const int nblk = half_cols >> 4;                        // 16-column blocks: 8, or 4 for the views layer
-      const int col_base = hcol * half_cols;
-      const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
-      const uint32_t t_addr = tmem_base + lane_base + slot * 256 + col_base;
-      uint32_t buf[2][16];
+#pragma unroll 1
+    for (int s = 0; s < 9; ++s) {
+      const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : kSmBiasFeat);
+      uint32_t pk[32];
       uint32_t mw[4] = {0u, 0u, 0u, 0u};
-#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 2
-      const int c0_dummy = (int)acc_phase + r;
-#else
-      tmem_ld16(t_addr, buf[0]);
-#endif
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b < nblk) {
-          uint32_t (&acc)[16] = buf[b & 1];
-#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 2
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = (uint32_t)(c0_dummy + i);
-#else
-          long long tw0 = clock64();
-          tmem_ld_wait_on16(acc);
-          t_ldw += clock64() - tw0;
-          if (b + 1 < nblk) tmem_ld16(t_addr + 16 * (b + 1), buf[(b + 1) & 1]);
-#endif
-          const int c0 = col_base + 16 * b;
-          float v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-#ifdef MVIP_EXP_NOBIAS
-            const float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-            const float4 bb = lds_f4(small_s + (bias_i + c0 + 4 * j4) * 4);
-#endif
-            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + bb.x;
-            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + bb.y;
-            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + bb.z;
-            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + bb.w;
-          }
-          if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 w = lds_f4(small_s + (kSmWAlpha + c0 + 4 * j4) * 4);
-              alpha_part += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y +
-                            fmaxf(v[4 * j4 + 2], 0.f) * w.z + fmaxf(v[4 * j4 + 3], 0.f) * w.w;
-            }
-          }
-          if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 w = lds_f4(small_s + (kSmWRgb + ch * 128 + c0 + 4 * j4) * 4);
-                rgb_part[ch] += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y +
-                                fmaxf(v[4 * j4 + 2], 0.f) * w.z + fmaxf(v[4 * j4 + 3], 0.f) * w.w;
-              }
-            }
-          }
-#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 1
-          {  // experiment: TMEM drain only
-            uint32_t x = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x ^= acc[i];
-            if (x == 0x12345678u) mw[0] ^= x;
-          }
-          if (false) {
-            uint32_t pk[8];
-#else
-          if (s != 9 || kTrain) {
-            uint32_t pk[8];
-#endif
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 4
-              pk[i] = __float_as_uint(v[2 * i]) ^ __float_as_uint(v[2 * i + 1]);
-#else
-              pk[i] = (s == 8) ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
-#endif
-            if (kTrain && s != 8) {
-              // ReLU mask bits of these 16 columns (non-zero bf16 halves), layout: mask_bit_of_column() in mlp_common.cuh
-              uint32_t m = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) m |= (((pk[i] + 0x7FFF7FFFu) >> 15) & 0x00010001u) << i;
-              mw[b >> 1] |= m << (8 * (b & 1));
-            }
-            // next layer's A operand (and the stash image): 16 columns = 2 x 16-byte groups of chunk c0/64
-            uint8_t* img = act + (c0 >> 6) * kActChunk;
-            const int g0 = (c0 & 63) >> 3;
-#if defined(MVIP_EXP_MODE) && MVIP_EXP_MODE == 3
-            if ((pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]) == 0x12345678u) mw[0] ^= 1u;
-            if (mw[0] == 0x9999u) *reinterpret_cast<uint4*>(img + chunk_off16(r, g0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-#else
-            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-#endif
-          }
+      // ---- N-half 0: drain, keep the packed result in registers (the old A operand is still being read by half 1)
+      wait_acc();
+      if (s == 7) drain_half<kTrain, 1, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+      else if (s == 8) drain_half<kTrain, 2, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+      else drain_half<kTrain, 0, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+      tc_fence_before();
+      named_bar_sync(bar_id, 256);
+      if (leader) act_arrive();                // accumulator drained: half 1 may be issued
+      if (kTrain) stage_out((s < 8 ? kStashH + 4 * s : kStashFeat), pk);
+      // ---- N-half 1: the MMAs of this layer are complete -> overwrite the A operand
+      wait_acc();
+      tmem_st32(tA + ch * 32, pk);
+      if (s == 7) drain_half<kTrain, 1, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+      else if (s == 8) drain_half<kTrain, 2, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+      else drain_half<kTrain, 0, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+      tmem_st32(tA + 64 + ch * 32, pk);
+      if (s == 8) {                            // PE(viewdir) replaces PE(pts): L5 has consumed it
+        write_pe_half<4>(pe, r, vx, vy, vz, ch);
+        fence_proxy_async_smem();
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      named_bar_sync(bar_id, 256);
+      if (leader) {
+        act_arrive();                          // next layer's A operand complete, accumulator drained
+        if (kTrain && s == 8 && tile_valid) {
+          tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
+          tma_store_commit();
         }
       }
-      if (kTrain && s != 8 && tile_valid) {
-        uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32);
-        if (s == 9) *reinterpret_cast<uint2*>(mrow + 2 * hcol) = make_uint2(mw[0], mw[1]);
-        else *reinterpret_cast<uint4*>(mrow + 4 * hcol) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+      if (kTrain) {
+        stage_out((s < 8 ? kStashH + 4 * s : kStashFeat) + 2, pk);
+        if (s != 8 && tile_valid) {
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)s * 128 + r) * 32);
+          *reinterpret_cast<uint2*>(mrow + 2 * ch) = make_uint2(mw[0], mw[1]);
+          *reinterpret_cast<uint2*>(mrow + 4 + 2 * ch) = make_uint2(mw[2], mw[3]);
+        }
       }
-      if (s == 8) write_pe_half<4>(pe, r, vx, vy, vz, hcol);  // PE(viewdir) replaces PE(pts): L5 has consumed it
-      if (s == 9 && hcol == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
-      t_loop += clock64() - t1;
+    }
+    {  // ---- views layer: one N-half of 128 columns, then the rgb head; raw = (rgb, alpha)
+      uint32_t pk[32];
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      wait_acc();
+      drain_half<kTrain, 3, 0>(tD, small_s, kSmBiasViews, ch * 64, pk, mw, alpha_part, rgb_part);
+      if (ch == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
       tc_fence_before();
-      fence_proxy_async_smem();
       named_bar_sync(bar_id, 256);
-      t_work += clock64() - t1;
-      if (s == 9 && hcol == 0 && valid) {
+      if (ch == 0 && valid) {
         const float4 o = *xch;
         p.raw[g] = make_float4(rgb_part[0] + o.x + lds_f1(small_s + kSmBRgb * 4), rgb_part[1] + o.y + lds_f1(small_s + (kSmBRgb + 1) * 4),
                                rgb_part[2] + o.z + lds_f1(small_s + (kSmBRgb + 2) * 4), alpha_part + o.w + lds_f1(small_s + kSmBAlpha * 4));
       }
-      if (leader) {
-        if (s < 9) act_arrive();
-        if (kTrain && tile_valid) {
-          if (s < 8) {
-            for (int j = 0; j < 4; ++j)
-              tma_store_1d(stash_tile + (size_t)(kStashH + 4 * s + j) * kActChunk, act + j * kActChunk, kActChunk);
-          } else if (s == 8) {
-            for (int j = 0; j < 4; ++j)
-              tma_store_1d(stash_tile + (size_t)(kStashFeat + j) * kActChunk, act + j * kActChunk, kActChunk);
-            tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
-          } else {
-            for (int j = 0; j < 2; ++j)
-              tma_store_1d(stash_tile + (size_t)(kStashHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
-          }
-          tma_store_commit();
+      if (kTrain) {
+        stage_out(kStashHidden, pk);
+        if (tile_valid) {
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)8 * 128 + r) * 32);
+          *reinterpret_cast<uint2*>(mrow + 2 * ch) = make_uint2(mw[0], mw[1]);
         }
       }
     }
   }
   if (kTrain && leader) tma_store_wait_all0();
-  if (blockIdx.x == 0 && warp == 4 && lane == 0) { g_prof[3] = t_accw; g_prof[4] = t_work; g_prof[5] = clock64() - t_begin; g_prof[7] = t_loop; g_prof[8] = t_ldw; }
+  if (blockIdx.x == 0 && warp == 4 && lane == 0) { g_prof[3] = t_accw; g_prof[5] = clock64() - t_begin; }
 }
 
 template <bool kTrain>
@@ -700,20 +712,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ===================== TMA producer: this CTA's half of every chunk, each chunk once per quad =====================
+    // ===================== TMA producer: this CTA's 64 rows of every (layer, N-half, K chunk), once per quad =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t it = first_it; it < n_quads; it += it_stride) {
         int cbase = 0;
         for (int s = 0; s < kNumSteps; ++s) {
           const int n = step_nchunks(s);
-          for (int pass = 0; pass < (kShare2 ? 1 : 2); ++pass) {     // unshared: once per tile slot
+          const int nh = (s == 9) ? 1 : 2;
+          for (int h = 0; h < nh; ++h) {
             for (int ci = 0; ci < n; ++ci) {
-              const int c = cbase + ci;
-              const uint32_t half = fwd_chunk_bytes(c) / 2;
+              const uint8_t* src = p.packed + fwd_chunk_off(cbase + ci) + (size_t)(2 * h + (int)rank) * kStageBytes2;
               mbar_wait(&bar_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&bar_full[stage], half);
-              tma_load_1d(smem + kSmemW + stage * kHalfW256, p.packed + fwd_chunk_off(c) + rank * half, half, &bar_full[stage]);
+              mbar_arrive_expect_tx(&bar_full[stage], kStageBytes2);
+              tma_load_1d(smem + kSmemW2 + stage * kStageBytes2, src, kStageBytes2, &bar_full[stage]);
               if (++stage == kStages2) { stage = 0; phase ^= 1; }
             }
           }
@@ -722,84 +734,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
       }
     }
   } else if (warp == 1) {
-    {
-      if (rank == 1 && lane != 0) {
-        // only lane 0 relays
-      } else if (rank == 1) {
-        // ===================== relay: tell the leader that this CTA's half has landed =====================
+    if (rank == 1) {
+      // ===================== relay: tell the leader that this CTA's part of a stage has landed =====================
+      if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
         for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          for (int c = 0; c < (kShare2 ? kFwdChunks : 2 * kFwdChunks); ++c) {
+          for (int c = 0; c < kFillsPerIter2; ++c) {
             mbar_wait(&bar_full[stage], phase);
             mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[stage]), 0));
             if (++stage == kStages2) { stage = 0; phase ^= 1; }
           }
         }
-      } else {
-        // ===================== MMA issuer (leader CTA) =====================
-        uint32_t act_phase[2] = {0, 0};
-        uint32_t gchunk = 0;   // running chunk counter -> ring stage and phase
-        long long t_act = 0, t_full = 0, t_begin = clock64();
-        const uint32_t idesc256 = umma_idesc_bf16(256, 256, 0, 0);
-        const uint32_t idesc128 = umma_idesc_bf16(256, 128, 0, 0);
-        const uint32_t sbase = smem_u32(smem);
-        for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          for (int s = 0; s < kNumSteps; ++s) {
-            const int n = step_nchunks(s);
-            const uint32_t idesc = (s == 9) ? idesc128 : idesc256;
-            int ia = 0, ib = 0;
-            while (ib < n) {
-              const bool do_a = (ia < n) && (kShare2 ? (ia - ib < kLead2) : true);
-              const int slot = do_a ? 0 : 1;
-              const int ci = do_a ? ia : ib;
-              const uint32_t g = gchunk + (uint32_t)ci + ((!kShare2 && !do_a) ? (uint32_t)n : 0u);
-              const uint32_t stage = g % kStages2, phase = (g / kStages2) & 1u;
-              if (ci == 0) {
+      }
+    } else {
+      // ===================== MMA issuer (leader CTA) =====================
+      uint32_t act_phase[2] = {0, 0};
+      int stage0 = 0; uint32_t phase0 = 0;          // ring position of the first K chunk of the current (layer, half)
+      long long t_act = 0, t_full = 0, t_begin = clock64();
+      const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
+      const uint32_t sbase = smem_u32(smem);
+      for (int64_t it = first_it; it < n_quads; it += it_stride) {
+        for (int s = 0; s < kNumSteps; ++s) {
+          const int n = step_nchunks(s);
+          const int nh = (s == 9) ? 1 : 2;
+          for (int h = 0; h < nh; ++h) {
+            for (int T = 0; T < 2; ++T) {
+              {
                 long long t0 = clock64();
-                mbar_wait(&bar_act[slot], act_phase[slot]);
+                mbar_wait(&bar_act[T], act_phase[T]);
                 t_act += clock64() - t0;
-                act_phase[slot] ^= 1;
+                act_phase[T] ^= 1;
                 tc_fence_after();
               }
-              if (do_a || !kShare2) {   // first use of the staged chunk: both halves must have landed
-                long long t0 = clock64();
-                mbar_wait(&bar_full[stage], phase);
-                t_full += clock64() - t0;
-                tc_fence_after();
-              }
-              const int src = step_asrc(s, ci);
-              const uint32_t a_addr = sbase + (src == 0 ? kSmemPE + slot * kActChunk
-                                                        : kSmemAct + slot * 4 * kActChunk + (src - 1) * kActChunk);
-              const uint32_t b_addr = sbase + kSmemW + stage * kHalfW256;
-              const int ksteps = (s == 9 && ci == 4) ? 2 : 4;
-              const uint32_t d_tmem = tmem_base + slot * 256;
-              if (do_a) ++ia; else ++ib;
-              if (elect_one_sync()) {
+              const uint32_t t_slot = tmem_base + T * 256;
+              int stage = stage0; uint32_t phase = phase0;
+              for (int ci = 0; ci < n; ++ci) {
+                if (T == 0) {   // first use of the staged chunk: both CTAs' parts must have landed
+                  long long t0 = clock64();
+                  mbar_wait(&bar_full[stage], phase);
+                  t_full += clock64() - t0;
+                  tc_fence_after();
+                }
+                const int src = step_asrc(s, ci);
+                const uint32_t b_addr = sbase + kSmemW2 + stage * kStageBytes2;
+                const int ksteps = (s == 9 && ci == 4) ? 2 : 4;   // viewdir PE has 27 (<32) channels
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  if (kk < ksteps) {
-                    uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                    uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                    umma_bf16_2cta(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
+                  for (int kk = 0; kk < 4; ++kk) {
+                    if (kk < ksteps) {
+                      const uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+                      const uint32_t accum = (ci > 0 || kk > 0) ? 1u : 0u;
+                      if (src == 0) {
+                        const uint64_t da = umma_desc_sw128(sbase + kSmemPE2 + T * kActChunk + kk * 32, 16, 1024);
+                        umma_bf16_2cta(t_slot + 128, da, db, idesc, accum);
+                      } else {
+                        umma_bf16_ts_2cta(t_slot + 128, t_slot + (src - 1) * 32 + kk * 8, db, idesc, accum);
+                      }
+                    }
                   }
+                  if (T == 1) umma_commit_2cta(&bar_empty[stage], 3);   // last use: free the stage in both CTAs
+                  if (ci == n - 1) umma_commit_2cta(&bar_acc[T], 3);
                 }
-                if (!do_a || !kShare2) umma_commit_2cta(&bar_empty[stage], 3);   // last use: free the stage in both CTAs
-                if (do_a) {
-                  if (ia == n) umma_commit_2cta(&bar_acc[0], 3);
-                } else {
-                  if (ib == n) umma_commit_2cta(&bar_acc[1], 3);
-                }
+                __syncwarp();
+                if (++stage == kStages2) { stage = 0; phase ^= 1; }
               }
-              __syncwarp();
+              if (T == 1) { stage0 = stage; phase0 = phase; }
             }
-            gchunk += (uint32_t)(kShare2 ? n : 2 * n);
           }
         }
-        if (blockIdx.x == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
       }
+      if (blockIdx.x == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
     }
   } else if (warp >= 4) {
-    pair_epilogue<kTrain>(p, smem, bar_acc, bar_act, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
+    ts_epilogue<kTrain>(p, smem, bar_acc, bar_act, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
   }
 
   tc_fence_before();
@@ -854,7 +861,7 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
     const int64_t n_quads = (p.n_tiles + 3) / 4;
     const int max_clusters = mvip_num_sms() / 2;
     const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
-    const size_t smem2 = kSmemBytes2 + 1024;
+    const size_t smem2 = (stash ? kSmemBytes2Train : kSmemBytes2Infer) + 1024;
     if (stash) {
       MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       mlp_forward_pair_kernel<true><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
