@@ -173,6 +173,8 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
 /* Debug aid: cycle counters recorded by CTA 0 of the last mvip_mlp_forward launch (host array of 16 u64;
  * synchronises the device). */
 int mvip_debug_profile(unsigned long long* out16);
+/* event trace of a -DMVIP_TRACE build: out[3][1024][2] (code, SM clock), n_out[3]; MVIP_E_UNSUPPORTED otherwise */
+int mvip_debug_trace(long long* out, int* n_out);
 
 int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
 

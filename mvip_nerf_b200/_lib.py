@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mvip_mlp_backward_phases": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_void_p), c_int,
                                          c_int, c_void_p]),
     "mvip_debug_profile": (c_int, [c_void_p]),
+    "mvip_debug_trace": (c_int, [c_void_p, c_void_p]),
     "mvip_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

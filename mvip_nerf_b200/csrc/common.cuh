@@ -216,8 +216,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // possibly remote barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a (possibly remote) barrier of the cluster.  Default semantics (release at CTA scope) on purpose: a
+// cluster-scope release costs ~1000 cycles on B200 (it drains/invalidates like a cluster fence), and what the remote
+// waiter consumes here is TMEM / async-proxy state that the arriving side has already fenced explicitly
+// (tcgen05.wait::st + tcgen05.fence::before_thread_sync, fence.proxy.async) - not generic-proxy memory.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -30,6 +30,20 @@ constexpr int kNumSteps = 10;
 // [2] mma: total, [3] epi slot0: acc wait, [4] epi slot0: work, [5] epi slot0: total, [6] producer: empty wait
 __device__ unsigned long long g_prof[16];
 
+// Optional event trace of CTA 0 (build with -DMVIP_TRACE): three logs (issuer, epilogue leader of slot 0 / slot 1) of
+// (code, clock) pairs for ONE iteration; read with mvip_debug_trace.
+#ifdef MVIP_TRACE
+__device__ long long g_trace[3][1024][2];
+__device__ int g_trace_n[3];
+#define TRACE_DECL(role) int tr_n_ = 0; const int tr_role_ = (role); bool tr_on_ = false
+#define TRACE_ARM(cond) tr_on_ = (cond)
+#define TRACE(code) do { if (tr_on_ && tr_n_ < 1024) { g_trace[tr_role_][tr_n_][0] = (code); g_trace[tr_role_][tr_n_][1] = clock64(); ++tr_n_; g_trace_n[tr_role_] = tr_n_; } } while (0)
+#else
+#define TRACE_DECL(role)
+#define TRACE_ARM(cond)
+#define TRACE(code)
+#endif
+
 struct Params {
   const uint8_t* packed;
   mvip_points pts;
@@ -453,29 +467,69 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
 //     multicasts "stage free" / "accumulator full" to both CTAs.
 // =================================================================================================
 constexpr int kThreads2 = 640;
-constexpr int kStages2 = 12;
-constexpr uint32_t kStageBytes2 = 64 * 128;                              // 64 weight rows x 64 k (bf16)
+constexpr uint32_t kSlotBytes2 = 64 * 128;                               // 64 weight rows x 64 k (bf16)
+// weight ring: 8 KB slots, filled and released in GROUPS = all K chunks of one (layer, N-half): 1, 4 or 5 slots.
+// One full / one empty barrier per group (a successful mbarrier wait costs the issuer ~200 cycles, so per-chunk
+// barriers would eat a third of its time).  The producer runs kLag groups ahead.
+template <bool kTrain> struct Ring2 {
+  static constexpr int kSlots = kTrain ? 12 : 20;
+  static constexpr int kLag = kTrain ? 2 : 4;      // any kLag consecutive groups fit: 5+5 <= 12, 4+5+5+4 <= 20
+};
+constexpr int kGroupBars2 = 4;
 constexpr uint32_t kSmemPE2 = 0;                                         // pe[2]: 2 x 16 KB
-constexpr uint32_t kSmemW2 = 2 * kActChunk;                              // weight ring
-constexpr uint32_t kSmemSmall2 = kSmemW2 + kStages2 * kStageBytes2;      // fp32 tail of the packed blob (12,320 B)
+constexpr uint32_t kSmemSmall2 = 2 * kActChunk;                          // fp32 tail of the packed blob (12,320 B)
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
-constexpr uint32_t kSmemStg2 = kSmemXch2 + 2 * 2048;                     // stash staging: 2 slots x 2 chunk images (train)
-constexpr uint32_t kSmemBytes2Infer = kSmemStg2;
+constexpr uint32_t kSmemW2 = kSmemXch2 + 2 * 2048;                       // weight ring
+constexpr uint32_t kSmemStg2 = kSmemW2 + Ring2<true>::kSlots * kSlotBytes2;   // stash staging: 2 slots x 2 chunk images (train)
 constexpr uint32_t kSmemBytes2Train = kSmemStg2 + 4 * kActChunk;         // 214,016
-constexpr int kFillsPerIter2 = 2 * (1 + 4 * 4 + 5 + 2 * 4 + 4) + 5;      // ring stages consumed per tile quad = 73
+constexpr uint32_t kSmemBytes2Infer = kSmemW2 + Ring2<false>::kSlots * kSlotBytes2;   // 214,016
+constexpr int kGroupsPerIter2 = 19;
 
-// One accumulator half (this thread: row r, 64 of its 128 columns) -> +bias, (ReLU), bf16 pairs in pk[32].
-// kStep: 0 = trunk layer (ReLU), 1 = layer 7 (ReLU + alpha head), 2 = feature layer (no ReLU), 3 = views layer (ReLU + rgb head)
+// UMMA smem descriptor (SWIZZLE_128B, K-major, LBO 16 B, SBO 1024 B) split into its two words, so that the issuer
+// only adds to the low word: lo = (addr >> 4) | (1 << 16), hi = 64 | version 1 (bit 14) | layout 2 (bits 29..31)
+constexpr uint32_t kDescHi2 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo2(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma2_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
+      : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// This thread's 64 accumulator columns -> registers (four loads in flight, one round trip).
+__device__ __forceinline__ void load_half(uint32_t tD, uint32_t (&raw)[4][16]) {
+  tmem_ld16(tD, raw[0]);
+  tmem_ld16(tD + 16, raw[1]);
+  tmem_ld16(tD + 32, raw[2]);
+  tmem_ld16(tD + 48, raw[3]);
+  tmem_ld_wait_on16(raw[0]);
+  tmem_ld_wait_on16(raw[1]);
+  tmem_ld_wait_on16(raw[2]);
+  tmem_ld_wait_on16(raw[3]);
+}
+// One accumulator half (row r, 64 of its 128 columns) -> +bias, (ReLU), bf16 pairs in pk[32].
+// kKind: 0 = trunk layer (ReLU), 1 = layer 7 (ReLU + alpha head), 2 = feature layer (no ReLU), 3 = views layer (ReLU + rgb head)
 template <bool kTrain, int kKind, int kHalf>
-__device__ __forceinline__ void drain_half(uint32_t tD, uint32_t small_s, int bias_i, int col0, uint32_t (&pk)[32],
-                                           uint32_t (&mw)[4], float& alpha_part, float (&rgb_part)[3]) {
-  uint32_t buf[2][16];
-  tmem_ld16(tD, buf[0]);
+__device__ __forceinline__ void math_half(const uint32_t (&raw)[4][16], uint32_t small_s, int bias_i, int col0, uint32_t (&pk)[32],
+                                          uint32_t (&mw)[4], float& alpha_part, float (&rgb_part)[3]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    uint32_t (&acc)[16] = buf[b & 1];
-    tmem_ld_wait_on16(acc);
-    if (b + 1 < 4) tmem_ld16(tD + 16 * (b + 1), buf[(b + 1) & 1]);
+    const uint32_t (&acc)[16] = raw[b];
     const int c0 = col0 + 16 * b;
     float v[16];
 #pragma unroll
@@ -519,11 +573,12 @@ __device__ __forceinline__ void drain_half(uint32_t tD, uint32_t small_s, int bi
 }
 
 template <bool kTrain>
-__device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
+__device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act, uint64_t* bar_hi,
                                             uint32_t tmem_base, int warp, int lane, uint32_t cta_rank,
                                             int64_t first_it, int64_t n_iters, int64_t it_stride) {
-  // warp e = warp-4: slot T = e/8, TMEM lane quarter q = e%4 (== warp%4), column half ch = (e%8)/4 of every accumulator half
-  const int e = warp - 4, T = e >> 3, q = e & 3, ch = (e & 7) >> 2;
+  // epilogue warps are warps 0..15 (the MMA issuer sits in the highest warp: the scheduler favours high warp ids);
+  // warp e: slot T = e/8, TMEM lane quarter q = e%4 (== warp%4), column half ch = (e%8)/4 of every accumulator half
+  const int e = warp, T = e >> 3, q = e & 3, ch = (e & 7) >> 2;
   const int r = q * 32 + lane;
   const bool leader = (e & 7) == 0 && lane == 0;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -537,10 +592,17 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
   float4* xch = reinterpret_cast<float4*>(smem + kSmemXch2 + T * 2048) + r;
   uint32_t acc_phase = 0;
   long long t_accw = 0, t_begin = clock64();
+  TRACE_DECL(1 + T);
 
+  // two barriers per slot: a signal must be consumed by the issuer before the next one on the same barrier can fire
+  // (parity waits); "A[128,256) ready" follows "A[0,128) ready" without any dependence on the issuer, so it has its own.
   auto act_arrive = [&]() {
     if (cta_rank == 0) mbar_arrive(&bar_act[T]);
     else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
+  };
+  auto hi_arrive = [&]() {
+    if (cta_rank == 0) mbar_arrive(&bar_hi[T]);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi[T]), 0));
   };
   auto wait_acc = [&]() {
     long long t0 = clock64();
@@ -552,6 +614,7 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
 
   for (int64_t it = first_it; it < n_iters; it += it_stride) {
     const int64_t tile = 4 * it + 2 * T + (int64_t)cta_rank;
+    TRACE_ARM(blockIdx.x == 0 && leader && it == first_it + 3 * it_stride);
     const bool tile_valid = tile < p.n_tiles;
     const int64_t g = tile * kTile + r;
     const bool valid = tile_valid && g < p.pts.n_points;
@@ -614,21 +677,41 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
       const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : kSmBiasFeat);
       uint32_t pk[32];
       uint32_t mw[4] = {0u, 0u, 0u, 0u};
-      // ---- N-half 0: drain, keep the packed result in registers (the old A operand is still being read by half 1)
-      wait_acc();
-      if (s == 7) drain_half<kTrain, 1, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-      else if (s == 8) drain_half<kTrain, 2, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-      else drain_half<kTrain, 0, 0>(tD, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-      tc_fence_before();
-      named_bar_sync(bar_id, 256);
-      if (leader) act_arrive();                // accumulator drained: half 1 may be issued
+      {  // ---- N-half 0: drain -> "accumulator free" at once; the packed result stays in registers (the old A
+         //      operand is still being read by the MMAs of half 1)
+        uint32_t raw[4][16];
+        TRACE(s * 16 + 0);
+        wait_acc();
+        TRACE(s * 16 + 1);
+        load_half(tD, raw);
+        TRACE(s * 16 + 2);
+        tc_fence_before();
+        named_bar_sync(bar_id, 256);
+        if (leader) act_arrive();              // half 1 may be issued
+        TRACE(s * 16 + 3);
+        if (s == 7) math_half<kTrain, 1, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+        else if (s == 8) math_half<kTrain, 2, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+        else math_half<kTrain, 0, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
+      }
       if (kTrain) stage_out((s < 8 ? kStashH + 4 * s : kStashFeat), pk);
-      // ---- N-half 1: the MMAs of this layer are complete -> overwrite the A operand
-      wait_acc();
-      tmem_st32(tA + ch * 32, pk);
-      if (s == 7) drain_half<kTrain, 1, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
-      else if (s == 8) drain_half<kTrain, 2, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
-      else drain_half<kTrain, 0, 1>(tD, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+      {  // ---- N-half 1: all MMAs of this layer are complete -> the A operand may be overwritten
+        uint32_t raw[4][16];
+        TRACE(s * 16 + 4);
+        wait_acc();
+        TRACE(s * 16 + 5);
+        tmem_st32(tA + ch * 32, pk);           // features [0,128) of the next layer's A operand
+        load_half(tD, raw);
+        tmem_st_wait();
+        TRACE(s * 16 + 6);
+        tc_fence_before();
+        named_bar_sync(bar_id, 256);
+        if (leader) act_arrive();              // A[0,128) ready + accumulator free: the next layer's first K chunks may start
+        TRACE(s * 16 + 7);
+        if (s == 7) math_half<kTrain, 1, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+        else if (s == 8) math_half<kTrain, 2, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+        else math_half<kTrain, 0, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
+      }
+      TRACE(s * 16 + 8);
       tmem_st32(tA + 64 + ch * 32, pk);
       if (s == 8) {                            // PE(viewdir) replaces PE(pts): L5 has consumed it
         write_pe_half<4>(pe, r, vx, vy, vz, ch);
@@ -637,8 +720,9 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
       tmem_st_wait();
       tc_fence_before();
       named_bar_sync(bar_id, 256);
+      TRACE(s * 16 + 9);
       if (leader) {
-        act_arrive();                          // next layer's A operand complete, accumulator drained
+        hi_arrive();                           // A[128,256) (and PE(viewdir)) ready
         if (kTrain && s == 8 && tile_valid) {
           tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
           tma_store_commit();
@@ -656,8 +740,12 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     {  // ---- views layer: one N-half of 128 columns, then the rgb head; raw = (rgb, alpha)
       uint32_t pk[32];
       uint32_t mw[4] = {0u, 0u, 0u, 0u};
-      wait_acc();
-      drain_half<kTrain, 3, 0>(tD, small_s, kSmBiasViews, ch * 64, pk, mw, alpha_part, rgb_part);
+      {
+        uint32_t raw[4][16];
+        wait_acc();
+        load_half(tD, raw);
+        math_half<kTrain, 3, 0>(raw, small_s, kSmBiasViews, ch * 64, pk, mw, alpha_part, rgb_part);
+      }
       if (ch == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
       tc_fence_before();
       named_bar_sync(bar_id, 256);
@@ -676,14 +764,15 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     }
   }
   if (kTrain && leader) tma_store_wait_all0();
-  if (blockIdx.x == 0 && warp == 4 && lane == 0) { g_prof[3] = t_accw; g_prof[5] = clock64() - t_begin; }
+  if (blockIdx.x == 0 && warp == 0 && lane == 0) { g_prof[3] = t_accw; g_prof[5] = clock64() - t_begin; }
 }
 
 template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_forward_pair_kernel(const Params p) {
+  constexpr int kSlots = Ring2<kTrain>::kSlots, kLag = Ring2<kTrain>::kLag, kG = kGroupBars2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[kStages2], bar_empty[kStages2], bar_acc[2], bar_act[2];
+  __shared__ uint64_t bar_gfull[kG], bar_gempty[kG], bar_acc[2], bar_act[2], bar_hi[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -692,14 +781,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
   const int64_t first_it = blockIdx.x >> 1, it_stride = gridDim.x >> 1;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages2; ++i) {
-      mbar_init(&bar_full[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
-      mbar_init(&bar_empty[i], 1);                  // multicast tcgen05.commit
+    for (int i = 0; i < kG; ++i) {
+      mbar_init(&bar_gfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
+      mbar_init(&bar_gempty[i], 2);                  // multicast tcgen05.commit of the two issuer warps
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 2); }   // act: one arrive per CTA
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 2); mbar_init(&bar_hi[i], 2); }   // act/hi: one arrive per CTA
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc_2cta(&tmem_base_s, 512);
+  if (warp == 17) tmem_alloc_2cta(&tmem_base_s, 512);
   {  // biases + alpha / rgb heads -> shared memory (read ~10^3 times per tile by the epilogue warps)
     const float4* src = reinterpret_cast<const float4*>(p.packed + kSmallOff);
     float4* dst = reinterpret_cast<float4*>(smem + kSmemSmall2);
@@ -711,108 +800,124 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    // ===================== TMA producer: this CTA's 64 rows of every (layer, N-half, K chunk), once per quad =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t it = first_it; it < n_quads; it += it_stride) {
-        int cbase = 0;
-        for (int s = 0; s < kNumSteps; ++s) {
-          const int n = step_nchunks(s);
-          const int nh = (s == 9) ? 1 : 2;
-          for (int h = 0; h < nh; ++h) {
-            for (int ci = 0; ci < n; ++ci) {
-              const uint8_t* src = p.packed + fwd_chunk_off(cbase + ci) + (size_t)(2 * h + (int)rank) * kStageBytes2;
-              mbar_wait(&bar_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&bar_full[stage], kStageBytes2);
-              tma_load_1d(smem + kSmemW2 + stage * kStageBytes2, src, kStageBytes2, &bar_full[stage]);
-              if (++stage == kStages2) { stage = 0; phase ^= 1; }
-            }
-          }
-          cbase += n;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 1) {
-      // ===================== relay: tell the leader that this CTA's part of a stage has landed =====================
+  if (warp < 16) {
+    reg_inc<104>();   // 16 x 32 x 104 + 4 x 32 x 40 <= 640 x 96 (the CTA's register pool)
+    ts_epilogue<kTrain>(p, smem, bar_acc, bar_act, bar_hi, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
+  } else {
+    reg_dec<40>();
+    if (warp == 16) {
+      // ===================== TMA producer: this CTA's 64 rows of every (layer, N-half, K chunk), once per quad =====================
       if (lane == 0) {
-        int stage = 0; uint32_t phase = 0;
+        uint32_t j = 0; int slot = 0;
         for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          for (int c = 0; c < kFillsPerIter2; ++c) {
-            mbar_wait(&bar_full[stage], phase);
-            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[stage]), 0));
-            if (++stage == kStages2) { stage = 0; phase ^= 1; }
+          int cbase = 0;
+          for (int s = 0; s < kNumSteps; ++s) {
+            const int n = step_nchunks(s);
+            const int nh = (s == 9) ? 1 : 2;
+            for (int h = 0; h < nh; ++h, ++j) {
+              if (j >= (uint32_t)kLag) mbar_wait(&bar_gempty[(j - kLag) % kG], ((j - kLag) / kG) & 1u);   // the slots are free again
+              uint64_t* full = &bar_gfull[j % kG];
+              mbar_arrive_expect_tx(full, (uint32_t)n * kSlotBytes2);
+              for (int ci = 0; ci < n; ++ci) {
+                const uint8_t* src = p.packed + fwd_chunk_off(cbase + ci) + (size_t)(2 * h + (int)rank) * kSlotBytes2;
+                tma_load_1d(smem + kSmemW2 + slot * kSlotBytes2, src, kSlotBytes2, full);
+                if (++slot == kSlots) slot = 0;
+              }
+            }
+            cbase += n;
           }
         }
       }
-    } else {
-      // ===================== MMA issuer (leader CTA) =====================
-      uint32_t act_phase[2] = {0, 0};
-      int stage0 = 0; uint32_t phase0 = 0;          // ring position of the first K chunk of the current (layer, half)
+    } else if (warp == 19 && rank == 1) {
+      // ===================== relay: tell the leader that this CTA's part of a group has landed =====================
+      if (lane == 0) {
+        uint32_t j = 0;
+        for (int64_t it = first_it; it < n_quads; it += it_stride) {
+          for (int c = 0; c < kGroupsPerIter2; ++c, ++j) {
+            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
+          }
+        }
+      }
+    } else if (warp >= 18 && rank == 0) {
+      // ===================== MMA issuers (leader CTA): warp 18 -> tile slot X, warp 19 -> tile slot Y =====================
+      // Two independent issuers: while one sits in an mbarrier wait (~200 cycles even when it succeeds) the other
+      // keeps the tensor pipe fed.  The order X.h0, Y.h0, X.h1, Y.h1 emerges from the dependencies.
+      const int T = warp - 18;
+      uint32_t act_phase = 0, hi_phase = 0, j = 0;
+      int slot0 = 0;
       long long t_act = 0, t_full = 0, t_begin = clock64();
+      TRACE_DECL(0);
       const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
       const uint32_t sbase = smem_u32(smem);
+      const uint32_t t_slot = tmem_base + T * 256;
+      const uint32_t pe_lo = desc_lo2(sbase + kSmemPE2 + T * kActChunk);
+      const uint32_t w_lo = desc_lo2(sbase + kSmemW2);
       for (int64_t it = first_it; it < n_quads; it += it_stride) {
+        TRACE_ARM(blockIdx.x == 0 && T == 0 && lane == 0 && it == first_it + 3 * it_stride);
         for (int s = 0; s < kNumSteps; ++s) {
           const int n = step_nchunks(s);
           const int nh = (s == 9) ? 1 : 2;
-          for (int h = 0; h < nh; ++h) {
-            for (int T = 0; T < 2; ++T) {
-              {
-                long long t0 = clock64();
-                mbar_wait(&bar_act[T], act_phase[T]);
-                t_act += clock64() - t0;
-                act_phase[T] ^= 1;
-                tc_fence_after();
-              }
-              const uint32_t t_slot = tmem_base + T * 256;
-              int stage = stage0; uint32_t phase = phase0;
-              for (int ci = 0; ci < n; ++ci) {
-                if (T == 0) {   // first use of the staged chunk: both CTAs' parts must have landed
-                  long long t0 = clock64();
-                  mbar_wait(&bar_full[stage], phase);
-                  t_full += clock64() - t0;
-                  tc_fence_after();
-                }
-                const int src = step_asrc(s, ci);
-                const uint32_t b_addr = sbase + kSmemW2 + stage * kStageBytes2;
-                const int ksteps = (s == 9 && ci == 4) ? 2 : 4;   // viewdir PE has 27 (<32) channels
-                if (elect_one_sync()) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    if (kk < ksteps) {
-                      const uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                      const uint32_t accum = (ci > 0 || kk > 0) ? 1u : 0u;
-                      if (src == 0) {
-                        const uint64_t da = umma_desc_sw128(sbase + kSmemPE2 + T * kActChunk + kk * 32, 16, 1024);
-                        umma_bf16_2cta(t_slot + 128, da, db, idesc, accum);
-                      } else {
-                        umma_bf16_ts_2cta(t_slot + 128, t_slot + (src - 1) * 32 + kk * 8, db, idesc, accum);
-                      }
-                    }
-                  }
-                  if (T == 1) umma_commit_2cta(&bar_empty[stage], 3);   // last use: free the stage in both CTAs
-                  if (ci == n - 1) umma_commit_2cta(&bar_acc[T], 3);
-                }
-                __syncwarp();
-                if (++stage == kStages2) { stage = 0; phase ^= 1; }
-              }
-              if (T == 1) { stage0 = stage; phase0 = phase; }
+          for (int h = 0; h < nh; ++h, ++j) {
+            {
+              TRACE(s * 64 + h * 32 + 0);
+              long long t0 = clock64();
+              mbar_wait(&bar_act[T], act_phase);
+              TRACE(s * 64 + h * 32 + 1);
+              t_act += clock64() - t0;
+              act_phase ^= 1;
+              t0 = clock64();
+              mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);   // both CTAs' parts of the group have landed
+              t_full += clock64() - t0;
+              TRACE(s * 64 + h * 32 + 5);
+              tc_fence_after();
             }
+            bool hi_ready = (s == 0) || (h == 1);   // A[128,256) is signalled separately by the previous layer's epilogue
+            int slot = slot0;
+            for (int ci = 0; ci < n; ++ci) {
+              const int src = step_asrc(s, ci);
+              if (!hi_ready && src >= 3) {
+                TRACE(s * 64 + h * 32 + 2);
+                long long t0 = clock64();
+                mbar_wait(&bar_hi[T], hi_phase);
+                TRACE(s * 64 + h * 32 + 3);
+                t_act += clock64() - t0;
+                hi_phase ^= 1;
+                tc_fence_after();
+                hi_ready = true;
+              }
+              const uint32_t b_lo = w_lo + (uint32_t)slot * (kSlotBytes2 >> 4);
+              const int ksteps = (s == 9 && ci == 4) ? 2 : 4;   // viewdir PE has 27 (<32) channels
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < ksteps) {
+                    const uint32_t accum = (ci > 0 || kk > 0) ? 1u : 0u;
+                    if (src == 0) mma2_ss(t_slot + 128, pe_lo + kk * 2, b_lo + kk * 2, idesc, accum);
+                    else mma2_ts(t_slot + 128, t_slot + (src - 1) * 32 + kk * 8, b_lo + kk * 2, idesc, accum);
+                  }
+                }
+                if (ci == n - 1) {
+                  umma_commit_2cta(&bar_gempty[j % kG], 3);   // this issuer is done with the group (both CTAs)
+                  umma_commit_2cta(&bar_acc[T], 3);
+                }
+              }
+              __syncwarp();
+              if (++slot == kSlots) slot = 0;
+            }
+            TRACE(s * 64 + h * 32 + 4);
+            slot0 = slot;
           }
         }
       }
-      if (blockIdx.x == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
+      if (blockIdx.x == 0 && T == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
     }
-  } else if (warp >= 4) {
-    ts_epilogue<kTrain>(p, smem, bar_acc, bar_act, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
   }
 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the peer may still signal our barriers / read our smem until it is done too
-  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
+  if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 int check_points(const char* who, const mvip_points* pts) {
@@ -838,6 +943,20 @@ int mvip_debug_profile(unsigned long long* out16) {
   MVIP_CUDA_OK(cudaDeviceSynchronize());
   MVIP_CUDA_OK(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
   return MVIP_OK;
+}
+
+// copies the event trace of a -DMVIP_TRACE build (3 logs x 1024 x (code, clock)); n_out[3] = entries per log
+int mvip_debug_trace(long long* out, int* n_out) {
+#ifdef MVIP_TRACE
+  MVIP_CUDA_OK(cudaDeviceSynchronize());
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 1024 * 2));
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(n_out, g_trace_n, sizeof(int) * 3));
+  return MVIP_OK;
+#else
+  (void)out; (void)n_out;
+  mvip_set_error("mvip_debug_trace: library built without -DMVIP_TRACE");
+  return MVIP_E_UNSUPPORTED;
+#endif
 }
 
 size_t mvip_mlp_stash_bytes(int64_t n_points) { return (size_t)mlp::num_tiles(n_points) * mlp::kStashTileBytes; }

@@ -9,19 +9,9 @@
 
 void mvip_set_error(const char*, ...) {}
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
+__device__ int g_commit_every = 16;
+__device__ int g_commit_mask = 1;
+__device__ int g_alt = 0;
 struct Res { unsigned long long cyc; unsigned long long noise_bytes; };
 
 // kCta: 1 or 2; ts: A from TMEM; N: MMA N; noise_gap: cycles of spin between noise stores (0 = no noise)
@@ -51,8 +41,10 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
       const uint32_t idesc = umma_idesc_bf16(128 * kCta, N, 0, 0);
       const uint32_t sb = smem_u32(smem);
       long long t0 = clock64();
+      const int ce = g_commit_every, cmask = g_commit_mask, alt = g_alt;
       for (int it = 0; it < iters; ++it) {
         if (elect_one_sync()) {
+          const uint32_t d_t = tmem_base + ((alt && (it & 1)) ? 128 : 0);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -60,14 +52,14 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
               uint64_t db = umma_desc_sw128(sb + 65536 + c * b_img + kk * 32, 16, 1024);
               if (ts) {
                 uint32_t ta = tmem_base + 256 + c * 32 + kk * 8;
-                if (kCta == 2) umma_bf16_ts_2cta(tmem_base, ta, db, idesc, 1u); else umma_bf16_ts(tmem_base, ta, db, idesc, 1u);
+                if (kCta == 2) umma_bf16_ts_2cta(d_t, ta, db, idesc, 1u); else umma_bf16_ts(d_t, ta, db, idesc, 1u);
               } else {
                 uint64_t da = umma_desc_sw128(sb + c * 16384 + kk * 32, 16, 1024);
-                if (kCta == 2) umma_bf16_2cta(tmem_base, da, db, idesc, 1u); else umma_bf16(tmem_base, da, db, idesc, 1u);
+                if (kCta == 2) umma_bf16_2cta(d_t, da, db, idesc, 1u); else umma_bf16(d_t, da, db, idesc, 1u);
               }
+              if (((c * 4 + kk + 1) % ce) == 0) { if (kCta == 2) umma_commit_2cta(&bar_sink, (uint16_t)cmask); else umma_commit(&bar_sink); }
             }
           }
-          if (kCta == 2) umma_commit_2cta(&bar_sink, 1); else umma_commit(&bar_sink);
         }
         __syncwarp();
       }
@@ -78,6 +70,29 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
       if ((tid & 31) == 0) res[blockIdx.x].cyc = (unsigned long long)(t1 - t0);
     }
     if ((tid & 31) == 0) stop_flag = 1;
+  } else if (warp >= 4 && noise_gap < 0) {
+    // 8 warps: 4 x tcgen05.ld.x16 (64 columns of the accumulator region) + pack + one tcgen05.st.x32 per batch
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ((warp - 4) >> 2) * 64;
+    unsigned long long n = 0; uint32_t accx = 0;
+    while (!stop_flag) {
+      uint32_t a[16], b[16], c[16], d[16];
+      tmem_ld16(taddr, a); tmem_ld16(taddr + 16, b); tmem_ld16(taddr + 32, c); tmem_ld16(taddr + 48, d);
+      tmem_ld_wait();
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { pk[i] = a[2*i] ^ a[2*i+1]; pk[8+i] = b[2*i] ^ b[2*i+1]; pk[16+i] = c[2*i] ^ c[2*i+1]; pk[24+i] = d[2*i] ^ d[2*i+1]; }
+      if (noise_gap <= -1000) { tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + ((warp - 4) >> 2) * 32, pk); tmem_st_wait(); }
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) accx ^= pk[i];
+      }
+      n += 32 * 64 * 4;
+      long long t = clock64();
+      const int gap = (-noise_gap) % 1000;
+      while (clock64() - t < gap) {}
+    }
+    if (accx == 0x1234567u) n += 1;
+    if (kCta == 1 || rank == 0) atomicAdd(&res[blockIdx.x].noise_bytes, n);
   } else if (warp >= 4 && noise_gap > 0) {
     // 8 warps x 512 B per store instruction, conflict-free
     uint4 v = make_uint4(tid, tid + 1, tid + 2, tid + 3);
@@ -199,12 +214,22 @@ void run_mma(int ts, int N, int gap, Res* d_res, int grid) {
 
 int main() {
   Res* d_res; CK(cudaMalloc(&d_res, sizeof(Res) * 148));
+  for (int alt = 0; alt < 2; ++alt)
+  for (int mask : {1, 3})
+    for (int ce : {16, 4, 2, 1}) {
+      CK(cudaMemcpyToSymbol(g_commit_every, &ce, 4)); CK(cudaMemcpyToSymbol(g_commit_mask, &mask, 4)); CK(cudaMemcpyToSymbol(g_alt, &alt, 4));
+      printf("alt_D=%d commit every %2d MMAs, mask %d: ", alt, ce, mask);
+      run_mma<2>(1, 128, 0, d_res, 148);
+    }
+  { int ce = 16, mask = 1, alt = 0; CK(cudaMemcpyToSymbol(g_commit_every, &ce, 4)); CK(cudaMemcpyToSymbol(g_commit_mask, &mask, 4)); CK(cudaMemcpyToSymbol(g_alt, &alt, 4)); }
+  if (getenv("UBENCH_ALL"))
   for (int ts = 0; ts < 2; ++ts)
     for (int N : {256, 128})
       for (int gap : {0, 400, 100, 1}) {
         run_mma<1>(ts, N, gap, d_res, 148);
         run_mma<2>(ts, N, gap, d_res, 148);
       }
+  if (!getenv("UBENCH_ALL")) return 0;
   for (int store = 0; store < 2; ++store)
     for (int nw : {4, 8, 16}) {
       CK(cudaMemset(d_res, 0, sizeof(Res) * 148));
