@@ -14,6 +14,7 @@
 // 16..28 B/point in (rays+z) and 16 B/point out (raw).  With a stash pointer (training) every layer's
 // input tile image is also bulk-stored for the backward pass (mlp_common.cuh, kStash*).
 #include "mlp_common.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace mlp;
@@ -32,6 +33,17 @@ __device__ unsigned long long g_prof[16];
 
 // Optional event trace of CTA 0 (build with -DMVIP_TRACE): three logs (issuer, epilogue leader of slot 0 / slot 1) of
 // (code, clock) pairs for ONE iteration; read with mvip_debug_trace.
+#ifdef MVIP_PROF
+#define PROF_DECL long long t_act = 0, t_full = 0, t_begin = clock64(), t0_ = 0
+#define PROF_T0 t0_ = clock64()
+#define PROF_ADD(x) x += clock64() - t0_
+#define PROF_STORE do { if (blockIdx.x == 0 && T == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0
+#define PROF_ADD(x)
+#define PROF_STORE
+#endif
 #ifdef MVIP_TRACE
 __device__ long long g_trace[3][1024][2];
 __device__ int g_trace_n[3];
@@ -50,6 +62,7 @@ struct Params {
   float4* raw;
   uint8_t* stash;
   int64_t n_tiles;
+  int flags;      // experiment switches (MVIP_EXP_FLAGS), 0 in production
 };
 
 // step s: number of K chunks, A source of each (0 = PE buffer, 1..4 = act chunk), N, K-steps of last chunk
@@ -523,10 +536,12 @@ __device__ __forceinline__ void load_half(uint32_t tD, uint32_t (&raw)[4][16]) {
   tmem_ld_wait_on16(raw[3]);
 }
 // One accumulator half (row r, 64 of its 128 columns) -> +bias, (ReLU), bf16 pairs in pk[32].
-// kKind: 0 = trunk layer (ReLU), 1 = layer 7 (ReLU + alpha head), 2 = feature layer (no ReLU), 3 = views layer (ReLU + rgb head)
-template <bool kTrain, int kKind, int kHalf>
-__device__ __forceinline__ void math_half(const uint32_t (&raw)[4][16], uint32_t small_s, int bias_i, int col0, uint32_t (&pk)[32],
-                                          uint32_t (&mw)[4], float& alpha_part, float (&rgb_part)[3]) {
+// ONE code instance for all layers (s is warp-uniform): the steady-state loop of the kernel has to stay inside the
+// 32 KB instruction cache, otherwise the single MMA-issuing warp starves on instruction fetches.
+// s == 7: + alpha head; s == 8 (feature layer): no ReLU; s == 9 (views layer): + rgb head.
+template <bool kTrain>
+__device__ __forceinline__ void math_half(const uint32_t (&raw)[4][16], uint32_t small_s, int s, int bias_i, int col0,
+                                          uint32_t (&pk)[32], uint32_t (&mw)[2], float& alpha_part, float (&rgb_part)[3]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const uint32_t (&acc)[16] = raw[b];
@@ -540,7 +555,7 @@ __device__ __forceinline__ void math_half(const uint32_t (&raw)[4][16], uint32_t
       v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + bb.z;
       v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + bb.w;
     }
-    if (kKind == 1) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
+    if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const float4 w = lds_f4(small_s + (kSmWAlpha + c0 + 4 * j4) * 4);
@@ -548,26 +563,32 @@ __device__ __forceinline__ void math_half(const uint32_t (&raw)[4][16], uint32_t
                       fmaxf(v[4 * j4 + 3], 0.f) * w.w;
       }
     }
-    if (kKind == 3) {  // rgb head (run_nerf_helpers.py:122)
-#pragma unroll
+    if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
+#pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
+        float a = 0.f;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 w = lds_f4(small_s + (kSmWRgb + ch * 128 + c0 + 4 * j4) * 4);
-          rgb_part[ch] += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y + fmaxf(v[4 * j4 + 2], 0.f) * w.z +
-                          fmaxf(v[4 * j4 + 3], 0.f) * w.w;
+          a += fmaxf(v[4 * j4], 0.f) * w.x + fmaxf(v[4 * j4 + 1], 0.f) * w.y + fmaxf(v[4 * j4 + 2], 0.f) * w.z +
+               fmaxf(v[4 * j4 + 3], 0.f) * w.w;
         }
+        if (ch == 0) rgb_part[0] += a; else if (ch == 1) rgb_part[1] += a; else rgb_part[2] += a;
       }
     }
+    if (s == 8) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      pk[8 * b + i] = (kKind == 2) ? pack_bf16x2(v[2 * i], v[2 * i + 1]) : pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
-    if (kTrain && kKind != 2) {
+      for (int i = 0; i < 8; ++i) pk[8 * b + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[8 * b + i] = pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+    }
+    if (kTrain) {
       // ReLU mask bits of these 16 columns (non-zero bf16 halves), layout: mask_bit_of_column() in mlp_common.cuh
       uint32_t m = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) m |= (((pk[8 * b + i] + 0x7FFF7FFFu) >> 15) & 0x00010001u) << i;
-      mw[2 * kHalf + (b >> 1)] |= m << (8 * (b & 1));
+      mw[b >> 1] |= m << (8 * (b & 1));
     }
   }
 }
@@ -596,13 +617,21 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
 
   // two barriers per slot: a signal must be consumed by the issuer before the next one on the same barrier can fire
   // (parity waits); "A[128,256) ready" follows "A[0,128) ready" without any dependence on the issuer, so it has its own.
+  // Every epilogue warp signals the issuer by itself (barrier count = 8 warps x 2 CTAs): no named barrier and no
+  // single "leader" arrive on the critical path.  Each lane has fenced its own TMEM / smem accesses before.
   auto act_arrive = [&]() {
-    if (cta_rank == 0) mbar_arrive(&bar_act[T]);
-    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
+    __syncwarp();
+    if (lane == 0) {
+      if (cta_rank == 0) mbar_arrive(&bar_act[T]);
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
+    }
   };
   auto hi_arrive = [&]() {
-    if (cta_rank == 0) mbar_arrive(&bar_hi[T]);
-    else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi[T]), 0));
+    __syncwarp();
+    if (lane == 0) {
+      if (cta_rank == 0) mbar_arrive(&bar_hi[T]);
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi[T]), 0));
+    }
   };
   auto wait_acc = [&]() {
     long long t0 = clock64();
@@ -661,10 +690,10 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     write_pe_half<10>(pe, r, px, py, pz, ch);
     fence_proxy_async_smem();
     tc_fence_before();
-    named_bar_sync(bar_id, 256);
-    if (leader) {
-      act_arrive();                            // L0 may start: PE ready, accumulator free
-      if (kTrain && tile_valid) {
+    act_arrive();                              // L0 may start: PE ready, accumulator free
+    if (kTrain) {
+      named_bar_sync(bar_id, 256);
+      if (leader && tile_valid) {
         tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
         tma_store_commit();
       }
@@ -672,93 +701,66 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
 
     float alpha_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
 
+    uint32_t pk[32];
 #pragma unroll 1
-    for (int s = 0; s < 9; ++s) {
-      const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : kSmBiasFeat);
-      uint32_t pk[32];
-      uint32_t mw[4] = {0u, 0u, 0u, 0u};
-      {  // ---- N-half 0: drain -> "accumulator free" at once; the packed result stays in registers (the old A
-         //      operand is still being read by the MMAs of half 1)
-        uint32_t raw[4][16];
-        TRACE(s * 16 + 0);
-        wait_acc();
-        TRACE(s * 16 + 1);
-        load_half(tD, raw);
-        TRACE(s * 16 + 2);
-        tc_fence_before();
-        named_bar_sync(bar_id, 256);
-        if (leader) act_arrive();              // half 1 may be issued
-        TRACE(s * 16 + 3);
-        if (s == 7) math_half<kTrain, 1, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-        else if (s == 8) math_half<kTrain, 2, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-        else math_half<kTrain, 0, 0>(raw, small_s, bias_i, ch * 64, pk, mw, alpha_part, rgb_part);
-      }
-      if (kTrain) stage_out((s < 8 ? kStashH + 4 * s : kStashFeat), pk);
-      {  // ---- N-half 1: all MMAs of this layer are complete -> the A operand may be overwritten
-        uint32_t raw[4][16];
-        TRACE(s * 16 + 4);
-        wait_acc();
-        TRACE(s * 16 + 5);
-        tmem_st32(tA + ch * 32, pk);           // features [0,128) of the next layer's A operand
-        load_half(tD, raw);
-        tmem_st_wait();
-        TRACE(s * 16 + 6);
-        tc_fence_before();
-        named_bar_sync(bar_id, 256);
-        if (leader) act_arrive();              // A[0,128) ready + accumulator free: the next layer's first K chunks may start
-        TRACE(s * 16 + 7);
-        if (s == 7) math_half<kTrain, 1, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
-        else if (s == 8) math_half<kTrain, 2, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
-        else math_half<kTrain, 0, 1>(raw, small_s, bias_i, 128 + ch * 64, pk, mw, alpha_part, rgb_part);
-      }
-      TRACE(s * 16 + 8);
-      tmem_st32(tA + 64 + ch * 32, pk);
-      if (s == 8) {                            // PE(viewdir) replaces PE(pts): L5 has consumed it
-        write_pe_half<4>(pe, r, vx, vy, vz, ch);
-        fence_proxy_async_smem();
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      named_bar_sync(bar_id, 256);
-      TRACE(s * 16 + 9);
-      if (leader) {
-        hi_arrive();                           // A[128,256) (and PE(viewdir)) ready
-        if (kTrain && s == 8 && tile_valid) {
-          tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
-          tma_store_commit();
+    for (int s = 0; s < kNumSteps; ++s) {
+      const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
+      const int stash_chunk = (s < 8 ? kStashH + 4 * s : (s == 8 ? kStashFeat : kStashHidden));
+      const int nh = (s == 9) ? 1 : 2;
+#pragma unroll 1
+      for (int h = 0; h < nh; ++h) {
+        uint32_t mw[2] = {0u, 0u};
+        {
+          uint32_t raw[4][16];
+          TRACE(s * 16 + 4 * h + 0);
+          wait_acc();
+          TRACE(s * 16 + 4 * h + 1);
+          // h == 1: all MMAs of this layer are complete -> the A operand may be overwritten; pk still holds half 0,
+          // i.e. features [0,128) of the next layer's A operand (it could not be stored earlier: half 1 was reading A)
+          if (h == 1) tmem_st32(tA + ch * 32, pk);
+          load_half(tD, raw);
+          if (h == 1) tmem_st_wait();
+          TRACE(s * 16 + 4 * h + 2);
+          tc_fence_before();
+          // h == 0: accumulator drained -> half 1 may be issued;  h == 1: A[0,128) ready + accumulator drained -> the
+          // next layer's first K chunks may start.  The math below is off the issuer's critical path.
+          if (s < 9) act_arrive();
+          TRACE(s * 16 + 4 * h + 3);
+          math_half<kTrain>(raw, small_s, s, bias_i, h * 128 + ch * 64, pk, mw, alpha_part, rgb_part);
         }
-      }
-      if (kTrain) {
-        stage_out((s < 8 ? kStashH + 4 * s : kStashFeat) + 2, pk);
-        if (s != 8 && tile_valid) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)s * 128 + r) * 32);
-          *reinterpret_cast<uint2*>(mrow + 2 * ch) = make_uint2(mw[0], mw[1]);
-          *reinterpret_cast<uint2*>(mrow + 4 + 2 * ch) = make_uint2(mw[2], mw[3]);
+        if (s < 9 && h == 1) {
+          tmem_st32(tA + 64 + ch * 32, pk);
+          if (s == 8) {                          // PE(viewdir) replaces PE(pts): L5 has consumed it
+            write_pe_half<4>(pe, r, vx, vy, vz, ch);
+            fence_proxy_async_smem();
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          TRACE(s * 16 + 9);
+          hi_arrive();                           // A[128,256) (and PE(viewdir)) ready
+          if (kTrain && s == 8) {
+            named_bar_sync(bar_id, 256);
+            if (leader && tile_valid) {
+              tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
+              tma_store_commit();
+            }
+          }
         }
-      }
-    }
-    {  // ---- views layer: one N-half of 128 columns, then the rgb head; raw = (rgb, alpha)
-      uint32_t pk[32];
-      uint32_t mw[4] = {0u, 0u, 0u, 0u};
-      {
-        uint32_t raw[4][16];
-        wait_acc();
-        load_half(tD, raw);
-        math_half<kTrain, 3, 0>(raw, small_s, kSmBiasViews, ch * 64, pk, mw, alpha_part, rgb_part);
-      }
-      if (ch == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
-      tc_fence_before();
-      named_bar_sync(bar_id, 256);
-      if (ch == 0 && valid) {
-        const float4 o = *xch;
-        p.raw[g] = make_float4(rgb_part[0] + o.x + lds_f1(small_s + kSmBRgb * 4), rgb_part[1] + o.y + lds_f1(small_s + (kSmBRgb + 1) * 4),
-                               rgb_part[2] + o.z + lds_f1(small_s + (kSmBRgb + 2) * 4), alpha_part + o.w + lds_f1(small_s + kSmBAlpha * 4));
-      }
-      if (kTrain) {
-        stage_out(kStashHidden, pk);
-        if (tile_valid) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)8 * 128 + r) * 32);
-          *reinterpret_cast<uint2*>(mrow + 2 * ch) = make_uint2(mw[0], mw[1]);
+        if (s == 9) {  // raw = (rgb, alpha): the two column halves of a row meet in shared memory
+          if (ch == 1) *xch = make_float4(rgb_part[0], rgb_part[1], rgb_part[2], alpha_part);
+          named_bar_sync(bar_id, 256);
+          if (ch == 0 && valid) {
+            const float4 o = *xch;
+            p.raw[g] = make_float4(rgb_part[0] + o.x + lds_f1(small_s + kSmBRgb * 4), rgb_part[1] + o.y + lds_f1(small_s + (kSmBRgb + 1) * 4),
+                                   rgb_part[2] + o.z + lds_f1(small_s + (kSmBRgb + 2) * 4), alpha_part + o.w + lds_f1(small_s + kSmBAlpha * 4));
+          }
+        }
+        if (kTrain) {
+          stage_out(stash_chunk + 2 * h, pk);
+          if (s != 8 && tile_valid) {
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32);
+            *reinterpret_cast<uint2*>(mrow + 2 * (2 * h + ch)) = make_uint2(mw[0], mw[1]);
+          }
         }
       }
     }
@@ -785,7 +787,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
       mbar_init(&bar_gfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
       mbar_init(&bar_gempty[i], 2);                  // multicast tcgen05.commit of the two issuer warps
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 2); mbar_init(&bar_hi[i], 2); }   // act/hi: one arrive per CTA
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 16); mbar_init(&bar_hi[i], 16); }   // act/hi: 8 epilogue warps x 2 CTAs
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc_2cta(&tmem_base_s, 512);
@@ -804,7 +806,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
     reg_inc<104>();   // 16 x 32 x 104 + 4 x 32 x 40 <= 640 x 96 (the CTA's register pool)
     ts_epilogue<kTrain>(p, smem, bar_acc, bar_act, bar_hi, tmem_base, warp, lane, rank, first_it, n_quads, it_stride);
   } else {
-    reg_dec<40>();
+    reg_dec<64>();   // 16 x 32 x 104 + 4 x 32 x 64 = 640 x 96: the issuer loop must not spill (local-memory loads on its critical path)
     if (warp == 16) {
       // ===================== TMA producer: this CTA's 64 rows of every (layer, N-half, K chunk), once per quad =====================
       if (lane == 0) {
@@ -843,74 +845,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) mlp_fo
       // ===================== MMA issuers (leader CTA): warp 18 -> tile slot X, warp 19 -> tile slot Y =====================
       // Two independent issuers: while one sits in an mbarrier wait (~200 cycles even when it succeeds) the other
       // keeps the tensor pipe fed.  The order X.h0, Y.h0, X.h1, Y.h1 emerges from the dependencies.
+      // The issue code is straight-line per (layer, N-half) block and spill-free: every cycle this warp loses delays the MMAs.
       const int T = warp - 18;
       uint32_t act_phase = 0, hi_phase = 0, j = 0;
-      int slot0 = 0;
-      long long t_act = 0, t_full = 0, t_begin = clock64();
+      PROF_DECL;
       TRACE_DECL(0);
       const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
       const uint32_t sbase = smem_u32(smem);
-      const uint32_t t_slot = tmem_base + T * 256;
+      const uint32_t tA = tmem_base + T * 256;        // A operand columns of this slot
+      const uint32_t tDm = tA + 128;                  // accumulator half
       const uint32_t pe_lo = desc_lo2(sbase + kSmemPE2 + T * kActChunk);
       const uint32_t w_lo = desc_lo2(sbase + kSmemW2);
+      const uint32_t w_end = w_lo + kSlots * (kSlotBytes2 >> 4);
+      uint32_t bpos = w_lo;                           // ring position (descriptor low word) of the next K chunk
+      auto next_slot = [&](uint32_t b) { b += (kSlotBytes2 >> 4); return b == w_end ? w_lo : b; };
       for (int64_t it = first_it; it < n_quads; it += it_stride) {
         TRACE_ARM(blockIdx.x == 0 && T == 0 && lane == 0 && it == first_it + 3 * it_stride);
+#pragma unroll 1
         for (int s = 0; s < kNumSteps; ++s) {
-          const int n = step_nchunks(s);
           const int nh = (s == 9) ? 1 : 2;
+#pragma unroll 1
           for (int h = 0; h < nh; ++h, ++j) {
-            {
-              TRACE(s * 64 + h * 32 + 0);
-              long long t0 = clock64();
-              mbar_wait(&bar_act[T], act_phase);
-              TRACE(s * 64 + h * 32 + 1);
-              t_act += clock64() - t0;
-              act_phase ^= 1;
-              t0 = clock64();
-              mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);   // both CTAs' parts of the group have landed
-              t_full += clock64() - t0;
-              TRACE(s * 64 + h * 32 + 5);
-              tc_fence_after();
+            // chunk order inside the block: [PE (s = 0, 5)] [A cols 0..63: K chunks 1, 2] [A cols 64..127: K chunks 3, 4] [PE(viewdir) (s = 9)]
+            const bool pe_first = (s == 0) || (s == 5);
+            const uint32_t b0 = bpos;                               // PE chunk (if pe_first)
+            const uint32_t b1 = pe_first ? next_slot(b0) : b0;      // K chunk 1
+            const uint32_t b2 = next_slot(b1), b3 = next_slot(b2), b4 = next_slot(b3);
+            const uint32_t b5 = next_slot(b4);                      // PE(viewdir) chunk (s == 9) / next block
+            bpos = (s == 0) ? b1 : ((s == 9) ? next_slot(b5) : b5);
+            uint64_t* gempty = &bar_gempty[j % kG];
+            PROF_T0;
+            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);   // both CTAs' parts of the group have landed (normally long ago)
+            PROF_ADD(t_full);
+            TRACE(s * 64 + h * 32 + 0);
+            PROF_T0;
+            mbar_wait(&bar_act[T], act_phase);              // s = 0: PE ready; h = 0: A[0,128) ready; always: accumulator drained
+            TRACE(s * 64 + h * 32 + 1);
+            PROF_ADD(t_act);
+            act_phase ^= 1;
+            tc_fence_after();
+            if (elect_one_sync()) {
+              if (pe_first) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ss(tDm, pe_lo + kk * 2, b0 + kk * 2, idesc, kk > 0 ? 1u : 0u);
+              }
+              if (s > 0) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + kk * 8, b1 + kk * 2, idesc, (pe_first || kk > 0) ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 32 + kk * 8, b2 + kk * 2, idesc, 1u);
+              } else {
+                umma_commit_2cta(gempty, 3);
+                umma_commit_2cta(&bar_acc[T], 3);
+              }
             }
-            bool hi_ready = (s == 0) || (h == 1);   // A[128,256) is signalled separately by the previous layer's epilogue
-            int slot = slot0;
-            for (int ci = 0; ci < n; ++ci) {
-              const int src = step_asrc(s, ci);
-              if (!hi_ready && src >= 3) {
+            __syncwarp();
+            if (s > 0) {
+              if (h == 0) {   // A[128,256) is signalled separately by the previous layer's epilogue
                 TRACE(s * 64 + h * 32 + 2);
-                long long t0 = clock64();
+                PROF_T0;
                 mbar_wait(&bar_hi[T], hi_phase);
                 TRACE(s * 64 + h * 32 + 3);
-                t_act += clock64() - t0;
+                PROF_ADD(t_act);
                 hi_phase ^= 1;
                 tc_fence_after();
-                hi_ready = true;
               }
-              const uint32_t b_lo = w_lo + (uint32_t)slot * (kSlotBytes2 >> 4);
-              const int ksteps = (s == 9 && ci == 4) ? 2 : 4;   // viewdir PE has 27 (<32) channels
               if (elect_one_sync()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  if (kk < ksteps) {
-                    const uint32_t accum = (ci > 0 || kk > 0) ? 1u : 0u;
-                    if (src == 0) mma2_ss(t_slot + 128, pe_lo + kk * 2, b_lo + kk * 2, idesc, accum);
-                    else mma2_ts(t_slot + 128, t_slot + (src - 1) * 32 + kk * 8, b_lo + kk * 2, idesc, accum);
-                  }
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 64 + kk * 8, b3 + kk * 2, idesc, 1u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 96 + kk * 8, b4 + kk * 2, idesc, 1u);
+                if (s == 9) {   // viewdir PE has 27 (< 32) channels: two K steps
+                  mma2_ss(tDm, pe_lo, b5, idesc, 1u);
+                  mma2_ss(tDm, pe_lo + 2, b5 + 2, idesc, 1u);
                 }
-                if (ci == n - 1) {
-                  umma_commit_2cta(&bar_gempty[j % kG], 3);   // this issuer is done with the group (both CTAs)
-                  umma_commit_2cta(&bar_acc[T], 3);
-                }
+                umma_commit_2cta(gempty, 3);            // this issuer is done with the group (both CTAs)
+                umma_commit_2cta(&bar_acc[T], 3);
               }
               __syncwarp();
-              if (++slot == kSlots) slot = 0;
             }
             TRACE(s * 64 + h * 32 + 4);
-            slot0 = slot;
           }
         }
       }
-      if (blockIdx.x == 0 && T == 0 && lane == 0) { g_prof[0] = t_act; g_prof[1] = t_full; g_prof[2] = clock64() - t_begin; }
+      PROF_STORE;
     }
   }
 
@@ -976,6 +994,7 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
   p.raw = reinterpret_cast<float4*>(raw);
   p.stash = static_cast<uint8_t*>(stash);
   p.n_tiles = mlp::num_tiles(pts->n_points);
+  { static int fl = -1; if (fl < 0) { const char* e = getenv("MVIP_EXP_FLAGS"); fl = e ? atoi(e) : 0; } p.flags = fl; }
   if (mlp::use_cta_pairs()) {
     const int64_t n_quads = (p.n_tiles + 3) / 4;
     const int max_clusters = mvip_num_sms() / 2;

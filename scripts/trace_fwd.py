@@ -25,7 +25,7 @@ for role in range(3):
 ev.sort()
 t0 = ev[0][0]
 ISS = {0: "act-wait>", 1: "act-wait<", 2: "hi-wait>", 3: "hi-wait<", 4: "issued", 5: "weights ok"}
-EPI = {0: "h0 acc-wait>", 1: "h0 wake", 2: "h0 loaded", 3: "h0 arrived(D free)", 4: "h1 acc-wait>", 5: "h1 wake", 6: "h1 loaded+st lo", 7: "h1 arrived(A lo)", 8: "h1 math done", 9: "h1 st hi done"}
+EPI = {0: "h0 acc-wait>", 1: "h0 wake", 2: "h0 loaded", 3: "h0 arrived(D free)", 4: "h1 acc-wait>", 5: "h1 wake", 6: "h1 loaded+st lo", 7: "h1 arrived(A lo)", 9: "h1 st hi done"}
 for t, role, code in ev:
     if role == 0:
         s, h, k = code // 64, (code // 32) & 1, code & 31

@@ -12,6 +12,8 @@ void mvip_set_error(const char*, ...) {}
 __device__ int g_commit_every = 16;
 __device__ int g_commit_mask = 1;
 __device__ int g_alt = 0;
+__device__ int g_acol = 256;
+__device__ int g_dcol = 0;
 struct Res { unsigned long long cyc; unsigned long long noise_bytes; };
 
 // kCta: 1 or 2; ts: A from TMEM; N: MMA N; noise_gap: cycles of spin between noise stores (0 = no noise)
@@ -41,17 +43,17 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
       const uint32_t idesc = umma_idesc_bf16(128 * kCta, N, 0, 0);
       const uint32_t sb = smem_u32(smem);
       long long t0 = clock64();
-      const int ce = g_commit_every, cmask = g_commit_mask, alt = g_alt;
+      const int ce = g_commit_every, cmask = g_commit_mask, alt = g_alt, acol = g_acol, dcol = g_dcol;
       for (int it = 0; it < iters; ++it) {
         if (elect_one_sync()) {
-          const uint32_t d_t = tmem_base + ((alt && (it & 1)) ? 128 : 0);
+          const uint32_t d_t = tmem_base + dcol + ((alt && (it & 1)) ? 128 : 0);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               uint64_t db = umma_desc_sw128(sb + 65536 + c * b_img + kk * 32, 16, 1024);
               if (ts) {
-                uint32_t ta = tmem_base + 256 + c * 32 + kk * 8;
+                uint32_t ta = tmem_base + acol + c * 32 + kk * 8;
                 if (kCta == 2) umma_bf16_ts_2cta(d_t, ta, db, idesc, 1u); else umma_bf16_ts(d_t, ta, db, idesc, 1u);
               } else {
                 uint64_t da = umma_desc_sw128(sb + c * 16384 + kk * 32, 16, 1024);
@@ -214,11 +216,11 @@ void run_mma(int ts, int N, int gap, Res* d_res, int grid) {
 
 int main() {
   Res* d_res; CK(cudaMalloc(&d_res, sizeof(Res) * 148));
-  for (int alt = 0; alt < 2; ++alt)
-  for (int mask : {1, 3})
-    for (int ce : {16, 4, 2, 1}) {
-      CK(cudaMemcpyToSymbol(g_commit_every, &ce, 4)); CK(cudaMemcpyToSymbol(g_commit_mask, &mask, 4)); CK(cudaMemcpyToSymbol(g_alt, &alt, 4));
-      printf("alt_D=%d commit every %2d MMAs, mask %d: ", alt, ce, mask);
+  for (int acol : {256, 0, 128, 384})
+    for (int dcol : {0, 128, 256, 384}) {
+      if (acol == dcol) continue;
+      CK(cudaMemcpyToSymbol(g_acol, &acol, 4)); CK(cudaMemcpyToSymbol(g_dcol, &dcol, 4));
+      printf("A cols [%d,+128) D cols [%d,+128): ", acol, dcol);
       run_mma<2>(1, 128, 0, d_res, 148);
     }
   { int ce = 16, mask = 1, alt = 0; CK(cudaMemcpyToSymbol(g_commit_every, &ce, 4)); CK(cudaMemcpyToSymbol(g_commit_mask, &mask, 4)); CK(cudaMemcpyToSymbol(g_alt, &alt, 4)); }
