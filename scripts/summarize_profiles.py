@@ -1,0 +1,61 @@
+"""gpurun_out/launches.csv + gpurun_out/prof.ncu-rep (scripts/profile.sh) -> profiles/rNN_*.{md,csv}.
+usage: python scripts/summarize_profiles.py r01"""
+import collections, csv, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+def short(k):
+    return k.replace("void ", "").replace("at::native::", "").replace("<unnamed>::", "")
+
+# ---- launch list ------------------------------------------------------------------------------------
+lines = [l for l in open(os.path.join(G, "launches.csv")) if l.startswith('"')]
+open(os.path.join(P, tag + "_launches.csv"), "w").writelines(lines)
+r = csv.reader(lines); hdr = next(r)
+ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+seq = [(short(row[ki]), float(row[vi].replace(",", "")) / 1000.0) for row in r]
+idx = [i for i, (k, _) in enumerate(seq) if k.startswith("sample_coarse_kernel")]
+step = seq[idx[-2]:idx[-1]]
+agg = collections.OrderedDict()
+for k, v in step:
+    k = k.split("(")[0][:80]
+    agg.setdefault(k, [0, 0.0]); agg[k][0] += 1; agg[k][1] += v
+tot = sum(v for _, v in agg.values())
+with open(os.path.join(P, tag + "_launches_summary.md"), "w") as f:
+    f.write("# %s - ncu launch list of `python bench.py --steps 2 --warmup 3` (first 400 launches), ONE training step\n\n" % tag)
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` on one B200 (scripts/profile.sh); times are cold-cache and "
+            "serialised - compare SHARES.  The step shown is the last complete one in the capture (%d launches, %.1f us).\n\n" % (len(step), tot))
+    f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+    for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("| `%s` | %d | %.1f | %.1f%% |\n" % (k, n, v, 100 * v / tot))
+
+# ---- full capture --------------------------------------------------------------------------------------
+raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+open(os.path.join(P, tag + "_ncu_full_raw.csv"), "w").write(raw)
+rows = list(csv.reader(raw.splitlines()))
+hdr, rows = rows[0], rows[2:]
+col = {h: i for i, h in enumerate(hdr)}
+def g(r, name):
+    return float(r[col[name]].replace(",", "")) if name in col and r[col[name]] not in ("", "n/a") else float("nan")
+seen = collections.OrderedDict()
+for r in rows:
+    name = short(r[col["Kernel Name"]]).split("(")[0]
+    grid = r[col["Grid Size"]] if "Grid Size" in col else ""
+    dur = g(r, "gpu__time_duration.sum")
+    key = (name, round(g(r, "dram__bytes_read.sum") + g(r, "dram__bytes_write.sum"), 1))
+    if key in seen:
+        continue
+    seen[key] = (name, dur, g(r, "dram__bytes_read.sum"), g(r, "dram__bytes_write.sum"),
+                 g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                 g(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                 g(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                 g(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                 g(r, "launch__registers_per_thread"))
+with open(os.path.join(P, tag + "_kernels_ncu.md"), "w") as f:
+    f.write("# %s - `ncu --set full` of the training kernels inside one bench step (B200, cfg 2: 4096 rays, P = 262,144 / 524,288 points)\n\n" % tag)
+    f.write("Command: `scripts/profile.sh`.  Raw metric dump: `%s_ncu_full_raw.csv`.  Durations under ncu are serialised; DRAM bytes are per launch "
+            "(units as printed by ncu: us, Gbyte).\n\n" % tag)
+    f.write("| kernel | duration us | dram read GB | dram write GB | dram % peak | tensor pipe active % | L2 % | smem wavefronts % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+    for v in seen.values():
+        f.write("| `%s` | %.1f | %.3f | %.3f | %.1f | %.1f | %.1f | %.1f | %d |\n" % v)
+print("wrote profiles/%s_*" % tag)
