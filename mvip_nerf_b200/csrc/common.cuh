@@ -123,6 +123,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // wait until the smem sources of all committed bulk stores have been read
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the most recent committed bulk store have finished reading their smem source (double-buffered staging)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -14,7 +14,8 @@
 //   3. head_grads_kernel   CUDA cores: alpha_linear / rgb_linear weight + bias grads (N = 1 and 3).
 //   4. reduce_kernel       deterministic (fixed-order) sum of the partials into the caller's grad tensors.
 // No gradient flows to pts / viewdirs (none is required by the reference: z_samples is detached, run.py:1812).
-#include "mlp_common.cuh"
+#include "mlp_pair.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace mlp;
@@ -255,6 +256,289 @@ __global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainPa
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// 1b. dgrad chain, CTA pairs (cta_group::2) with the gradient tiles resident in tensor memory - same skeleton as
+//     mlp_forward_pair_kernel (mlp_forward.cu): two tile slots per CTA, one N-half (128 columns) of a layer per block of
+//     MMAs, A operand (the previous dZ, bf16) in TMEM columns [0,128) of the slot, accumulator half in [128,256);
+//     two independent issuer warps; weights (transposed chunks) in a ring of 8 KB slots shared by the two slots.
+//     Every dZ tile image is also staged in shared memory (double-buffered, 2 x 32 KB per slot) and bulk-stored.
+// =================================================================================================
+constexpr int kDThreads = 640;
+constexpr int kDSlots = 10, kDLag = 2;                                   // groups have 2 or 4 slots: 4 + 4 <= 10
+constexpr uint32_t kDSmemHeads = 0;                                      // w_alpha[256], W_rgb[3][128] fp32 (2,560 B)
+constexpr uint32_t kDSmemW = 3072;                                       // weight ring
+constexpr uint32_t kDSmemStg = kDSmemW + kDSlots * kSlotBytes2;          // staging: [slot][buffer] x 2 chunk images
+constexpr uint32_t kDSmemBytes = kDSmemStg + 2 * 2 * 2 * kActChunk;      // 216,064
+constexpr int kDGroupsPerIter = 18;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_pair_kernel(const ChainParams p) {
+  constexpr int kG = kGroupBars2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_gfull[kG], bar_gempty[kG], bar_acc[2], bar_act[2], bar_hi[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t n_quads = (p.n_tiles + 3) / 4;
+  const int64_t first_it = blockIdx.x >> 1, it_stride = gridDim.x >> 1;
+  const uint8_t* wT = p.packed + kFwdBytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < kG; ++i) {
+      mbar_init(&bar_gfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
+      mbar_init(&bar_gempty[i], 2);                  // multicast tcgen05.commit of the two issuer warps
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 16); mbar_init(&bar_hi[i], 16); }
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc_2cta(&tmem_base_s, 512);
+  {
+    const float* sm = reinterpret_cast<const float*>(p.packed + kSmallOff);
+    float* heads_s = reinterpret_cast<float*>(smem + kDSmemHeads);
+    for (int i = tid; i < 256; i += kDThreads) heads_s[i] = __ldg(sm + kSmWAlpha + i);
+    for (int i = tid; i < 384; i += kDThreads) heads_s[256 + i] = __ldg(sm + kSmWRgb + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 16) {
+    // ===================== epilogue warps: slot T = warp/8, TMEM lane quarter q = warp%4, column half ch of every N-half =====================
+    reg_inc<104>();
+    const int T = warp >> 3, q = warp & 3, ch = (warp & 7) >> 2;
+    const int r = q * 32 + lane;
+    const bool leader = (warp & 7) == 0 && lane == 0;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t tA = tmem_base + lane_base + T * 256;
+    const uint32_t tD = tA + 128 + ch * 64;
+    const uint32_t bar_id = 1 + T;
+    const uint32_t heads_a = smem_u32(smem + kDSmemHeads);
+    uint8_t* stg_slot = smem + kDSmemStg + T * 4 * kActChunk;
+    uint32_t acc_phase = 0, stg_buf = 0;
+
+    auto act_arrive = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&bar_act[T]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
+      }
+    };
+    auto hi_arrive = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&bar_hi[T]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi[T]), 0));
+      }
+    };
+
+    for (int64_t it = first_it; it < n_quads; it += it_stride) {
+      const int64_t tile = 4 * it + 2 * T + (int64_t)rank;
+      const bool tile_valid = tile < p.n_tiles;
+      const int64_t g = tile * kTile + r;
+      const bool valid = tile_valid && g < p.n_points;
+      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
+
+      // packed bf16 rows of both column halves -> staging images (double-buffered) -> one 32 KB bulk store into the dZ stash
+      auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32]) {
+        uint8_t* buf = stg_slot + stg_buf * 2 * kActChunk;
+        stg_buf ^= 1;
+        if (leader) tma_store_wait_read1();     // the store issued two calls ago has finished reading this buffer
+        named_bar_sync(bar_id, 256);
+        uint8_t* img = buf + ch * kActChunk;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq)
+          *reinterpret_cast<uint4*>(img + chunk_off16(r, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 256);
+        if (leader) {
+          if (tile_valid) tma_store_1d(dz_tile + (size_t)first_chunk * kActChunk, buf, 2 * kActChunk);
+          tma_store_commit();                   // (possibly empty) group: keeps the wait_group accounting uniform
+        }
+      };
+
+      uint32_t pk[32];
+      const float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      {  // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0] -> A columns [0,64) (K = 128) of step 0
+        const uint2 mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + ((size_t)8 * 128 + r) * 8 + 2 * ch)) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c0 = ch * 64 + 16 * b;
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            float4 w0, w1, w2;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0.x), "=f"(w0.y), "=f"(w0.z), "=f"(w0.w) : "r"(heads_a + (256 + c0 + 4 * j4) * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w1.x), "=f"(w1.y), "=f"(w1.z), "=f"(w1.w) : "r"(heads_a + (384 + c0 + 4 * j4) * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w) : "r"(heads_a + (512 + c0 + 4 * j4) * 4));
+            v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+            v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+            v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+            v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+          }
+          const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
+        }
+        tmem_st32(tA + ch * 32, pk);            // the previous tile's last MMAs are complete (its last accumulator was drained)
+        tmem_st_wait();
+        tc_fence_before();
+        act_arrive();                           // step 0 may start
+        stage_out(kDzHidden, pk);
+      }
+
+#pragma unroll 1
+      for (int s = 0; s < kCSteps; ++s) {
+        // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
+        const int first_chunk = (s == 0) ? kDzFeat : kDzTrunk + 4 * (s - 1);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint2 mw = make_uint2(~0u, ~0u);
+          if (s >= 1) mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + ((size_t)(8 - s) * 128 + r) * 8 + 2 * (2 * h + ch))) : make_uint2(0u, 0u);
+          else if (!valid) mw = make_uint2(0u, 0u);
+          {
+            uint32_t raw[4][16];
+            mbar_wait(&bar_acc[T], acc_phase);
+            acc_phase ^= 1;
+            tc_fence_after();
+            if (h == 1 && s < kCSteps - 1) tmem_st32(tA + ch * 32, pk);      // half 0 of dZ -> next A operand, K columns [0,128)
+            load_half(tD, raw);
+            if (h == 1 && s < kCSteps - 1) tmem_st_wait();
+            tc_fence_before();
+            if (h == 0 || s < kCSteps - 1) act_arrive();   // h = 0: accumulator drained; h = 1: A[0,128) ready + accumulator drained
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float v[16];
+              if (s == 1) {
+                const int c0 = h * 128 + ch * 64 + 16 * b;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  float4 w;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(heads_a + (c0 + 4 * j4) * 4));
+                  v[4 * j4 + 0] = __uint_as_float(raw[b][4 * j4 + 0]) + dr.w * w.x;
+                  v[4 * j4 + 1] = __uint_as_float(raw[b][4 * j4 + 1]) + dr.w * w.y;
+                  v[4 * j4 + 2] = __uint_as_float(raw[b][4 * j4 + 2]) + dr.w * w.z;
+                  v[4 * j4 + 3] = __uint_as_float(raw[b][4 * j4 + 3]) + dr.w * w.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[b][j]);
+              }
+              const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
+            }
+          }
+          if (h == 1 && s < kCSteps - 1) {
+            tmem_st32(tA + 64 + ch * 32, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            hi_arrive();                        // A[128,256) ready
+          }
+          stage_out(first_chunk + 2 * h, pk);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all0();
+  } else {
+    reg_dec<64>();
+    if (warp == 16) {
+      // ===================== TMA producer: this CTA's 64 rows of every (step, N-half, K chunk), once per quad =====================
+      if (lane == 0) {
+        uint32_t j = 0; int slot = 0;
+        for (int64_t it = first_it; it < n_quads; it += it_stride) {
+          int cbase = 0;
+          for (int s = 0; s < kCSteps; ++s) {
+            const int n = chain_nchunks(s);
+            for (int h = 0; h < 2; ++h, ++j) {
+              if (j >= (uint32_t)kDLag) mbar_wait(&bar_gempty[(j - kDLag) % kG], ((j - kDLag) / kG) & 1u);
+              uint64_t* full = &bar_gfull[j % kG];
+              mbar_arrive_expect_tx(full, (uint32_t)n * kSlotBytes2);
+              for (int ci = 0; ci < n; ++ci) {
+                const uint8_t* src = wT + (size_t)(cbase + ci) * kW256 + (size_t)(2 * h + (int)rank) * kSlotBytes2;
+                tma_load_1d(smem + kDSmemW + slot * kSlotBytes2, src, kSlotBytes2, full);
+                if (++slot == kDSlots) slot = 0;
+              }
+            }
+            cbase += n;
+          }
+        }
+      }
+    } else if (warp == 19 && rank == 1) {
+      if (lane == 0) {
+        uint32_t j = 0;
+        for (int64_t it = first_it; it < n_quads; it += it_stride) {
+          for (int c = 0; c < kDGroupsPerIter; ++c, ++j) {
+            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
+          }
+        }
+      }
+    } else if (warp >= 18 && rank == 0) {
+      // ===================== MMA issuers (leader CTA): warp 18 -> slot X, warp 19 -> slot Y =====================
+      const int T = warp - 18;
+      uint32_t act_phase = 0, hi_phase = 0, j = 0;
+      const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
+      const uint32_t tA = tmem_base + T * 256;
+      const uint32_t tDm = tA + 128;
+      const uint32_t w_lo = desc_lo2(smem_u32(smem) + kDSmemW);
+      const uint32_t w_end = w_lo + kDSlots * (kSlotBytes2 >> 4);
+      uint32_t bpos = w_lo;
+      auto next_slot = [&](uint32_t b) { b += (kSlotBytes2 >> 4); return b == w_end ? w_lo : b; };
+      for (int64_t it = first_it; it < n_quads; it += it_stride) {
+#pragma unroll 1
+        for (int s = 0; s < kCSteps; ++s) {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h, ++j) {
+            const uint32_t b1 = bpos, b2 = next_slot(b1), b3 = next_slot(b2), b4 = next_slot(b3);
+            bpos = (s == 0) ? b3 : next_slot(b4);
+            uint64_t* gempty = &bar_gempty[j % kG];
+            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
+            mbar_wait(&bar_act[T], act_phase);
+            act_phase ^= 1;
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + kk * 8, b1 + kk * 2, idesc, kk > 0 ? 1u : 0u);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 32 + kk * 8, b2 + kk * 2, idesc, 1u);
+              if (s == 0) {
+                umma_commit_2cta(gempty, 3);
+                umma_commit_2cta(&bar_acc[T], 3);
+              }
+            }
+            __syncwarp();
+            if (s > 0) {
+              if (h == 0) {
+                mbar_wait(&bar_hi[T], hi_phase);
+                hi_phase ^= 1;
+                tc_fence_after();
+              }
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 64 + kk * 8, b3 + kk * 2, idesc, 1u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 96 + kk * 8, b4 + kk * 2, idesc, 1u);
+                umma_commit_2cta(gempty, 3);
+                umma_commit_2cta(&bar_acc[T], 3);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // =================================================================================================
@@ -698,12 +982,22 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     cp.dz = wsb + ws.dz;
     cp.n_points = n_points;
     cp.n_tiles = n_tiles;
-    const int64_t n_pairs = (n_tiles + 1) / 2;
-    const int grid = (int)(n_pairs < sms ? n_pairs : sms);
-    const size_t smem = kCSmemBytes + 2560 + 128;
-    MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
-    MVIP_LAUNCH_OK("dgrad_chain_kernel");
+    if (mlp::use_cta_pairs()) {
+      const int64_t n_quads = (n_tiles + 3) / 4;
+      const int max_clusters = sms / 2;
+      const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
+      const size_t smem2 = kDSmemBytes + 1024;
+      MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      dgrad_pair_kernel<<<grid2, kDThreads, smem2, st>>>(cp);
+      MVIP_LAUNCH_OK("dgrad_pair_kernel");
+    } else {
+      const int64_t n_pairs = (n_tiles + 1) / 2;
+      const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+      const size_t smem = kCSmemBytes + 2560 + 128;
+      MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
+      MVIP_LAUNCH_OK("dgrad_chain_kernel");
+    }
   }
   // 2. wgrad
   const int w_grid = sms;

@@ -13,7 +13,7 @@
 // other tile's MMAs.  Activations never leave the SM; the only HBM traffic at inference is
 // 16..28 B/point in (rays+z) and 16 B/point out (raw).  With a stash pointer (training) every layer's
 // input tile image is also bulk-stored for the backward pass (mlp_common.cuh, kStash*).
-#include "mlp_common.cuh"
+#include "mlp_pair.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -480,7 +480,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p
 //     multicasts "stage free" / "accumulator full" to both CTAs.
 // =================================================================================================
 constexpr int kThreads2 = 640;
-constexpr uint32_t kSlotBytes2 = 64 * 128;                               // 64 weight rows x 64 k (bf16)
 // weight ring: 8 KB slots, filled and released in GROUPS = all K chunks of one (layer, N-half): 1, 4 or 5 slots.
 // One full / one empty barrier per group (a successful mbarrier wait costs the issuer ~200 cycles, so per-chunk
 // barriers would eat a third of its time).  The producer runs kLag groups ahead.
@@ -488,7 +487,6 @@ template <bool kTrain> struct Ring2 {
   static constexpr int kSlots = kTrain ? 12 : 20;
   static constexpr int kLag = kTrain ? 2 : 4;      // any kLag consecutive groups fit: 5+5 <= 12, 4+5+5+4 <= 20
 };
-constexpr int kGroupBars2 = 4;
 constexpr uint32_t kSmemPE2 = 0;                                         // pe[2]: 2 x 16 KB
 constexpr uint32_t kSmemSmall2 = 2 * kActChunk;                          // fp32 tail of the packed blob (12,320 B)
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
@@ -498,43 +496,6 @@ constexpr uint32_t kSmemBytes2Train = kSmemStg2 + 4 * kActChunk;         // 214,
 constexpr uint32_t kSmemBytes2Infer = kSmemW2 + Ring2<false>::kSlots * kSlotBytes2;   // 214,016
 constexpr int kGroupsPerIter2 = 19;
 
-// UMMA smem descriptor (SWIZZLE_128B, K-major, LBO 16 B, SBO 1024 B) split into its two words, so that the issuer
-// only adds to the low word: lo = (addr >> 4) | (1 << 16), hi = 64 | version 1 (bit 14) | layout 2 (bits 29..31)
-constexpr uint32_t kDescHi2 = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo2(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
-__device__ __forceinline__ void mma2_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
-      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
-      : "memory");
-}
-__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d),
-      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
-      : "memory");
-}
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
-// This thread's 64 accumulator columns -> registers (four loads in flight, one round trip).
-__device__ __forceinline__ void load_half(uint32_t tD, uint32_t (&raw)[4][16]) {
-  tmem_ld16(tD, raw[0]);
-  tmem_ld16(tD + 16, raw[1]);
-  tmem_ld16(tD + 32, raw[2]);
-  tmem_ld16(tD + 48, raw[3]);
-  tmem_ld_wait_on16(raw[0]);
-  tmem_ld_wait_on16(raw[1]);
-  tmem_ld_wait_on16(raw[2]);
-  tmem_ld_wait_on16(raw[3]);
-}
 // One accumulator half (row r, 64 of its 128 columns) -> +bias, (ReLU), bf16 pairs in pk[32].
 // ONE code instance for all layers (s is warp-uniform): the steady-state loop of the kernel has to stay inside the
 // 32 KB instruction cache, otherwise the single MMA-issuing warp starves on instruction fetches.
