@@ -288,11 +288,14 @@ def run_ours(a):
         per_kernel[name] = {"launches_per_step": len(vals) / a.steps, "ms_per_step": sum(vals) / a.steps,
                             "share_of_step": sum(vals) / a.steps / ms_step}
     npts = pts["coarse"] + pts["fine"]
-    flops = {"mvip_mlp_forward": FLOP_FWD * npts, "dgrad_chain_kernel": FLOP_DGRAD * npts, "wgrad_kernel": FLOP_WGRAD * npts}
+    flops = {"mvip_mlp_forward": FLOP_FWD * npts, "dgrad_chain_kernel": FLOP_DGRAD * npts, "wgrad_kernel": FLOP_WGRAD * npts,
+             "backward_fused_kernel": (FLOP_DGRAD + FLOP_WGRAD) * npts}
     # algorithmic HBM bytes per point of the training kernels: forward writes the activation stash,
     # the dgrad chain reads the ReLU masks and writes the dZ stash, wgrad reads both stashes (bf16 chunk images only)
     hbm_bytes = {"mvip_mlp_forward": (HBM_FWD_TRAIN, "write"), "dgrad_chain_kernel": (HBM_DGRAD, "write"),
-                 "wgrad_kernel": (HBM_WGRAD, "read"), "head_grads_kernel": (HBM_HEADS, "read")}
+                 "wgrad_kernel": (HBM_WGRAD, "read"), "head_grads_kernel": (HBM_HEADS, "read"),
+                 # fused backward: the dZ stash is written once and re-read by the concurrent wgrad CTAs out of L2
+                 "backward_fused_kernel": (HBM_DGRAD + 40 * 128, "read+write")}
     top = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     for k in flops:

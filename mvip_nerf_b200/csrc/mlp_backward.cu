@@ -37,7 +37,9 @@ struct ChainParams {
   uint8_t* dz;
   int64_t n_points;
   int64_t n_tiles;
+  uint32_t* flags;      // fused backward: [n_tiles][kFlagsPerTile] "dZ group stored" flags for the concurrent wgrad CTAs, or null
 };
+constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
 
 __device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
 
@@ -273,7 +275,8 @@ constexpr uint32_t kDSmemStg = kDSmemW + kDSlots * kSlotBytes2;          // stag
 constexpr uint32_t kDSmemBytes = kDSmemStg + 2 * 2 * 2 * kActChunk;      // 216,064
 constexpr int kDGroupsPerIter = 18;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_pair_kernel(const ChainParams p) {
+// first_it / it_stride: this cluster's first tile quad and the number of clusters working on the chain
+__device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int64_t first_it, const int64_t it_stride) {
   constexpr int kG = kGroupBars2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -283,7 +286,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int64_t n_quads = (p.n_tiles + 3) / 4;
-  const int64_t first_it = blockIdx.x >> 1, it_stride = gridDim.x >> 1;
   const uint8_t* wT = p.packed + kFwdBytes;
 
   if (tid == 0) {
@@ -320,6 +322,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
     const uint32_t heads_a = smem_u32(smem + kDSmemHeads);
     uint8_t* stg_slot = smem + kDSmemStg + T * 4 * kActChunk;
     uint32_t acc_phase = 0, stg_buf = 0;
+    uint32_t* flag_prev1 = nullptr;   // leader only: flags of the two most recent bulk stores, not yet published
+    uint32_t* flag_prev2 = nullptr;
 
     auto act_arrive = [&]() {
       __syncwarp();
@@ -345,10 +349,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
 
       // packed bf16 rows of both column halves -> staging images (double-buffered) -> one 32 KB bulk store into the dZ stash
-      auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32]) {
+      // flag_id >= 0: this store completes dZ group `flag_id` of the tile.  The flag is published two calls later, when
+      // cp.async.bulk.wait_group 1 has shown the store to be complete (written), not merely read out of shared memory.
+      auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32], int flag_id) {
         uint8_t* buf = stg_slot + stg_buf * 2 * kActChunk;
         stg_buf ^= 1;
-        if (leader) tma_store_wait_read1();     // the store issued two calls ago has finished reading this buffer
+        if (leader) {
+          if (p.flags) {
+            tma_store_wait_all1();              // every store but the latest is complete; so is its smem read
+            if (flag_prev2) { fence_proxy_async_all(); st_release_gpu(flag_prev2, 1u); }
+            flag_prev2 = flag_prev1;
+            flag_prev1 = (flag_id >= 0 && tile_valid) ? p.flags + (size_t)tile * kFlagsPerTile + flag_id : nullptr;
+          } else {
+            tma_store_wait_read1();             // the store issued two calls ago has finished reading this buffer
+          }
+        }
         named_bar_sync(bar_id, 256);
         uint8_t* img = buf + ch * kActChunk;
 #pragma unroll
@@ -389,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
         tmem_st_wait();
         tc_fence_before();
         act_arrive();                           // step 0 may start
-        stage_out(kDzHidden, pk);
+        stage_out(kDzHidden, pk, 0);
       }
 
 #pragma unroll 1
@@ -440,11 +455,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
             tc_fence_before();
             hi_arrive();                        // A[128,256) ready
           }
-          stage_out(first_chunk + 2 * h, pk);
+          stage_out(first_chunk + 2 * h, pk, h == 1 ? 1 + s : -1);
         }
       }
     }
-    if (leader) tma_store_wait_all0();
+    if (leader) {
+      tma_store_wait_all0();
+      if (p.flags) {
+        fence_proxy_async_all();
+        if (flag_prev2) st_release_gpu(flag_prev2, 1u);
+        if (flag_prev1) st_release_gpu(flag_prev1, 1u);
+      }
+    }
   } else {
     reg_dec<64>();
     if (warp == 16) {
@@ -541,6 +563,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_
   if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_pair_kernel(const ChainParams p) {
+  dgrad_pair_body(p, blockIdx.x >> 1, gridDim.x >> 1);
+}
+
 // =================================================================================================
 // 2. wgrad
 // =================================================================================================
@@ -590,8 +616,8 @@ constexpr int kRealItems = kNumItems;
 
 struct Segment {
   int item;       // -1 = empty
-  int t0, t1;     // tile range
-  int pad;
+  int t0, t1;     // tiles t0, t0 + stride, ... < t1
+  int stride;
 };
 
 struct WParams {
@@ -601,7 +627,12 @@ struct WParams {
   float* partials;        // [grid][2] slots of kPartialSlotBytes
   float* bias_partials;   // [grid][2][256]
   Segment* segs;          // [grid][2]
+  // fused backward (tile-major): CTA b works on item i with item_first[i] <= b < item_first[i + 1] and owns the tiles
+  // t = b - item_first[i] (mod item_first[i + 1] - item_first[i]); it waits for the chain's flag of (tile, item).
+  const uint32_t* flags;  // null: stand-alone launch, cost-balanced contiguous (item, tile) ranges
+  int item_first[kNumItems + 1];
 };
+__device__ __forceinline__ int item_flag(int item) { return item <= 4 ? item : (item == 5 ? 4 : item - 1); }
 
 // Cost-balanced static schedule: CTA b owns the cost range [b*C/G, (b+1)*C/G) of the concatenated
 // (item, tile) list; boundaries are snapped to tiles.  Returns up to 2 segments.
@@ -620,7 +651,7 @@ __device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, Segment* 
     if (t0 < 0) t0 = 0;
     if (t1 > n_tiles) t1 = n_tiles;
     if (t1 > t0 && hi > base && lo < end) {
-      out[n].item = i; out[n].t0 = (int)t0; out[n].t1 = (int)t1; out[n].pad = 0;
+      out[n].item = i; out[n].t0 = (int)t0; out[n].t1 = (int)t1; out[n].stride = 1;
       ++n;
     }
     base = end;
@@ -628,7 +659,8 @@ __device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, Segment* 
   return n;
 }
 
-__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
+// cta / n_ctas: index of this CTA among the wgrad CTAs.  Uses warps 0..7 of the block (more are allowed and idle).
+__device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, const int n_ctas) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar_full[kWStages], bar_empty[kWStages], bar_acc, bar_drained;
@@ -643,11 +675,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
     mbar_init(&bar_drained, 4);
     mbar_fence_init();
     Segment sg[2];
-    sg[0].item = sg[1].item = -1; sg[0].t0 = sg[0].t1 = sg[1].t0 = sg[1].t1 = 0; sg[0].pad = sg[1].pad = 0;
-    nseg_s = schedule(blockIdx.x, gridDim.x, p.n_tiles, sg);
+    sg[0].item = sg[1].item = -1; sg[0].t0 = sg[0].t1 = sg[1].t0 = sg[1].t1 = 0; sg[0].stride = sg[1].stride = 1;
+    if (p.flags) {
+      int item = 0;
+      while (item + 1 < kNumItems && cta >= p.item_first[item + 1]) ++item;
+      const int k = cta - p.item_first[item], n_i = p.item_first[item + 1] - p.item_first[item];
+      nseg_s = 0;
+      if (k < p.n_tiles) { sg[0].item = item; sg[0].t0 = k; sg[0].t1 = (int)p.n_tiles; sg[0].stride = n_i; nseg_s = 1; }
+    } else {
+      nseg_s = schedule(cta, n_ctas, p.n_tiles, sg);
+    }
     seg_s[0] = sg[0]; seg_s[1] = sg[1];
-    p.segs[blockIdx.x * 2 + 0] = sg[0];
-    p.segs[blockIdx.x * 2 + 1] = sg[1];
+    p.segs[cta * 2 + 0] = sg[0];
+    p.segs[cta * 2 + 1] = sg[1];
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
@@ -660,22 +700,32 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint64_t pol = l2_policy_evict_first();      // both operand streams are read exactly once
       for (int sg = 0; sg < nseg; ++sg) {
         const WItem& itm = kItems[seg_s[sg].item];
         const int na = 2 * itm.m_blocks;
-        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+        const int fl = item_flag(seg_s[sg].item);
+        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
           const uint8_t* dz_tile = p.dz + (size_t)t * kDzTileBytes;
           const uint8_t* st_tile = p.stash + (size_t)t * kStashTileBytes;
+          if (p.flags) {   // the dgrad chain (other SMs of this launch) has stored this tile's dZ group
+            const uint32_t* f = p.flags + (size_t)t * kFlagsPerTile + fl;
+            long long t0 = clock64();
+            while (ld_acquire_gpu(f) == 0u) {
+              if (clock64() - t0 > 8000000000LL) { printf("mvip: wgrad flag timeout cta %d tile %d flag %d\n", cta, t, fl); __trap(); }
+            }
+            fence_proxy_async_all();
+          }
           for (int h = 0; h < 2; ++h) {
             uint8_t* sbase = smem + stage * kWStageBytes;
             mbar_wait(&bar_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(na + itm.nb) * kHalf);
             for (int j = 0; j < na; ++j)
-              tma_load_1d(sbase + kWStageA + j * kHalf, dz_tile + (size_t)(itm.a_chunk + j) * kActChunk + h * kHalf, kHalf,
-                          &bar_full[stage]);
+              tma_load_1d_hint(sbase + kWStageA + j * kHalf, dz_tile + (size_t)(itm.a_chunk + j) * kActChunk + h * kHalf, kHalf,
+                               &bar_full[stage], pol);
             for (int j = 0; j < itm.nb; ++j)
-              tma_load_1d(sbase + kWStageB + j * kHalf, st_tile + (size_t)itm.b_chunk[j] * kActChunk + h * kHalf, kHalf,
-                          &bar_full[stage]);
+              tma_load_1d_hint(sbase + kWStageB + j * kHalf, st_tile + (size_t)itm.b_chunk[j] * kActChunk + h * kHalf, kHalf,
+                               &bar_full[stage], pol);
             if (++stage == kWStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -697,7 +747,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
           tc_fence_after();
         }
         bool first = true;
-        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
           for (int h = 0; h < 2; ++h) {
             const uint32_t sbase = smem_u32(smem) + stage * kWStageBytes;
             mbar_wait(&bar_full[stage], phase);
@@ -728,7 +778,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================== bias column sums + accumulator drain =====================
     const int t4 = tid - 128;                 // 0..127
     const int w4 = warp - 4;
@@ -743,7 +793,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
       const int bg = (t4 & 31) >> 2;
       const uint32_t bw = (uint32_t)(t4 & 3) * 4;
       float b0 = 0.f, b1 = 0.f;
-      for (int t = seg_s[sg].t0; t < seg_s[sg].t1; ++t) {
+      for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&bar_full[stage], phase);
           if (do_bias) {
@@ -760,13 +810,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
           if (++stage == kWStages) { stage = 0; phase ^= 1; }
         }
       }
-      float* bias_out = p.bias_partials + ((size_t)blockIdx.x * 2 + sg) * 256;
+      float* bias_out = p.bias_partials + ((size_t)cta * 2 + sg) * 256;
       if (do_bias) { bias_out[2 * t4] = b0; bias_out[2 * t4 + 1] = b1; }
       // drain: TMEM lane i of M block m = output row 128 m + i; columns = input features
       mbar_wait(&bar_acc, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      float* part = p.partials + ((size_t)blockIdx.x * 2 + sg) * (kPartialSlotBytes / sizeof(float));
+      float* part = p.partials + ((size_t)cta * 2 + sg) * (kPartialSlotBytes / sizeof(float));
       for (int m = 0; m < itm.m_blocks; ++m) {
         float* prow = part + (size_t)(128 * m + t4) * ntot;
         for (int c0 = 0; c0 < ntot; c0 += 32) {
@@ -788,6 +838,23 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) { wgrad_body(p, blockIdx.x, gridDim.x); }
+
+// =================================================================================================
+// 2b. fused backward: the dgrad chain (CTA pairs 0 .. n_dgrad_ctas/2 - 1) and the weight-gradient GEMMs (remaining CTAs) run
+//     CONCURRENTLY in one launch of one CTA per SM.  wgrad is tile-major here: every wgrad CTA is bound to one item (layer)
+//     and consumes that layer's dZ of tile after tile as soon as the chain has stored it (per (tile, group) flags in global
+//     memory), i.e. while the 128 B/point/chunk images are still in the 126 MB L2.  Stand-alone, wgrad re-reads the
+//     whole dZ stash (4.9 KB/point) from HBM after the chain has written it; fused, that read is served by L2 and HBM sees the
+//     chain's writes overlapped with wgrad's reads of the forward stash.  The chain never waits for wgrad (dZ has its
+//     own full-size buffer), wgrad only waits for flags, and all CTAs are resident (grid <= #SMs): no deadlock.
+// =================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
+backward_fused_kernel(const ChainParams cp, const WParams wp, const int n_dgrad_ctas) {
+  if ((int)blockIdx.x < n_dgrad_ctas) dgrad_pair_body(cp, blockIdx.x >> 1, n_dgrad_ctas >> 1);
+  else wgrad_body(wp, (int)blockIdx.x - n_dgrad_ctas, (int)gridDim.x - n_dgrad_ctas);
 }
 
 // =================================================================================================
@@ -927,7 +994,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
 
 // workspace carve-up (all offsets 1024-aligned)
 struct Workspace {
-  size_t dz, partials, bias, segs, heads, total;
+  size_t dz, partials, bias, segs, heads, flags, total;
 };
 Workspace carve(int64_t n_points) {
   Workspace w;
@@ -938,6 +1005,7 @@ Workspace carve(int64_t n_points) {
   w.bias = take((size_t)kMaxCtas * 2 * 256 * sizeof(float));
   w.segs = take((size_t)kMaxCtas * 2 * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
+  w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
   return w;
 }
@@ -973,15 +1041,65 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   const int64_t n_tiles = num_tiles(n_points);
   const int sms = mvip_num_sms() < kMaxCtas ? mvip_num_sms() : kMaxCtas;
 
+  ChainParams cp;
+  cp.packed = static_cast<const uint8_t*>(packed);
+  cp.d_raw = reinterpret_cast<const float4*>(d_raw);
+  cp.stash = static_cast<const uint8_t*>(stash);
+  cp.dz = wsb + ws.dz;
+  cp.n_points = n_points;
+  cp.n_tiles = n_tiles;
+  cp.flags = nullptr;
+  WParams wp;
+  wp.stash = static_cast<const uint8_t*>(stash);
+  wp.dz = wsb + ws.dz;
+  wp.n_tiles = n_tiles;
+  wp.partials = reinterpret_cast<float*>(wsb + ws.partials);
+  wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
+  wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
+  wp.flags = nullptr;
+  for (int i = 0; i <= kNumItems; ++i) wp.item_first[i] = 0;
+  int w_grid = sms;
+
+  // 1+2 fused: chain on n_dgrad SMs, tile-major wgrad on the others (needs both phases in one call and enough tiles to fill both)
+  static int fused_env = -1, dgrad_sms_env = 0;
+  if (fused_env < 0) {
+    const char* e = getenv("MVIP_BWD_FUSED");
+    fused_env = (e && e[0] == '1') ? 1 : 0;   // opt-in: see DESIGN.md (measured 1.74 ms fused vs 1.64 ms separate at P = 524,288)
+    const char* d = getenv("MVIP_BWD_DGRAD_SMS");
+    dgrad_sms_env = d ? atoi(d) : 0;
+  }
+  const bool fused = fused_env && mlp::use_cta_pairs() && (phase_mask & 3) == 3 && sms >= 64 && sms % 2 == 0 && n_tiles >= 2 * sms;
+  if (fused) {
+    int n_dgrad = dgrad_sms_env > 0 ? dgrad_sms_env : (sms * 46 / 100);
+    n_dgrad &= ~1;
+    if (n_dgrad < 2) n_dgrad = 2;
+    if (n_dgrad > sms - kNumItems) n_dgrad = (sms - kNumItems) & ~1;
+    w_grid = sms - n_dgrad;
+    // CTAs per item proportional to its cost (largest remainder)
+    int total_cost = 0, assigned = 0, n_i[kNumItems];
+    WItem items_h[kNumItems];
+    MVIP_CUDA_OK(cudaMemcpyFromSymbol(items_h, kItems, sizeof(items_h)));
+    for (int i = 0; i < kNumItems; ++i) total_cost += items_h[i].cost;
+    for (int i = 0; i < kNumItems; ++i) { n_i[i] = w_grid * items_h[i].cost / total_cost; if (n_i[i] < 1) n_i[i] = 1; assigned += n_i[i]; }
+    while (assigned < w_grid) {   // give the next CTA to the item with the largest cost per CTA
+      int best = 0;
+      for (int i = 1; i < kNumItems; ++i)
+        if ((long long)items_h[i].cost * n_i[best] > (long long)items_h[best].cost * n_i[i]) best = i;
+      ++n_i[best]; ++assigned;
+    }
+    for (int i = 0; i < kNumItems; ++i) wp.item_first[i + 1] = wp.item_first[i] + n_i[i];
+    uint32_t* flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
+    MVIP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t), st));
+    cp.flags = flags;
+    wp.flags = flags;
+    const size_t smem = (kDSmemBytes > kWSmemBytes ? kDSmemBytes : kWSmemBytes) + 1024;
+    MVIP_CUDA_OK(cudaFuncSetAttribute(backward_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    backward_fused_kernel<<<sms, kDThreads, smem, st>>>(cp, wp, n_dgrad);
+    MVIP_LAUNCH_OK("backward_fused_kernel");
+  }
+
   // 1. dgrad chain
-  if (phase_mask & 1) {
-    ChainParams cp;
-    cp.packed = static_cast<const uint8_t*>(packed);
-    cp.d_raw = reinterpret_cast<const float4*>(d_raw);
-    cp.stash = static_cast<const uint8_t*>(stash);
-    cp.dz = wsb + ws.dz;
-    cp.n_points = n_points;
-    cp.n_tiles = n_tiles;
+  if (!fused && (phase_mask & 1)) {
     if (mlp::use_cta_pairs()) {
       const int64_t n_quads = (n_tiles + 3) / 4;
       const int max_clusters = sms / 2;
@@ -1000,15 +1118,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     }
   }
   // 2. wgrad
-  const int w_grid = sms;
-  if (phase_mask & 2) {
-    WParams wp;
-    wp.stash = static_cast<const uint8_t*>(stash);
-    wp.dz = wsb + ws.dz;
-    wp.n_tiles = n_tiles;
-    wp.partials = reinterpret_cast<float*>(wsb + ws.partials);
-    wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
-    wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
+  if (!fused && (phase_mask & 2)) {
     const size_t smem = kWSmemBytes + 1024;
     MVIP_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<<<w_grid, kWThreads, smem, st>>>(wp);

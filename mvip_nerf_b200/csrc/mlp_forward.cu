@@ -492,7 +492,8 @@ constexpr uint32_t kSmemSmall2 = 2 * kActChunk;                          // fp32
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
 constexpr uint32_t kSmemW2 = kSmemXch2 + 2 * 2048;                       // weight ring
 constexpr uint32_t kSmemStg2 = kSmemW2 + Ring2<true>::kSlots * kSlotBytes2;   // stash staging: 2 slots x 2 chunk images (train)
-constexpr uint32_t kSmemBytes2Train = kSmemStg2 + 4 * kActChunk;         // 214,016
+constexpr uint32_t kSmemMask2 = kSmemStg2 + 4 * kActChunk;               // ReLU-mask staging: [slot][step parity] x 4 KB (train)
+constexpr uint32_t kSmemBytes2Train = kSmemMask2 + 2 * 2 * 4096;         // 230,400
 constexpr uint32_t kSmemBytes2Infer = kSmemW2 + Ring2<false>::kSlots * kSlotBytes2;   // 214,016
 constexpr int kGroupsPerIter2 = 19;
 
@@ -611,8 +612,9 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
 
     // packed bf16 rows of both column halves -> staging images -> one 32 KB bulk store into the stash
-    auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32]) {
-      if (leader) tma_store_wait_read0();       // the previous bulk store has finished reading the staging images
+    // mask_layer >= 0: the 4 KB of ReLU mask words of that layer (staged by all threads before the call) go out with it
+    auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32], int mask_layer, const uint8_t* mask_stg) {
+      if (leader) tma_store_wait_read0();       // the previous bulk stores have finished reading the staging images
       named_bar_sync(bar_id, 256);
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq)
@@ -621,6 +623,7 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
       named_bar_sync(bar_id, 256);
       if (leader && tile_valid) {
         tma_store_1d(stash_tile + (size_t)first_chunk * kActChunk, stg_slot, 2 * kActChunk);
+        if (mask_layer >= 0) tma_store_1d(stash_tile + kStashMaskOff + (size_t)mask_layer * 4096, mask_stg, 4096);
         tma_store_commit();
       }
     };
@@ -717,11 +720,12 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
           }
         }
         if (kTrain) {
-          stage_out(stash_chunk + 2 * h, pk);
-          if (s != 8 && tile_valid) {
-            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff + ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32);
-            *reinterpret_cast<uint2*>(mrow + 2 * (2 * h + ch)) = make_uint2(mw[0], mw[1]);
-          }
+          // mask words: [128 rows][8 words] per layer, staged in shared memory (the 8-byte pieces of a row come from four
+          // different threads at two different times) and stored as one 4 KB bulk copy with the layer's last half
+          uint8_t* mstg = smem + kSmemMask2 + T * 8192 + (s & 1) * 4096;
+          if (s != 8) *reinterpret_cast<uint2*>(mstg + r * 32 + 8 * (2 * h + ch)) = make_uint2(mw[0], mw[1]);
+          const bool last_half = (h == 1) || (s == 9);
+          stage_out(stash_chunk + 2 * h, pk, (s != 8 && last_half) ? (s == 9 ? 8 : s) : -1, mstg);
         }
       }
     }

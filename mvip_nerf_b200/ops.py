@@ -4,6 +4,7 @@ PyTorch is plumbing only: it owns device memory and the stream; every computatio
 our sm_100a kernels in libmvip_nerf.so.  Inputs must be CUDA tensors — there is no CPU path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -314,8 +315,10 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-    if kernel_timer.on:   # one bracket per launch: dgrad chain, wgrad, head grads, reduce
-        for bit, label in ((1, "dgrad_chain_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
+    if kernel_timer.on:   # one bracket per launch: fused dgrad chain + wgrad (or the two separately), head grads, reduce
+        fused = os.environ.get("MVIP_BWD_FUSED", "0") == "1" and os.environ.get("MVIP_MLP_CTA_PAIRS", "1") != "0"
+        first = ((3, "backward_fused_kernel"),) if fused else ((1, "dgrad_chain_kernel"), (2, "wgrad_kernel"))
+        for bit, label in first + ((4, "head_grads_kernel"), (8, "reduce_kernel")):
             _call(("mvip_mlp_backward_phases", label), _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr,
                   int(bool(accumulate)), bit, _stream())
     else:
