@@ -175,6 +175,8 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
 int mvip_debug_profile(unsigned long long* out16);
 /* event trace of a -DMVIP_TRACE build: out[3][1024][2] (code, SM clock), n_out[3]; MVIP_E_UNSUPPORTED otherwise */
 int mvip_debug_trace(long long* out, int* n_out);
+/* wgrad cycle counters of CTA 0: producer empty-wait / total, issuer full-wait / total, bias warps full-wait / total, flag wait */
+int mvip_debug_wgrad_profile(unsigned long long* out8);
 
 int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
 

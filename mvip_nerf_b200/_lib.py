@@ -53,6 +53,7 @@ _SIGNATURES = {
                                          c_int, c_void_p]),
     "mvip_debug_profile": (c_int, [c_void_p]),
     "mvip_debug_trace": (c_int, [c_void_p, c_void_p]),
+    "mvip_debug_wgrad_profile": (c_int, [c_void_p]),
     "mvip_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

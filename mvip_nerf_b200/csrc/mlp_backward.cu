@@ -580,6 +580,7 @@ constexpr int kNumItems = 11;
 constexpr size_t kPartialSlotBytes = (size_t)256 * 320 * sizeof(float);
 constexpr int kMaxCtas = 160;
 
+__device__ unsigned long long g_wprof[8];
 struct WItem {
   int a_chunk;      // first dZ-stash chunk of the M side
   int m_blocks;     // 1 (128 output rows) or 2 (256)
@@ -700,6 +701,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      long long pw = 0, pf = 0, pt0 = clock64();
       const uint64_t pol = l2_policy_evict_first();      // both operand streams are read exactly once
       for (int sg = 0; sg < nseg; ++sg) {
         const WItem& itm = kItems[seg_s[sg].item];
@@ -711,14 +713,18 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
           if (p.flags) {   // the dgrad chain (other SMs of this launch) has stored this tile's dZ group
             const uint32_t* f = p.flags + (size_t)t * kFlagsPerTile + fl;
             long long t0 = clock64();
+            long long tq = t0;
             while (ld_acquire_gpu(f) == 0u) {
               if (clock64() - t0 > 8000000000LL) { printf("mvip: wgrad flag timeout cta %d tile %d flag %d\n", cta, t, fl); __trap(); }
             }
             fence_proxy_async_all();
+            pf += clock64() - tq;
           }
           for (int h = 0; h < 2; ++h) {
             uint8_t* sbase = smem + stage * kWStageBytes;
+            long long tw = clock64();
             mbar_wait(&bar_empty[stage], phase ^ 1);
+            pw += clock64() - tw;
             mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(na + itm.nb) * kHalf);
             for (int j = 0; j < na; ++j)
               tma_load_1d_hint(sbase + kWStageA + j * kHalf, dz_tile + (size_t)(itm.a_chunk + j) * kActChunk + h * kHalf, kHalf,
@@ -730,11 +736,13 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
           }
         }
       }
+      if (cta == 0) { g_wprof[0] = pw; g_wprof[1] = clock64() - pt0; g_wprof[6] = pf; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (all lanes run the loop, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0; uint32_t drained_phase = 0;
+      long long mw = 0, mt0 = clock64();
       for (int sg = 0; sg < nseg; ++sg) {
         const WItem& itm = kItems[seg_s[sg].item];
         const int ntot = 64 * itm.nb;                        // accumulator columns per M block
@@ -747,27 +755,27 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
           tc_fence_after();
         }
         bool first = true;
+        const bool two_m = itm.m_blocks == 2, tail = itm.nb > 4;
+        const uint32_t d0 = tmem_base, d1 = tmem_base + ntot;
         for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
           for (int h = 0; h < 2; ++h) {
+            // descriptor low words of this stage: A = dZ half chunks (M side), B = forward-stash half chunks; 16 points per MMA
             const uint32_t sbase = smem_u32(smem) + stage * kWStageBytes;
+            const uint32_t a_lo = desc_lo_mn(sbase + kWStageA, kHalf), b_lo = desc_lo_mn(sbase + kWStageB, kHalf);
+            long long tw = clock64();
             mbar_wait(&bar_full[stage], phase);
+            mw += clock64() - tw;
             tc_fence_after();
             if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                 // 16 points per MMA
-              for (int m = 0; m < itm.m_blocks; ++m) {
-                const uint64_t da = umma_desc_sw128(sbase + kWStageA + (2 * m) * kHalf + ks * 2048, kHalf, 1024);
-                const uint64_t db = umma_desc_sw128(sbase + kWStageB + ks * 2048, kHalf, 1024);
-                const uint32_t d = tmem_base + m * ntot;
+              for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t accum = (first && ks == 0) ? 0u : 1u;
-                umma_bf16(d, da, db, idesc_main, accum);
-                if (itm.nb > 4) {
-                  const uint64_t db2 = umma_desc_sw128(sbase + kWStageB + 4 * kHalf + ks * 2048, kHalf, 1024);
-                  umma_bf16(d + 256, da, db2, idesc_tail, accum);
-                }
+                const uint32_t ko = (uint32_t)ks * (2048u >> 4);
+                mma1_ss(d0, a_lo + ko, b_lo + ko, idesc_main, accum);
+                if (tail) mma1_ss(d0 + 256, a_lo + ko, b_lo + ko + (4 * kHalf >> 4), idesc_tail, accum);
+                if (two_m) mma1_ss(d1, a_lo + ko + (2 * kHalf >> 4), b_lo + ko, idesc_main, accum);
               }
-            }
-            umma_commit(&bar_empty[stage]);
+              umma_commit(&bar_empty[stage]);
             }
             __syncwarp();
             first = false;
@@ -777,6 +785,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
         if (elect_one_sync()) umma_commit(&bar_acc);
         __syncwarp();
       }
+      if (cta == 0 && lane == 0) { g_wprof[2] = mw; g_wprof[3] = clock64() - mt0; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== bias column sums + accumulator drain =====================
@@ -784,6 +793,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
     const int w4 = warp - 4;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
     int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+    long long bw_ = 0, bt0 = clock64();
     for (int sg = 0; sg < nseg; ++sg) {
       const WItem& itm = kItems[seg_s[sg].item];
       const int ntot = 64 * itm.nb;
@@ -795,14 +805,23 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
       float b0 = 0.f, b1 = 0.f;
       for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
         for (int h = 0; h < 2; ++h) {
+          long long tw = clock64();
           mbar_wait(&bar_full[stage], phase);
+          bw_ += clock64() - tw;
           if (do_bias) {
-            const uint8_t* a = smem + stage * kWStageBytes + kWStageA + boff;
-#pragma unroll 8
-            for (int row = 0; row < 64; ++row) {
-              const uint32_t pr = *reinterpret_cast<const uint32_t*>(a + chunk_off16(row, bg) + bw);
-              b0 += __uint_as_float(pr << 16);
-              b1 += __uint_as_float(pr & 0xffff0000u);
+            // explicit shared-space loads with per-thread row-phase offsets (row = 8 i + k): generic loads with 64-bit
+            // address arithmetic made this loop the slowest stage of the pipeline (1,900 cycles vs 1,400 for the MMAs)
+            const uint32_t a32 = smem_u32(smem) + stage * kWStageBytes + kWStageA + boff + bw;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint32_t pr;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
+                b0 += __uint_as_float(pr << 16);
+                b1 += __uint_as_float(pr & 0xffff0000u);
+              }
             }
           }
           __syncwarp();
@@ -833,6 +852,7 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_drained);
     }
+    if (cta == 0 && tid == 128) { g_wprof[4] = bw_; g_wprof[5] = clock64() - bt0; }
   }
 
   tc_fence_before();
@@ -1014,6 +1034,12 @@ Workspace carve(int64_t n_points) {
 
 extern "C" {
 
+int mvip_debug_wgrad_profile(unsigned long long* out8) {
+  MVIP_CUDA_OK(cudaDeviceSynchronize());
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(out8, g_wprof, sizeof(unsigned long long) * 8));
+  return MVIP_OK;
+}
+
 size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_points).total; }
 
 int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, const void* stash, void* workspace,
@@ -1059,6 +1085,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   wp.flags = nullptr;
   for (int i = 0; i <= kNumItems; ++i) wp.item_first[i] = 0;
   int w_grid = sms;
+  { static int wg = -1; if (wg < 0) { const char* e = getenv("MVIP_EXP_WGRAD_CTAS"); wg = e ? atoi(e) : 0; } if (wg > 0 && wg < w_grid) w_grid = wg; }
 
   // 1+2 fused: chain on n_dgrad SMs, tile-major wgrad on the others (needs both phases in one call and enough tiles to fill both)
   static int fused_env = -1, dgrad_sms_env = 0;

@@ -31,6 +31,21 @@ __device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint32_t b_
       "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
       : "memory");
 }
+// cta_group::1, both operands in shared memory, descriptor low words only (wgrad)
+__device__ __forceinline__ void mma1_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi2)
+      : "memory");
+}
+// MN-major SWIZZLE_128B operand: LBO = stride between 64-wide MN blocks, SBO = 1024 (8 K rows)
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 

@@ -35,3 +35,8 @@ if os.environ.get("MVIP_BWD_FUSED", "1") == "0":
     print("%s: dgrad %.3f ms  wgrad %.3f ms  both %.3f ms" % (tag, t(1), t(2), t(3)))
 else:
     print("%s: dgrad+wgrad %.3f ms" % (tag, t(3)))
+
+out = (ctypes.c_ulonglong * 8)()
+run(2 if os.environ.get("MVIP_BWD_FUSED", "0") != "1" else 3); lib.mvip_debug_wgrad_profile(out); v = list(out)
+print("  wgrad CTA 0: producer empty-wait %.0f%% of %d cyc (flag wait %.0f%%); issuer full-wait %.0f%% of %d; bias warps full-wait %.0f%% of %d" % (
+    100 * v[0] / max(v[1], 1), v[1], 100 * v[6] / max(v[1], 1), 100 * v[2] / max(v[3], 1), v[3], 100 * v[4] / max(v[5], 1), v[5]))

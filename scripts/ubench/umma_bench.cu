@@ -14,6 +14,7 @@ __device__ int g_commit_mask = 1;
 __device__ int g_alt = 0;
 __device__ int g_acol = 256;
 __device__ int g_dcol = 0;
+__device__ int g_mn = 0;   // 1: both smem operands MN-major (wgrad layout)
 struct Res { unsigned long long cyc; unsigned long long noise_bytes; };
 
 // kCta: 1 or 2; ts: A from TMEM; N: MMA N; noise_gap: cycles of spin between noise stores (0 = no noise)
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
 
   if (warp == 1) {
     if (rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128 * kCta, N, 0, 0);
+      const int mn = g_mn;
+      const uint32_t idesc = umma_idesc_bf16(128 * kCta, N, mn, mn);
       const uint32_t sb = smem_u32(smem);
       long long t0 = clock64();
       const int ce = g_commit_every, cmask = g_commit_mask, alt = g_alt, acol = g_acol, dcol = g_dcol;
@@ -51,12 +53,12 @@ __global__ void __launch_bounds__(384, 1) mma_bench(int ts, int N, int iters, in
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              uint64_t db = umma_desc_sw128(sb + 65536 + c * b_img + kk * 32, 16, 1024);
+              uint64_t db = mn ? umma_desc_sw128(sb + 65536 + (c * 4 + kk) * 2048, 8192, 1024) : umma_desc_sw128(sb + 65536 + c * b_img + kk * 32, 16, 1024);
               if (ts) {
                 uint32_t ta = tmem_base + acol + c * 32 + kk * 8;
                 if (kCta == 2) umma_bf16_ts_2cta(d_t, ta, db, idesc, 1u); else umma_bf16_ts(d_t, ta, db, idesc, 1u);
               } else {
-                uint64_t da = umma_desc_sw128(sb + c * 16384 + kk * 32, 16, 1024);
+                uint64_t da = mn ? umma_desc_sw128(sb + (c * 4 + kk) * 2048, 8192, 1024) : umma_desc_sw128(sb + c * 16384 + kk * 32, 16, 1024);
                 if (kCta == 2) umma_bf16_2cta(d_t, da, db, idesc, 1u); else umma_bf16(d_t, da, db, idesc, 1u);
               }
               if (((c * 4 + kk + 1) % ce) == 0) { if (kCta == 2) umma_commit_2cta(&bar_sink, (uint16_t)cmask); else umma_commit(&bar_sink); }
@@ -216,13 +218,16 @@ void run_mma(int ts, int N, int gap, Res* d_res, int grid) {
 
 int main() {
   Res* d_res; CK(cudaMalloc(&d_res, sizeof(Res) * 148));
-  for (int acol : {256, 0, 128, 384})
-    for (int dcol : {0, 128, 256, 384}) {
-      if (acol == dcol) continue;
-      CK(cudaMemcpyToSymbol(g_acol, &acol, 4)); CK(cudaMemcpyToSymbol(g_dcol, &dcol, 4));
-      printf("A cols [%d,+128) D cols [%d,+128): ", acol, dcol);
-      run_mma<2>(1, 128, 0, d_res, 148);
-    }
+  for (int mn = 0; mn < 2; ++mn) {
+    CK(cudaMemcpyToSymbol(g_mn, &mn, 4));
+    printf("smem operands %s: ", mn ? "MN-major (wgrad)" : "K-major");
+    run_mma<1>(0, 256, 0, d_res, 148);
+    printf("smem operands %s: ", mn ? "MN-major (wgrad)" : "K-major");
+    run_mma<2>(0, 256, 0, d_res, 148);
+    printf("smem operands %s: ", mn ? "MN-major (wgrad)" : "K-major");
+    run_mma<1>(0, 128, 0, d_res, 148);
+  }
+  { int mn = 0; CK(cudaMemcpyToSymbol(g_mn, &mn, 4)); }
   { int ce = 16, mask = 1, alt = 0; CK(cudaMemcpyToSymbol(g_commit_every, &ce, 4)); CK(cudaMemcpyToSymbol(g_commit_mask, &mask, 4)); CK(cudaMemcpyToSymbol(g_alt, &alt, 4)); }
   if (getenv("UBENCH_ALL"))
   for (int ts = 0; ts < 2; ++ts)
