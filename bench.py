@@ -188,9 +188,8 @@ def run_ours(a):
     with tempfile.TemporaryDirectory() as td:
         os.makedirs(os.path.join(td, "bench"))
         torch.manual_seed(0)
-        kw_train, kw_test, _, grad_vars, _ = run.create_nerf(nerf_args(td))
+        kw_train, kw_test, _, grad_vars, optimizer = run.create_nerf(nerf_args(td))   # optimizer: FusedAdam (one launch)
     coarse, fine = kw_train["network_fn"], kw_train["network_fine"]
-    optimizer = torch.optim.Adam(grad_vars, lr=5e-4, betas=(0.9, 0.999), fused=True)
     groups = [list(fine.parameters()), list(coarse.parameters())]
 
     o, d, target = synth_rays_np(N_RAND, 100 + rank)

@@ -119,6 +119,17 @@ int mvip_normal_backward_xyz(const float* xyz, int H, int W, int k, const float*
 int mvip_embed(const float* in, int64_t in_stride, int64_t n, int dims, int num_freqs, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One-launch Adam step over a list of fp32 tensors.   replaces optimizer.step() of the training loop
+ *   (DS_NeRF/run.py:1003; torch.optim.Adam built at run.py:1536-1537; the decayed learning rate of
+ *   run.py:1031-1039 is passed as `lr`).  torch.optim.Adam semantics with weight_decay = 0, amsgrad = False.
+ *   params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers; sizes: host array of
+ *   element counts; step: 1-based step number of this update (bias correction).
+ */
+int mvip_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, float lr, float beta1,
+                   float beta2, float eps, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused positional encoding + 8x256 NeRF MLP (use_viewdirs, skip at 4).
  *   replaces DS_NeRF/run.py:1108-1124 (run_network), run_nerf_helpers.py:22-52 (Embedder.embed) and
  *   :104-127 (NeRF.forward); backward = autograd of the same.

@@ -18,6 +18,8 @@ PARAM_SHAPES = ([(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (2
 
 # kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_count = 0
+# bumped by optim.FusedAdam.step(): parameters changed in place without torch's version counters noticing
+param_epoch = 0
 _LAUNCHES = {"mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
              "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
              "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}

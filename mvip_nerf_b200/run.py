@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .optim import FusedAdam
 from .run_nerf_helpers import (NeRF, _NormalFromXYZ, get_embedder, get_rays, ndc_rays, raw2outputs, sample_pdf)
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -148,7 +149,7 @@ def create_nerf(args):
         model_fine = DataParallel(model_fine)
 
     network_query_fn = _FusedQuery(embed_fn, embeddirs_fn, args.netchunk)
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    optimizer = FusedAdam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))   # torch.optim.Adam semantics, one launch per step
 
     start = 0
     basedir, expname = args.basedir, args.expname

@@ -138,7 +138,7 @@ class NeRF(nn.Module):
 
     def packed(self):
         params = self._ordered_params()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (ops.param_epoch,) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
             self._packed = ops.mlp_pack(params, out=self._packed)
             self._packed_key = key

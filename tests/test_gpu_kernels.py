@@ -208,3 +208,37 @@ def test_umma_mn_major(ops, N, K):
         out2 = ops.selftest_umma(2, a, b)
         err2 = float((out2 - ref).abs().max())
         pytest.fail("MN-major convention 1 wrong (err %.3g); swapped convention err %.3g" % (err1, err2))
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam(ops):
+    """mvip_adam_step / optim.FusedAdam == torch.optim.Adam (run.py:1536-1537) over several steps, incl. a changed lr
+    (run.py:1031-1039) and state_dict interchange."""
+    from mvip_nerf_b200.optim import FusedAdam
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(256, 63), (256,), (256, 319), (1, 256), (1,), (3, 128), (3,)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    oa = FusedAdam(ours, lr=5e-4, betas=(0.9, 0.999))
+    ra = torch.optim.Adam(ref, lr=5e-4, betas=(0.9, 0.999))
+    for it in range(6):
+        if it == 3:
+            for grp in oa.param_groups + ra.param_groups:
+                grp["lr"] = 2e-4
+            import copy
+            sd = copy.deepcopy(oa.state_dict())       # torch.optim.Adam <-> FusedAdam checkpoints interchange (deep copy:
+                                                      # load_state_dict would otherwise alias our moment buffers)
+            ra2 = torch.optim.Adam(ref, lr=2e-4, betas=(0.9, 0.999))
+            ra2.load_state_dict(sd)
+            ra = ra2
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, device="cuda", generator=g) * (10.0 ** (it - 3))
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        e0 = ops.param_epoch
+        oa.step()
+        ra.step()
+        assert ops.param_epoch == e0 + 1
+    for a, b in zip(ours, ref):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), float((a - b).abs().max())
+    assert int(oa.state[ours[0]]["step"]) == 6
