@@ -998,7 +998,13 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
     const int j = n >> 6, w = n & 63;
     if (w >= itm.valid[j]) continue;
     float s = 0.f;
-    for (int k = 0; k < nslots; ++k) s += p.partials[(size_t)slots[k] * slot_floats + e];
+    int k = 0;
+    for (; k + 4 <= nslots; k += 4) {   // four loads in flight, summed in slot order (deterministic)
+      const float a0 = p.partials[(size_t)slots[k] * slot_floats + e], a1 = p.partials[(size_t)slots[k + 1] * slot_floats + e];
+      const float a2 = p.partials[(size_t)slots[k + 2] * slot_floats + e], a3 = p.partials[(size_t)slots[k + 3] * slot_floats + e];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; k < nslots; ++k) s += p.partials[(size_t)slots[k] * slot_floats + e];
     float* dst = p.grads.p[itm.dst] + (size_t)row * itm.ld + itm.col[j] + w;
     *dst = p.accumulate ? *dst + s : s;
   }

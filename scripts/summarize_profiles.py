@@ -30,17 +30,38 @@ with open(os.path.join(P, tag + "_launches_summary.md"), "w") as f:
         f.write("| `%s` | %d | %.1f | %.1f%% |\n" % (k, n, v, 100 * v / tot))
 
 # ---- full capture --------------------------------------------------------------------------------------
-raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-open(os.path.join(P, tag + "_ncu_full_raw.csv"), "w").write(raw)
-rows = list(csv.reader(raw.splitlines()))
-hdr, rows = rows[0], rows[2:]
-col = {h: i for i, h in enumerate(hdr)}
-def g(r, name):
-    return float(r[col[name]].replace(",", "")) if name in col and r[col[name]] not in ("", "n/a") else float("nan")
+def raw_table(stem):
+    """raw metric table of a capture: the csv written on the GPU box, or converted here from the .ncu-rep"""
+    c = os.path.join(G, stem + "_raw.csv")
+    if os.path.isfile(c):
+        return open(c).read()
+    rep = os.path.join(G, stem + ".ncu-rep")
+    if os.path.isfile(rep):
+        return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return ""
+SCALE = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "second": 1e6}
+tables = []
+for stem, out in (("prof", "_ncu_full_raw.csv"), ("prof_render", "_ncu_render_raw.csv")):
+    raw = raw_table(stem)
+    if not raw:
+        continue
+    open(os.path.join(P, tag + out), "w").write(raw)
+    t = list(csv.reader(raw.splitlines()))
+    tables.append((t[0], t[1], t[2:]))
+rows = []
+for hdr, units, body in tables:
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in body:
+        rows.append((col, units, r))
+def g(row, name):
+    """metric value normalised to us / GB (percentages and counts unchanged)"""
+    col, units, r = row
+    if name not in col or r[col[name]] in ("", "n/a"):
+        return float("nan")
+    return float(r[col[name]].replace(",", "")) * SCALE.get(units[col[name]], 1.0)
 seen = collections.OrderedDict()
 for r in rows:
-    name = short(r[col["Kernel Name"]]).split("(")[0]
-    grid = r[col["Grid Size"]] if "Grid Size" in col else ""
+    name = short(r[2][r[0]["Kernel Name"]]).split("(")[0]
     dur = g(r, "gpu__time_duration.sum")
     key = (name, round(g(r, "dram__bytes_read.sum") + g(r, "dram__bytes_write.sum"), 1))
     if key in seen:
@@ -52,9 +73,9 @@ for r in rows:
                  g(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
                  g(r, "launch__registers_per_thread"))
 with open(os.path.join(P, tag + "_kernels_ncu.md"), "w") as f:
-    f.write("# %s - `ncu --set full` of the training kernels inside one bench step (B200, cfg 2: 4096 rays, P = 262,144 / 524,288 points)\n\n" % tag)
+    f.write("# %s - `ncu --set full` of the kernels inside one bench step (B200, cfg 2: 4096 rays, P = 262,144 / 524,288 points) and of the render-only forward / compositing / sampling kernels at image-sized batches (scripts/time_kernels.py)\n\n" % tag)
     f.write("Command: `scripts/profile.sh`.  Raw metric dump: `%s_ncu_full_raw.csv`.  Durations under ncu are serialised; DRAM bytes are per launch "
-            "(units as printed by ncu: us, Gbyte).\n\n" % tag)
+            "(normalised to us and GB).\n\n" % tag)
     f.write("| kernel | duration us | dram read GB | dram write GB | dram % peak | tensor pipe active % | L2 % | smem wavefronts % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
     for v in seen.values():
         f.write("| `%s` | %.1f | %.3f | %.3f | %.1f | %.1f | %.1f | %.1f | %d |\n" % v)
