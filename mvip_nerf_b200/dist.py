@@ -88,34 +88,57 @@ def render_sharded(render_fn, rays_flat, **kwargs):
     return {"rgb_map": full[:, 0:3], "disp_map": full[:, 3], "acc_map": full[:, 4], "depth_map": full[:, 5]}
 
 
+def _flat_view(grads):
+    """If the gradient tensors are consecutive views of ONE contiguous buffer (what ops.mlp_backward returns: 24 views of
+    one flat fp32 tensor per network), returns that buffer as a 1-D tensor sharing their memory; otherwise None."""
+    g0 = grads[0]
+    if not g0.is_contiguous():
+        return None
+    st = g0.untyped_storage()
+    off = g0.storage_offset()
+    total = 0
+    for g in grads:
+        if (g.dtype != g0.dtype or g.device != g0.device or not g.is_contiguous() or
+                g.untyped_storage().data_ptr() != st.data_ptr() or g.storage_offset() != off + total):
+            return None
+        total += g.numel()
+    return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, off, (total,))
+
+
 class GradAllReducer:
-    """Sum-allreduce of the gradients of a list of parameters as ONE flat fp32 bucket (async)."""
+    """Sum-allreduce of the gradients of a list of parameters as ONE flat fp32 bucket (async).  When the gradients already
+    live back to back in one buffer (the MLP backward writes them that way) the collective runs IN PLACE on it: no
+    concatenation before and no 24 copy kernels after."""
 
     def __init__(self, params):
         self.params = [p for p in params]
         self.handle = None
         self.flat = None
+        self.in_place = False
 
     def start(self):
         if world() == 1:
             return
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        self.flat = torch.cat([g.reshape(-1) for g in grads])
+        view = _flat_view(grads) if all(p.grad is not None for p in self.params) else None
+        self.in_place = view is not None
+        self.flat = view if self.in_place else torch.cat([g.reshape(-1) for g in grads])
         self.handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
 
     def finish(self):
         if self.handle is None:
             return
         self.handle.wait()
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+        if not self.in_place:
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                g = self.flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
         self.handle, self.flat = None, None
 
 

@@ -46,6 +46,20 @@ def _worker(rank, world, port, n):
     md.allreduce_grads([list(lin_a.parameters()), list(lin_b.parameters())])
     for p, g in zip(list(lin_a.parameters()) + list(lin_b.parameters()), ga_full):
         torch.testing.assert_close(p.grad, g, rtol=1e-5, atol=1e-5)
+    # --- in-place path: gradients that are consecutive views of one flat buffer (what the MLP backward produces)
+    ps = list(lin_a.parameters())
+    flat = torch.full((sum(p.numel() for p in ps),), float(rank + 1))
+    off = 0
+    for p in ps:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    assert md._flat_view([p.grad for p in ps]).data_ptr() == flat.data_ptr()
+    red = md.GradAllReducer(ps)
+    red.start()
+    assert red.in_place
+    red.finish()
+    assert torch.equal(flat, torch.full_like(flat, float(sum(range(1, world + 1)))))     # reduced in place, no copies
+    assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in ps)
     dist.barrier()
     dist.destroy_process_group()
 
