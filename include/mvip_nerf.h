@@ -40,6 +40,19 @@ const char* mvip_last_error(void);
 int mvip_device_arch(void);
 
 /* ------------------------------------------------------------------------------------------------
+ * Camera rays of a pinhole view, packed as the ray batch of the hot path.
+ *   replaces DS_NeRF/run_nerf_helpers.py:249-260 (get_rays) + the batch assembly of render(), run.py:1171-1207
+ *   c2w        [3,4] row-major camera-to-world pose (DEVICE pointer, 12 floats)
+ *   c2w_static nullable [3,4]: if given, rays_o / rays_d come from this pose and only the view directions
+ *              from c2w (the c2w_staticcam option, run.py:1180-1183)
+ *   window     rows [i0, i0+h) x columns [j0, j0+w) of the H x W image (the `patch` option; whole image: 0,0,H,W)
+ *   out        [h*w, 8 + 3*use_viewdirs]: o(0:3) d(3:6) near far [viewdir(8:11) = d_c2w / |d_c2w|]
+ * Bit-exact against the reference's CPU result (no ndc: the ndc_rays warp stays elementwise torch glue).
+ */
+int mvip_rays_from_pose(const float* c2w, const float* c2w_static, int H, int W, float focal, float near,
+                        float far, int i0, int j0, int h, int w, int use_viewdirs, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stratified sampling along rays.            replaces DS_NeRF/run.py:1759-1781 (render_rays)
  *   rays    [n_rays, ray_stride] fp32: o(0:3) d(3:6) near(6) far(7) ...
  *   t_vals  [n_samples]  the torch.linspace(0,1,n_samples) table, computed by the host

@@ -24,6 +24,8 @@ _SIGNATURES = {
     "mvip_abi_version": (c_int, []),
     "mvip_last_error": (c_char_p, []),
     "mvip_device_arch": (c_int, []),
+    "mvip_rays_from_pose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p]),
     "mvip_sample_coarse": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mvip_sample_pdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),

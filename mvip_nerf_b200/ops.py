@@ -20,7 +20,7 @@ PARAM_SHAPES = ([(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (2
 launch_count = 0
 # bumped by optim.FusedAdam.step(): parameters changed in place without torch's version counters noticing
 param_epoch = 0
-_LAUNCHES = {"mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
+_LAUNCHES = {"mvip_rays_from_pose": 1, "mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
              "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
              "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
 
@@ -83,6 +83,24 @@ def _call(name, *args):
         rc = getattr(lib, name)(*args)
     _lib.check(rc, name)
     launch_count += 1 if label else _LAUNCHES.get(name, 1)
+
+
+# ---------------------------------------------------------------------------------------------- rays
+def rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=True, c2w_staticcam=None, patch=None, device=None):
+    """-> ray batch [h*w, 8 | 11] (o, d, near, far[, viewdir]) of a pinhole view   (get_rays + run.py:1171-1207)"""
+    def pose(x):
+        if x is None:
+            return None
+        t = torch.as_tensor(x, dtype=torch.float32)
+        dev = device or (t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        return t.to(dev)[:3, :4].contiguous()
+    c = pose(c2w)
+    cs = pose(c2w_staticcam)
+    i0, j0, h, w = (0, 0, H, W) if patch is None else [int(v) for v in patch]
+    out = torch.empty((h * w, 11 if use_viewdirs else 8), device=c.device, dtype=torch.float32)
+    _call("mvip_rays_from_pose", _ptr(c), _ptr(cs), int(H), int(W), float(focal), float(near), float(far), i0, j0, h, w,
+          int(bool(use_viewdirs)), _ptr(out), _stream())
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- sampling

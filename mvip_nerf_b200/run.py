@@ -94,6 +94,18 @@ def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=F
 def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
     """(run.py:1143-1219) -> [rgb_map, disp_map, acc_map, depth_map, extras]."""
+    if c2w is not None and not ndc and depths is None and torch.cuda.is_available():
+        # fused route: one kernel writes the [N, 8|11] ray batch (get_rays + patch + viewdir normalisation + near/far + cat)
+        if patch is not None and (patch[0] + patch[2] > H or patch[1] + patch[3] > W):
+            raise RuntimeError("patch outside the image")
+        rays_flat = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2w_staticcam,
+                                       patch=patch)
+        sh = ((H, W) if patch is None else (int(patch[2]), int(patch[3]))) + (3,)
+        all_ret = batchify_rays(rays_flat, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+        k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, focal, c2w)
         if patch is not None:

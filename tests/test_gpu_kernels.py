@@ -242,3 +242,30 @@ def test_fused_adam_matches_torch_adam(ops):
     for a, b in zip(ours, ref):
         assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), float((a - b).abs().max())
     assert int(oa.state[ours[0]]["step"]) == 6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_viewdirs,static,patch", [(True, False, None), (True, True, (5, 7, 40, 33)), (False, False, None)])
+def test_rays_from_pose_bit_exact_vs_reference_cpu(ops, use_viewdirs, static, patch):
+    """mvip_rays_from_pose == get_rays (run_nerf_helpers.py:249-260) + the batch assembly of render() (run.py:1171-1207),
+    evaluated with the reference's torch ops on the CPU (the bit-exactness authority)."""
+    from mvip_nerf_b200.run_nerf_helpers import get_rays
+    H, W, focal, near, far = 61, 83, 77.31, 1.2, 7.7369
+    rng = np.random.RandomState(3)
+    def pose():
+        q, _ = np.linalg.qr(rng.randn(3, 3))
+        return torch.from_numpy(np.concatenate([q, rng.randn(3, 1)], 1).astype(np.float32))
+    c2w, c2s = pose(), (pose() if static else None)
+    ro, rd = get_rays(H, W, focal, c2w)                       # CPU tensors -> torch CPU arithmetic
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    if static:
+        ro, rd = get_rays(H, W, focal, c2s)
+    if patch is not None:
+        i, j, l1, l2 = patch
+        ro, rd, vd = ro[i:i + l1, j:j + l2], rd[i:i + l1, j:j + l2], vd[i:i + l1, j:j + l2]
+    ones = torch.ones_like(rd[..., :1])
+    cols = [ro, rd, near * ones, far * ones] + ([vd] if use_viewdirs else [])
+    want = torch.cat(cols, -1).reshape(-1, 11 if use_viewdirs else 8).numpy()
+    got = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2s, patch=patch).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), float(np.abs(got - want).max())
