@@ -37,6 +37,11 @@ FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 1186816, 1114112, 1185536       # per point, 
 # HBM bytes per point: stash 40 chunk images x 128 B + 288 B masks; dZ stash 38 x 128 B (+ masks read, + 16 B d_raw);
 # wgrad reads both sets of images; head grads read hidden (2) + h8 (4) images + d_raw
 HBM_FWD_TRAIN, HBM_DGRAD, HBM_WGRAD, HBM_HEADS = 40 * 128 + 288 + 16, 38 * 128 + 288 + 16, 78 * 128, 6 * 128 + 16
+# measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch, mean of the coarse (262,144 points) and the
+# fine (524,288 points) launch of one step, from the ncu --set full capture committed as profiles/r01_kernels_ncu.md
+NCU_TRAFFIC = {"wgrad_kernel": (2.713 + 0.009 + 5.430 + 0.040) / 2 * 1e9,
+               "mvip_mlp_forward": (0.018 + 1.389 + 0.033 + 2.834) / 2 * 1e9,
+               "dgrad_chain_kernel": (0.087 + 1.216 + 0.175 + 2.491) / 2 * 1e9}
 
 
 def peaks():
@@ -313,7 +318,8 @@ def run_ours(a):
         e = per_kernel[top]
         if e.get("frac_of_hbm_peak", 0.0) >= e.get("frac_of_tensor_peak", 0.0):
             roofline = {"kernel": top, "bound": "hbm", "achieved": e["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": e["frac_of_hbm_peak"], "traffic": None,
+                        "frac": e["frac_of_hbm_peak"], "traffic": NCU_TRAFFIC.get(top),
+                        "algorithmic_bytes_per_launch": hbm_bytes[top][0] * npts / 2,
                         "peak_source": "%s hbm_gbs (STREAM-style copy; this kernel's traffic is %s-only, for which "
                                        "the same box measures ~3.9 TB/s write / ~5.9 TB/s read, scripts/hbm_write_bw.py)"
                                        % (pk["_source"], e["hbm_direction"]),

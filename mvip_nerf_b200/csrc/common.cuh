@@ -150,6 +150,8 @@ __device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.b
 // all but the most recent committed bulk store have finished reading their smem source (double-buffered staging)
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+// all but the 5 most recent committed bulk stores are complete (their global writes performed)
+__device__ __forceinline__ void tma_store_wait_all5() { asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

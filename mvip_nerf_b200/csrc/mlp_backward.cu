@@ -322,8 +322,12 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
     const uint32_t heads_a = smem_u32(smem + kDSmemHeads);
     uint8_t* stg_slot = smem + kDSmemStg + T * 4 * kActChunk;
     uint32_t acc_phase = 0, stg_buf = 0;
-    uint32_t* flag_prev1 = nullptr;   // leader only: flags of the two most recent bulk stores, not yet published
-    uint32_t* flag_prev2 = nullptr;
+    // leader only: flags of the six most recent bulk stores, not yet published (FIFO in shared memory, newest at [0]).
+    // A flag goes out once cp.async.bulk.wait_group 5 shows its store to be COMPLETE; waiting with so much slack never stalls
+    // (a store issued six stage_out calls = ~7 us earlier has long been written), unlike a wait on the previous store.
+    __shared__ uint32_t* flag_fifo_s[2][6];
+    uint32_t** flag_fifo = flag_fifo_s[T];
+    if (leader) { for (int i = 0; i < 6; ++i) flag_fifo[i] = nullptr; }
 
     auto act_arrive = [&]() {
       __syncwarp();
@@ -355,13 +359,13 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
         uint8_t* buf = stg_slot + stg_buf * 2 * kActChunk;
         stg_buf ^= 1;
         if (leader) {
+          tma_store_wait_read1();               // the store issued two calls ago has finished reading this buffer
           if (p.flags) {
-            tma_store_wait_all1();              // every store but the latest is complete; so is its smem read
-            if (flag_prev2) { fence_proxy_async_all(); st_release_gpu(flag_prev2, 1u); }
-            flag_prev2 = flag_prev1;
-            flag_prev1 = (flag_id >= 0 && tile_valid) ? p.flags + (size_t)tile * kFlagsPerTile + flag_id : nullptr;
-          } else {
-            tma_store_wait_read1();             // the store issued two calls ago has finished reading this buffer
+            tma_store_wait_all5();              // the store issued six calls ago is complete
+            if (flag_fifo[5]) { fence_proxy_async_all(); st_release_gpu(flag_fifo[5], 1u); }
+#pragma unroll
+            for (int i = 5; i > 0; --i) flag_fifo[i] = flag_fifo[i - 1];
+            flag_fifo[0] = (flag_id >= 0 && tile_valid) ? p.flags + (size_t)tile * kFlagsPerTile + flag_id : nullptr;
           }
         }
         named_bar_sync(bar_id, 256);
@@ -463,8 +467,8 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
       tma_store_wait_all0();
       if (p.flags) {
         fence_proxy_async_all();
-        if (flag_prev2) st_release_gpu(flag_prev2, 1u);
-        if (flag_prev1) st_release_gpu(flag_prev1, 1u);
+        for (int i = 5; i >= 0; --i)
+          if (flag_fifo[i]) st_release_gpu(flag_fifo[i], 1u);
       }
     }
   } else {

@@ -90,11 +90,12 @@ class _MLPFunction(torch.autograd.Function):
             raw = ops.mlp_forward(packed, **kw)
         ctx.need_grad = need_grad
         ctx.n_params = len(params)
+        ctx.set_materialize_grads(False)
         return raw
 
     @staticmethod
     def backward(ctx, d_raw):
-        if not ctx.need_grad:
+        if not ctx.need_grad or d_raw is None:
             return (None,) * (6 + ctx.n_params)
         grads = ops.mlp_backward(ctx.packed, d_raw.contiguous(), ctx.stash)
         ctx.stash = None
@@ -253,6 +254,7 @@ class _CompositeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, need_alpha, detach_weights):
         rgb, disp, acc, weights, depth, alpha = ops.composite_forward(raw, z_vals, rays_d, noise, white_bkgd, need_alpha)
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None (the kernel takes NULL = zeros): no fill kernels
         ctx.save_for_backward(raw, z_vals, rays_d, noise)
         ctx.flags = (bool(white_bkgd), bool(detach_weights), bool(need_alpha))
         if not need_alpha:
@@ -264,6 +266,8 @@ class _CompositeFunction(torch.autograd.Function):
     def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha):
         raw, z_vals, rays_d, noise = ctx.saved_tensors
         white, detach_w, need_alpha = ctx.flags
+        if all(g is None for g in (g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha)):
+            return None, None, None, None, None, None, None
         d_raw = ops.composite_backward(raw, z_vals, rays_d, noise, white, detach_w, g_rgb, g_disp, g_acc, g_depth,
                                        g_weights, g_alpha if need_alpha else None)
         return d_raw, None, None, None, None, None, None
