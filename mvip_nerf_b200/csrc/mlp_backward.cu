@@ -1095,7 +1095,6 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   wp.flags = nullptr;
   for (int i = 0; i <= kNumItems; ++i) wp.item_first[i] = 0;
   int w_grid = sms;
-  { static int wg = -1; if (wg < 0) { const char* e = getenv("MVIP_EXP_WGRAD_CTAS"); wg = e ? atoi(e) : 0; } if (wg > 0 && wg < w_grid) w_grid = wg; }
 
   // 1+2 fused: chain on n_dgrad SMs, tile-major wgrad on the others (needs both phases in one call and enough tiles to fill both)
   static int fused_env = -1, dgrad_sms_env = 0;

@@ -2,17 +2,22 @@
 //   replaces DS_NeRF/run.py:1108-1124 (run_network), run_nerf_helpers.py:22-52 (Embedder.embed) and
 //   run_nerf_helpers.py:104-127 (NeRF.forward)
 //
-// Persistent kernel, one CTA per SM, 384 threads:
-//   warp 0      TMA producer: streams the packed bf16 weight chunks (cp.async.bulk -> 2-stage smem ring)
-//   warp 1      MMA issuer:   tcgen05.mma 128xNx16 (bf16 x bf16 -> fp32 in TMEM), one elected thread
-//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
-//   warps 4-7   epilogue of tile slot 0 (TMEM lanes = the 128 points of the tile)
-//   warps 8-11  epilogue of tile slot 1
-// Each CTA iteration processes two 128-point tiles that ping-pong through the layer sequence, so
-// one tile's epilogue (TMEM -> +bias, ReLU, bf16 -> next layer's A operand in smem) overlaps the
-// other tile's MMAs.  Activations never leave the SM; the only HBM traffic at inference is
-// 16..28 B/point in (rays+z) and 16 B/point out (raw).  With a stash pointer (training) every layer's
-// input tile image is also bulk-stored for the backward pass (mlp_common.cuh, kStash*).
+// Two kernels:
+//   mlp_forward_pair_kernel  (default) CTA pairs (cta_group::2), activations resident in TENSOR MEMORY: the A operand of
+//                            every layer is read from TMEM ("TS" tcgen05.mma), the epilogue writes the next layer's
+//                            bf16 activations straight back to TMEM.  1,443 TFLOP/s at inference on one B200
+//                            (87 % of the cuBLAS bf16 burst peak).  Described in the comment block above the kernel.
+//   mlp_forward_kernel       the first version, kept as an A/B reference behind MVIP_MLP_CTA_PAIRS=0: one CTA per SM,
+//                            384 threads, activations as swizzled bf16 tiles in SHARED memory ("SS" MMAs, 868 TFLOP/s):
+//     warp 0      TMA producer: streams the packed bf16 weight chunks (cp.async.bulk -> 2-stage smem ring)
+//     warp 1      MMA issuer:   tcgen05.mma 128xNx16 (bf16 x bf16 -> fp32 in TMEM), one elected thread
+//     warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//     warps 4-7   epilogue of tile slot 0 (TMEM lanes = the 128 points of the tile)
+//     warps 8-11  epilogue of tile slot 1
+//   Two 128-point tiles ping-pong through the layer sequence, so one tile's epilogue overlaps the other tile's MMAs.
+// In both, activations never leave the SM; the only HBM traffic at inference is 16..28 B/point in (rays+z) and
+// 16 B/point out (raw).  With a stash pointer (training) every layer's input tile image is also bulk-stored for the
+// backward pass (mlp_common.cuh, kStash*).
 #include "mlp_pair.cuh"
 #include <stdlib.h>
 
@@ -62,7 +67,6 @@ struct Params {
   float4* raw;
   uint8_t* stash;
   int64_t n_tiles;
-  int flags;      // experiment switches (MVIP_EXP_FLAGS), 0 in production
 };
 
 // step s: number of K chunks, A source of each (0 = PE buffer, 1..4 = act chunk), N, K-steps of last chunk
@@ -959,7 +963,6 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
   p.raw = reinterpret_cast<float4*>(raw);
   p.stash = static_cast<uint8_t*>(stash);
   p.n_tiles = mlp::num_tiles(pts->n_points);
-  { static int fl = -1; if (fl < 0) { const char* e = getenv("MVIP_EXP_FLAGS"); fl = e ? atoi(e) : 0; } p.flags = fl; }
   if (mlp::use_cta_pairs()) {
     const int64_t n_quads = (p.n_tiles + 3) / 4;
     const int max_clusters = mvip_num_sms() / 2;

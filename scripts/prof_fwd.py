@@ -6,13 +6,6 @@ from oracle import nerf_oracle as orc
 dev = "cuda"
 p = orc.init_params(1)
 blob = ops.mlp_pack([torch.from_numpy(p[n]).to(dev) for n in ops.PARAM_ORDER])
-R = int(os.environ.get("MVIP_EXP_REPL", "1"))
-if R > 1:
-    stride = (blob.numel() + 1023) // 1024 * 1024
-    big = ops._aligned_bytes(stride * R, blob.device)
-    for i in range(R):
-        big[i * stride:i * stride + blob.numel()] = blob
-    blob = big
 P = 4194304
 pts = torch.rand(P, 3, device=dev) * 4 - 2
 dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev), dim=-1)
@@ -26,7 +19,5 @@ for stash in (False, True):
     v = list(out)
     n = pts.shape[0]
     print("stash=%s P=%d  %.3f ms  %.1f TF" % (stash, n, a.elapsed_time(b), n * 1186816 / a.elapsed_time(b) / 1e9))
-    print("  mma: act-wait %.1f%%  weight-wait %.1f%%  total %d cyc" % (100 * v[0] / max(v[2], 1), 100 * v[1] / max(v[2], 1), v[2]))
-    print("  producer: empty-wait %.1f%% of %d cyc; mean issue->observed-full %.0f cyc over %d chunks" % (100 * v[6] / max(v[9], 1), v[9], v[10] / max(v[11], 1), v[11]))
-    print("  epi loop-only per step %.0f cyc, of which tmem-ld wait %.0f cyc" % (v[7] / max(1, (n / 128 / 4 / 74) * 10), v[8] / max(1, (n / 128 / 4 / 74) * 10)))
-    print("  epi(slot0): acc-wait %.1f%%  work %.1f%%  total %d cyc;  work per layer-step %.0f cyc" % (100 * v[3] / max(v[5], 1), 100 * v[4] / max(v[5], 1), v[5], v[4] / max(1, (n / 128 / 4 / 74) * 10)))
+    print("  issuer X (needs a -DMVIP_PROF build): act-wait %.1f%%  weight-wait %.1f%%  total %d cyc" % (100 * v[0] / max(v[2], 1), 100 * v[1] / max(v[2], 1), v[2]))
+    print("  epilogue (slot 0, warp 0): acc-wait %.1f%% of %d cyc" % (100 * v[3] / max(v[5], 1), v[5]))
