@@ -47,10 +47,21 @@ int mvip_device_arch(void);
  *              from c2w (the c2w_staticcam option, run.py:1180-1183)
  *   window     rows [i0, i0+h) x columns [j0, j0+w) of the H x W image (the `patch` option; whole image: 0,0,H,W)
  *   out        [h*w, 8 + 3*use_viewdirs]: o(0:3) d(3:6) near far [viewdir(8:11) = d_c2w / |d_c2w|]
- * Bit-exact against the reference's CPU result (no ndc: the ndc_rays warp stays elementwise torch glue).
+ * Bit-exact against the reference's CPU result.
  */
 int mvip_rays_from_pose(const float* c2w, const float* c2w_static, int H, int W, float focal, float near,
                         float far, int i0, int j0, int h, int w, int use_viewdirs, float* out, void* stream);
+/* Same, with the NDC warp of DS_NeRF/run_nerf_helpers.py:283-300 (ndc_rays) applied to o / d when ndc != 0 (the view
+ * directions stay those of the un-warped rays, run.py:1176-1190).  `focal` and `ndc_near` are doubles because the reference
+ * forms -1/(W/(2 focal)) and 2*near as Python floats before they meet an fp32 tensor; render() passes ndc_near = 1. */
+int mvip_rays_from_pose_ndc(const float* c2w, const float* c2w_static, int H, int W, double focal, float near,
+                            float far, int i0, int j0, int h, int w, int use_viewdirs, int ndc, double ndc_near,
+                            float* out, void* stream);
+/* The `rays=` entry of render() (DS_NeRF/run.py:1176-1207): given rays_o / rays_d [n,3] (and optionally the directions the
+ * view vectors are taken from, view_d [n,3], NULL = rays_d) -> the packed batch [n, 8 + 3*use_viewdirs] in one launch
+ * (viewdir normalisation, optional ndc_rays, near / far columns, cat).  H, W, focal, ndc_near are read only when ndc != 0. */
+int mvip_rays_pack(const float* rays_o, const float* rays_d, const float* view_d, int64_t n, float near, float far,
+                   int use_viewdirs, int ndc, int H, int W, double focal, double ndc_near, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stratified sampling along rays.            replaces DS_NeRF/run.py:1759-1781 (render_rays)

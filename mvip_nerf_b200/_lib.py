@@ -4,7 +4,7 @@ There is no fallback: if the shared library is missing or a call fails, a Runtim
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvip_nerf.so")
@@ -26,6 +26,10 @@ _SIGNATURES = {
     "mvip_device_arch": (c_int, []),
     "mvip_rays_from_pose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
+    "mvip_rays_from_pose_ndc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_double, c_void_p, c_void_p]),
+    "mvip_rays_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_int, c_int, c_int, c_double,
+                               c_double, c_void_p, c_void_p]),
     "mvip_sample_coarse": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mvip_sample_pdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),

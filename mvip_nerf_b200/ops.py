@@ -20,7 +20,7 @@ PARAM_SHAPES = ([(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (2
 launch_count = 0
 # bumped by optim.FusedAdam.step(): parameters changed in place without torch's version counters noticing
 param_epoch = 0
-_LAUNCHES = {"mvip_rays_from_pose": 1, "mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
+_LAUNCHES = {"mvip_rays_from_pose": 1, "mvip_rays_from_pose_ndc": 1, "mvip_rays_pack": 1, "mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
              "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
              "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
 
@@ -86,8 +86,9 @@ def _call(name, *args):
 
 
 # ---------------------------------------------------------------------------------------------- rays
-def rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=True, c2w_staticcam=None, patch=None, device=None):
-    """-> ray batch [h*w, 8 | 11] (o, d, near, far[, viewdir]) of a pinhole view   (get_rays + run.py:1171-1207)"""
+def rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=True, c2w_staticcam=None, patch=None, device=None, ndc=False,
+                   ndc_near=1.):
+    """-> ray batch [h*w, 8 | 11] (o, d, near, far[, viewdir]) of a pinhole view   (get_rays [+ ndc_rays] + run.py:1171-1207)"""
     def pose(x):
         if x is None:
             return None
@@ -98,8 +99,22 @@ def rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=True, c2w_staticcam
     cs = pose(c2w_staticcam)
     i0, j0, h, w = (0, 0, H, W) if patch is None else [int(v) for v in patch]
     out = torch.empty((h * w, 11 if use_viewdirs else 8), device=c.device, dtype=torch.float32)
-    _call("mvip_rays_from_pose", _ptr(c), _ptr(cs), int(H), int(W), float(focal), float(near), float(far), i0, j0, h, w,
-          int(bool(use_viewdirs)), _ptr(out), _stream())
+    _call("mvip_rays_from_pose_ndc", _ptr(c), _ptr(cs), int(H), int(W), float(focal), float(near), float(far), i0, j0, h, w,
+          int(bool(use_viewdirs)), int(bool(ndc)), float(ndc_near), _ptr(out), _stream())
+    return out
+
+
+def rays_pack(rays_o, rays_d, near, far, use_viewdirs=True, view_d=None, ndc=False, H=0, W=0, focal=1., ndc_near=1.):
+    """rays_o / rays_d [n,3] -> ray batch [n, 8 | 11]   (the `rays=` entry of render(), run.py:1176-1207)"""
+    rays_o = _f32(rays_o, "rays_o").reshape(-1, 3)
+    rays_d = _f32(rays_d, "rays_d").reshape(-1, 3)
+    view_d = None if view_d is None else _f32(view_d, "view_d").reshape(-1, 3)
+    n = rays_d.shape[0]
+    if rays_o.shape[0] != n or (view_d is not None and view_d.shape[0] != n):
+        raise RuntimeError("rays_o / rays_d / view_d row counts differ")
+    out = torch.empty((n, 11 if use_viewdirs else 8), device=rays_d.device, dtype=torch.float32)
+    _call("mvip_rays_pack", _ptr(rays_o), _ptr(rays_d), _ptr(view_d), n, float(near), float(far), int(bool(use_viewdirs)),
+          int(bool(ndc)), int(H), int(W), float(focal), float(ndc_near), _ptr(out), _stream())
     return out
 
 

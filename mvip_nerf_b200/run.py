@@ -91,16 +91,30 @@ def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=F
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
 
 
+def _is_number(x):
+    return isinstance(x, (int, float)) or (isinstance(x, np.generic) and np.ndim(x) == 0)
+
+
 def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
-    """(run.py:1143-1219) -> [rgb_map, disp_map, acc_map, depth_map, extras]."""
-    if c2w is not None and not ndc and depths is None and torch.cuda.is_available():
-        # fused route: one kernel writes the [N, 8|11] ray batch (get_rays + patch + viewdir normalisation + near/far + cat)
+    """(run.py:1143-1219) -> [rgb_map, disp_map, acc_map, depth_map, extras].
+
+    The ray batch [N, 8|11] is written by ONE kernel (get_rays / patch / viewdir normalisation / ndc_rays / near / far /
+    cat): mvip_rays_from_pose for `c2w=`, mvip_rays_pack for `rays=`.  Only the `depths=` column (used by the out-of-scope
+    sigma loss) and non-scalar near / far / focal take the elementwise torch route below."""
+    fusable = depths is None and torch.cuda.is_available() and _is_number(near) and _is_number(far) and _is_number(focal)
+    rays_flat = None
+    if fusable and c2w is not None:
         if patch is not None and (patch[0] + patch[2] > H or patch[1] + patch[3] > W):
             raise RuntimeError("patch outside the image")
         rays_flat = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2w_staticcam,
-                                       patch=patch)
+                                       patch=patch, ndc=ndc)
         sh = ((H, W) if patch is None else (int(patch[2]), int(patch[3]))) + (3,)
+    elif fusable and c2w is None and (c2w_staticcam is None or not use_viewdirs):
+        rays_o, rays_d = rays
+        sh = rays_d.shape
+        rays_flat = ops.rays_pack(rays_o, rays_d, near, far, use_viewdirs=use_viewdirs, ndc=ndc, H=H, W=W, focal=focal)
+    if rays_flat is not None:
         all_ret = batchify_rays(rays_flat, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
         for k in all_ret:
             all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))

@@ -458,15 +458,47 @@ def get_rays(H, W, focal, c2w):
     return rays_o, rays_d
 
 
-def make_ray_batch(rays_o, rays_d, near, far):
-    """render(): run.py:1182-1207 with use_viewdirs=True, ndc=False -> [N,11]."""
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """run_nerf_helpers.py:283-300.  Python-float scalars are formed in double and rounded to fp32 where they meet a
+    tensor; `c / tensor` is reciprocal(tensor) * c (Tensor.__rtruediv__); every tensor op rounds to fp32."""
+    rays_o = np.asarray(rays_o, dtype=f32)
+    rays_d = np.asarray(rays_d, dtype=f32)
+    t = (-(f32(near) + rays_o[..., 2]) / rays_d[..., 2]).astype(f32)
+    rays_o = (rays_o + (t[..., None] * rays_d).astype(f32)).astype(f32)
+    sx = f32(-1. / (W / (2. * focal)))
+    sy = f32(-1. / (H / (2. * focal)))
+    rz = (f32(1.) / rays_o[..., 2]).astype(f32)
+    o0 = ((sx * rays_o[..., 0]).astype(f32) / rays_o[..., 2]).astype(f32)
+    o1 = ((sy * rays_o[..., 1]).astype(f32) / rays_o[..., 2]).astype(f32)
+    o2 = (f32(1.) + (rz * f32(2. * near)).astype(f32)).astype(f32)
+    d0 = (sx * ((rays_d[..., 0] / rays_d[..., 2]).astype(f32) - (rays_o[..., 0] / rays_o[..., 2]).astype(f32)).astype(f32)).astype(f32)
+    d1 = (sy * ((rays_d[..., 1] / rays_d[..., 2]).astype(f32) - (rays_o[..., 1] / rays_o[..., 2]).astype(f32)).astype(f32)).astype(f32)
+    d2 = (rz * f32(-2. * near)).astype(f32)
+    return np.stack([o0, o1, o2], -1), np.stack([d0, d1, d2], -1)
+
+
+def _norm3(v):
+    """torch.norm(v, dim=-1) for 3-vectors on CPU: sqrt(fma(z, z, fma(y, y, x*x))) — evaluated in double and rounded once per
+    step, which equals the fused fp32 operations (a product of two fp32 is exact in double)."""
+    x, y, z = [np.asarray(v[..., k], dtype=np.float64) for k in range(3)]
+    a = (x * x).astype(f32).astype(np.float64)
+    a = (y * y + a).astype(f32).astype(np.float64)
+    a = (z * z + a).astype(f32)
+    return np.sqrt(a).astype(f32)
+
+
+def make_ray_batch(rays_o, rays_d, near, far, use_viewdirs=True, view_d=None, ndc=False, H=0, W=0, focal=1., ndc_near=1.):
+    """render(): run.py:1176-1207 -> [N, 8 | 11] (o, d, near, far[, viewdir]); view_d = directions the view vectors come from
+    when they differ from rays_d (c2w_staticcam)."""
     rays_o = np.asarray(rays_o, dtype=f32).reshape(-1, 3)
     rays_d = np.asarray(rays_d, dtype=f32).reshape(-1, 3)
-    nrm = np.sqrt((rays_d * rays_d).astype(f32).sum(-1, dtype=f32)).astype(f32)[:, None]
-    viewdirs = (rays_d / nrm).astype(f32)
+    vsrc = rays_d if view_d is None else np.asarray(view_d, dtype=f32).reshape(-1, 3)
+    viewdirs = (vsrc / _norm3(vsrc)[:, None]).astype(f32)
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, focal, ndc_near, rays_o, rays_d)
     n = np.full_like(rays_d[:, :1], near)
     f = np.full_like(rays_d[:, :1], far)
-    return np.concatenate([rays_o, rays_d, n, f, viewdirs], -1).astype(f32)
+    return np.concatenate([rays_o, rays_d, n, f] + ([viewdirs] if use_viewdirs else []), -1).astype(f32)
 
 
 # --------------------------------------------------------------------------------------

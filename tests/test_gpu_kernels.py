@@ -269,3 +269,48 @@ def test_rays_from_pose_bit_exact_vs_reference_cpu(ops, use_viewdirs, static, pa
     got = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2s, patch=patch).cpu().numpy()
     assert got.shape == want.shape
     assert np.array_equal(got, want), float(np.abs(got - want).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plain", "ndc", "ndc_static", "ndc_patch", "ndc_nodirs", "static", "patch"])
+def test_ray_batch_bit_exact_vs_reference_golden(ops, golden, name):
+    """mvip_rays_from_pose_ndc / mvip_rays_pack == the [N, 8|11] batch the unmodified reference render() assembled on CPU
+    (tests/golden/ray_batch.npz, oracle/make_golden_rays.py): get_rays, patch, c2w_staticcam, viewdirs, ndc_rays, near/far."""
+    from test_oracle_golden import ray_case
+    g = golden("ray_batch")
+    c = ray_case(g, name)
+    whole = c["patch"] == (0, 0, c["H"], c["W"])
+    got = ops.rays_from_pose(c["H"], c["W"], c["focal"], cu(c["c2w"]), c["near"], c["far"], use_viewdirs=c["use_viewdirs"],
+                             c2w_staticcam=None if c["c2w_static"] is None else cu(c["c2w_static"]),
+                             patch=None if whole else c["patch"], ndc=c["ndc"])
+    assert np.array_equal(npy(got), g[name + "_batch"])
+    if name + "_rays_batch" in g:
+        got = ops.rays_pack(cu(g[name + "_rays_o"]), cu(g[name + "_rays_d"]), c["near"], c["far"], use_viewdirs=c["use_viewdirs"],
+                            ndc=c["ndc"], H=c["H"], W=c["W"], focal=c["focal"])
+        assert np.array_equal(npy(got), g[name + "_rays_batch"])
+
+
+@pytest.mark.gpu
+def test_render_ndc_and_rays_entry_use_fused_batch(ops, golden):
+    """run.render(ndc=True, c2w=...) and run.render(rays=...) go through the one-launch batch kernels and match the torch route."""
+    from mvip_nerf_b200 import run
+    seen = {}
+
+    def fake_batchify(rays_flat, chunk, **kw):
+        seen["rays"] = rays_flat
+        n = rays_flat.shape[0]
+        z = torch.zeros(n, device=rays_flat.device)
+        return {"rgb_map": torch.zeros(n, 3, device=rays_flat.device), "disp_map": z, "acc_map": z, "depth_map": z}
+    orig, run.batchify_rays = run.batchify_rays, fake_batchify
+    try:
+        g = golden("ray_batch")
+        c2w = cu(g["ndc_c2w"])
+        l0 = ops.launch_count
+        out = run.render(37, 53, 41.7, c2w=c2w, ndc=True, near=0., far=1., use_viewdirs=True)
+        assert ops.launch_count == l0 + 1 and out[0].shape == (37, 53, 3)
+        assert np.array_equal(npy(seen["rays"]), g["ndc_batch"])
+        run.render(37, 53, 41.7, rays=torch.stack([cu(g["ndc_rays_o"]), cu(g["ndc_rays_d"])], 0), ndc=True, near=0., far=1., use_viewdirs=True)
+        assert ops.launch_count == l0 + 2
+        assert np.array_equal(npy(seen["rays"]), g["ndc_rays_batch"])
+    finally:
+        run.batchify_rays = orig

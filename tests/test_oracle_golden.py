@@ -182,3 +182,31 @@ def test_oracle_train_step_matches_torch_port():
         for gn, pt in ((g0, pc), (g1, pf)):
             ref = pt[name].grad.numpy()
             assert np.abs(gn[name] - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1e-12), name
+
+
+RAY_CASES = ["plain", "ndc", "ndc_static", "ndc_patch", "ndc_nodirs", "static", "patch"]
+
+
+def ray_case(g, name):
+    H, W, focal, near, far, ndc, vd, i0, j0, h, w = g[name + "_args"]
+    return dict(H=int(H), W=int(W), focal=float(focal), near=float(near), far=float(far), ndc=bool(ndc), use_viewdirs=bool(vd),
+                patch=(int(i0), int(j0), int(h), int(w)), c2w=g[name + "_c2w"], c2w_static=g.get(name + "_c2w_static"))
+
+
+@pytest.mark.parametrize("name", RAY_CASES)
+def test_ray_batch_bit_exact(golden, name):
+    """get_rays + ndc_rays + the batch assembly of render() (run.py:1171-1207) vs the batch the reference's render() built."""
+    g = golden("ray_batch")
+    c = ray_case(g, name)
+    ro, rd = orc.get_rays(c["H"], c["W"], c["focal"], c["c2w"])
+    view = rd
+    if c["c2w_static"] is not None:
+        ro, rd = orc.get_rays(c["H"], c["W"], c["focal"], c["c2w_static"])
+    i0, j0, h, w = c["patch"]
+    sl = (slice(i0, i0 + h), slice(j0, j0 + w))
+    got = orc.make_ray_batch(ro[sl], rd[sl], c["near"], c["far"], c["use_viewdirs"], view[sl], c["ndc"], c["H"], c["W"], c["focal"])
+    assert np.array_equal(got, g[name + "_batch"])
+    if name + "_rays_batch" in g:
+        got = orc.make_ray_batch(g[name + "_rays_o"], g[name + "_rays_d"], c["near"], c["far"], c["use_viewdirs"], None, c["ndc"],
+                                 c["H"], c["W"], c["focal"])
+        assert np.array_equal(got, g[name + "_rays_batch"])
