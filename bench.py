@@ -176,6 +176,53 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def hbm_stage_times(ops, dev, hbm_peak):
+    """Sampling / compositing / ray / normal-map kernels on a 262,144-ray batch (a third of a cfg-3 image): achieved GB/s =
+    ALGORITHMIC bytes per launch / CUDA-event time of the launch, best and median of 10."""
+    N = 262144
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *sh: torch.rand(*sh, device=dev, generator=g)  # noqa: E731
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts)), float(np.min(ts))
+    out = {}
+
+    def add(name, nbytes, fn):
+        med, best = timeit(fn)
+        out[name] = {"bytes_per_launch": nbytes, "ms_median": med, "ms_best": best, "gbs": nbytes / med / 1e6,
+                     "frac_of_hbm_peak": nbytes / med / 1e6 / hbm_peak}
+    for S in (64, 128):
+        raw = rnd(N, S, 4) * 2 - 1
+        z = torch.sort(rnd(N, S) * 6 + 1.2, -1)[0]
+        rd = rnd(N, 3) - .5
+        add("composite_fwd_S%d" % S, N * (S * 20 + 12 + S * 4 + 24), lambda: ops.composite_forward(raw, z, rd, None, True))
+        gs = [rnd(N, 3), rnd(N), rnd(N), rnd(N)]
+        add("composite_bwd_S%d" % S, N * (S * 20 + 12 + 24 + S * 16), lambda: ops.composite_backward(raw, z, rd, None, True, False, *gs))
+    z = torch.sort(rnd(N, 64) * 6 + 1.2, -1)[0]
+    w = rnd(N, 64) ** 4
+    u = rnd(N, 64)
+    add("sample_fine_rand_u", N * (512 + 256 + 512 + 4), lambda: ops.sample_fine(z, w, u, want_samples=False))
+    rays = rnd(N, 11) + 1
+    tv = torch.linspace(0, 1, 64, device=dev)
+    tr = rnd(N, 64)
+    add("sample_coarse_perturb", N * (8 + 256 + 256), lambda: ops.sample_coarse(rays, tv, tr, True))
+    c2w = torch.eye(4, device=dev)[:3, :4].contiguous()
+    add("rays_from_pose_1008x756", H * W * 44, lambda: ops.rays_from_pose(H, W, FOCAL, c2w, NEAR, FAR))
+    d = rnd(512, 512) + 3
+    add("normal_fwd_512x512_k31", 512 * 512 * 24, lambda: ops.normal_forward(d, 500., 500., 256., 256., 31))
+    return out
+
+
 # =====================================================================================================
 # our arm
 # =====================================================================================================
@@ -279,10 +326,33 @@ def run_ours(a):
     ms_render = timed(render_image, r_steps) / r_steps
     render_value = n_img / (ms_render * 1e-3)
 
+    # ---- secondary: guidance batch (cfg 5): 4 views x 512 x 512, rgb + disp + acc + depth, normal maps on rank 0 --------
+    GV, GH, GW = 4, 512, 512
+    gfocal = FOCAL * GW / W
+    gposes = []
+    for v in range(GV):
+        pz = torch.eye(4, device=dev)[:3, :4].clone()
+        pz[0, 3] = 0.1 * v
+        gposes.append(pz)
+
+    def render_nograd(*args, **kw):
+        with torch.no_grad():
+            return run.render(*args, chunk=1 << 17, **kw)
+
+    def guidance():
+        return md.render_views_sharded(render_nograd, gposes, GH, GW, gfocal, NEAR, FAR, **kw_test)
+    guidance()
+    g_steps = 2
+    ms_guid = timed(guidance, g_steps) / g_steps
+    guid_value = GV * GH * GW / (ms_guid * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- HBM-bound stages at image-sized batches (rank 0, CUDA events per launch, L2 flushed between launches) ---------
+    hbm_stages = hbm_stage_times(ops, dev, pk["hbm_gbs"])
 
     # ---- roofline of the dominant kernel (CUDA events around each launch, inside the timed region) -----
     pts = {"coarse": N_RAND * 64, "fine": N_RAND * 128}
@@ -359,6 +429,10 @@ def run_ours(a):
                    "tflops": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12,
                    "bound": "tensor", "peak": peak_tf * world,
                    "frac_of_peak": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12 / (peak_tf * world)},
+        "guidance": {"value": guid_value, "unit": "rays/s", "ms_per_batch": ms_guid,
+                     "workload": "cfg5: %d views of %dx%d (rgb + disp + acc + depth), image rows sharded over %d GPU(s), one gather, "
+                                 "normal maps (k=31) of all views on rank 0" % (GV, GH, GW, world)},
+        "hbm_stages": hbm_stages,
         "train_tflops": world * N_RAND * 192 * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) / (ms_step * 1e-3) / 1e12,
     }
     line["train_frac_of_peak"] = line["train_tflops"] / (peak_tf * world)

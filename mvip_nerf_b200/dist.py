@@ -62,18 +62,7 @@ def gather_rows(local, n_total, dst=0):
     if world() == 1:
         return local
     w = world()
-    sizes = [shard_bounds(n_total, r, w) for r in range(w)]
-    max_rows = max(hi - lo for lo, hi in sizes)
-    pad = local.new_zeros((max_rows,) + tuple(local.shape[1:]))
-    pad[:local.shape[0]] = local
-    out = local.new_empty((w * max_rows,) + tuple(local.shape[1:]))
-    if local.is_cuda:
-        dist.all_gather_into_tensor(out, pad)
-    else:
-        dist.all_gather([out[r * max_rows:(r + 1) * max_rows] for r in range(w)], pad)
-    if rank() != dst:
-        return None
-    return torch.cat([out[r * max_rows:r * max_rows + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+    return _gather_uneven(local, [hi - lo for lo, hi in (shard_bounds(n_total, r, w) for r in range(w))], dst)
 
 
 def render_sharded(render_fn, rays_flat, **kwargs):
@@ -86,6 +75,68 @@ def render_sharded(render_fn, rays_flat, **kwargs):
     if full is None:
         return None
     return {"rgb_map": full[:, 0:3], "disp_map": full[:, 3], "acc_map": full[:, 4], "depth_map": full[:, 5]}
+
+
+def view_row_bands(n_views, H, r=None, w=None):
+    """Rows of a stack of n_views images of H rows, split evenly over the ranks: rank r gets the contiguous range
+    shard_bounds(n_views * H) of the global row index; returned as [(view, first_row, n_rows)] (a range may straddle views)."""
+    lo, hi = shard_bounds(n_views * H, r, w)
+    bands = []
+    while lo < hi:
+        v, i0 = divmod(lo, H)
+        n = min(H - i0, hi - lo)
+        bands.append((v, i0, n))
+        lo += n
+    return bands
+
+
+def render_views_sharded(render_fn, poses, H, W, focal, near, far, normal_k=31, with_normals=True, **kwargs):
+    """The guidance render batch (BASELINE cfg 5; render_path_4view + the normal-map branch of train(), DS_NeRF/run.py:948-982):
+    V views of H x W, rgb + disp + acc + depth per pixel and, on rank 0, the depth-derived normal map of each view.
+
+    Rows of the V*H image rows are sharded over the ranks (row bands -> mvip_rays_from_pose windows), every rank renders its
+    bands with render_fn(H, W, focal, c2w=pose, patch=(i0, 0, n, W), near=, far=, **kwargs) -> [rgb, disp, acc, depth, extras],
+    ONE gather of 24 B/pixel brings them to rank 0, which runs the normal-map kernels (a 31 x 31 stencil over the whole
+    image; 24 B/pixel of traffic).  Returns on rank 0 a dict of [V,H,W,...] tensors (+ 'normal' [V,3,H,W], mapped to
+    (n + 1) / 2 as in run.py:965); None on the other ranks."""
+    from .run_nerf_helpers import depth2normal
+    V = len(poses)
+    pieces = []
+    for v, i0, n in view_row_bands(V, H):
+        rgb, disp, acc, depth, _ = render_fn(H, W, focal, c2w=poses[v][:3, :4], patch=(i0, 0, n, W), near=near, far=far, **kwargs)
+        pieces.append(torch.cat([rgb.reshape(-1, 3), disp.reshape(-1, 1), acc.reshape(-1, 1), depth.reshape(-1, 1)], -1))
+    some = poses[0]
+    dev = some.device if torch.is_tensor(some) and some.is_cuda else (
+        torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+    packed = torch.cat(pieces, 0) if pieces else torch.empty((0, 6), device=dev)
+    # row bands are whole rows, so the row-sharded gather of pixels == gather_rows with W pixels per row
+    full = _gather_uneven(packed.contiguous(), [(b[1] - b[0]) * W for b in (shard_bounds(V * H, r, world()) for r in range(world()))])
+    if full is None:
+        return None
+    full = full.view(V, H, W, 6)
+    out = {"rgb_map": full[..., 0:3], "disp_map": full[..., 3], "acc_map": full[..., 4], "depth_map": full[..., 5]}
+    if with_normals:
+        K = [[focal, 0., W / 2], [0., focal, H / 2], [0., 0., 1.]]
+        out["normal"] = torch.cat([(depth2normal(out["depth_map"][v].contiguous(), K, normal_k) + 1) / 2 for v in range(V)], 0)
+    return out
+
+
+def _gather_uneven(local, sizes, dst=0):
+    """all ranks contribute `sizes[r]` rows; rank dst gets the concatenation (one padded all_gather), others None."""
+    if world() == 1:
+        return local
+    w = world()
+    max_rows = max(sizes)
+    pad = local.new_zeros((max_rows,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    out = local.new_empty((w * max_rows,) + tuple(local.shape[1:]))
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, pad)
+    else:
+        dist.all_gather([out[r * max_rows:(r + 1) * max_rows] for r in range(w)], pad)
+    if rank() != dst:
+        return None
+    return torch.cat([out[r * max_rows:r * max_rows + sizes[r]] for r in range(w)], 0)
 
 
 def _flat_view(grads):

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .dist import _flat_view
 from .optim import FusedAdam
 from .run_nerf_helpers import (NeRF, _NormalFromXYZ, get_embedder, get_rays, ndc_rays, raw2outputs, sample_pdf)
 
@@ -307,6 +308,277 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
                 print(f"! [Numerical Error] {k} contains nan or inf.")
     return ret
+
+
+# ---------------------------------------------------------------------------------------------------
+# deferred back-propagation (SURVEY.md §8 f2): full guidance views with gradients in bounded memory
+# ---------------------------------------------------------------------------------------------------
+_DIFF_KEYS = ("rgb_map", "disp_map", "acc_map", "depth_map", "rgb0", "disp0", "acc0")
+
+
+def _net_params(render_kwargs):
+    """[(net, ordered parameter list)] of the coarse / fine networks of a render-kwargs dict."""
+    nets = []
+    for key in ("network_fn", "network_fine"):
+        net = render_kwargs.get(key)
+        if net is not None:
+            net = _unwrap(net)
+            nets.append((net, net._ordered_params() if isinstance(net, NeRF) else list(net.parameters())))
+    return nets
+
+
+class _DeferredRays(torch.autograd.Function):
+    """rays_flat -> the integrated maps of batchify_rays, WITHOUT keeping any per-sample state for the backward pass.
+
+    forward  renders every chunk under no_grad (no activation stash: the tensor-bound render kernel);
+    backward re-renders one chunk at a time with the stash enabled, back-propagates the slice of the upstream image
+             gradients that belongs to it and accumulates the parameter gradients.
+    Peak memory is one chunk's stash (10.3 KB per sample point) instead of the whole view's: 4 x 512 x 512 rays x 192 points
+    would need 2 TB, which is why the reference cannot run its guidance views at normalmap_render_factor = 1 (README.md:61).
+    The random streams (perturb / raw_noise_std) are replayed by restoring the CUDA generator state, so the re-rendered
+    chunks are the ones the loss saw."""
+
+    @staticmethod
+    def forward(ctx, rays_flat, chunk, kw, holder, *params):
+        dev = rays_flat.device
+        ctx.rng = torch.cuda.get_rng_state(dev) if dev.type == "cuda" else torch.get_rng_state()
+        ret = batchify_rays(rays_flat, chunk, **kw)
+        keys = list(ret.keys())
+        holder["keys"] = keys
+        ctx.keys, ctx.chunk, ctx.kw, ctx.rays = keys, chunk, kw, rays_flat
+        ctx.params = params
+        ctx.set_materialize_grads(False)
+        outs = tuple(ret[k] for k in keys)
+        ctx.mark_non_differentiable(*[ret[k] for k in keys if k not in _DIFF_KEYS])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        grads = {k: g for k, g in zip(ctx.keys, gouts) if g is not None and k in _DIFF_KEYS}
+        none = (None,) * (4 + len(ctx.params))
+        if not grads:
+            return none
+        params = [p for p in ctx.params]
+        live = [i for i, p in enumerate(params) if p.requires_grad]
+        if not live:
+            return none
+        dev = ctx.rays.device
+        acc = [None] * len(params)
+        flat_acc = {}            # first parameter index of a network -> (flat accumulator, its per-parameter views)
+        with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
+            if dev.type == "cuda":
+                torch.cuda.set_rng_state(ctx.rng, dev)
+            else:
+                torch.set_rng_state(ctx.rng)
+            for i in range(0, ctx.rays.shape[0], ctx.chunk):
+                with torch.enable_grad():
+                    ret = render_rays(ctx.rays[i:i + ctx.chunk], **ctx.kw)
+                    outs = [ret[k] for k in grads]
+                    gs = [grads[k][i:i + ctx.chunk].contiguous() for k in grads]
+                    g = dict(zip(live, torch.autograd.grad(outs, [params[j] for j in live], gs, allow_unused=True)))
+                for a in range(0, len(params), len(ops.PARAM_ORDER)):
+                    # the MLP backward writes a network's 24 gradients back to back: accumulate them as ONE tensor
+                    idx = list(range(a, min(a + len(ops.PARAM_ORDER), len(params))))
+                    gl = [g.get(j) for j in idx]
+                    flat = _flat_view(gl) if all(x is not None for x in gl) else None
+                    if flat is not None and (a in flat_acc or all(acc[j] is None for j in idx)):
+                        if a not in flat_acc:
+                            buf = flat.clone()
+                            views, off = [], 0
+                            for x in gl:
+                                views.append(buf[off:off + x.numel()].view(x.shape))
+                                off += x.numel()
+                            flat_acc[a] = buf
+                            for j, v in zip(idx, views):
+                                acc[j] = v
+                        else:
+                            flat_acc[a].add_(flat)
+                        continue
+                    for j, gj in zip(idx, gl):
+                        if gj is not None:
+                            acc[j] = gj.clone() if acc[j] is None else acc[j].add_(gj)
+        return (None, None, None, None) + tuple(acc)
+
+
+def render_deferred(H, W, focal, chunk=1024 * 8, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+                    c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
+    """render() with deferred back-propagation: same arguments and return list; rgb / disp / acc / depth (+ rgb0 / disp0 / acc0)
+    carry gradients to the network parameters, the per-sample extras (weights, z_vals, raw, alpha) are detached.
+    `chunk` is the number of rays whose activations exist at any one time during backward (default 8192: 16 GB)."""
+    if depths is not None:
+        raise NotImplementedError("render_deferred: the depths column (sigma loss) is out of scope")
+    if c2w is not None:
+        if patch is not None and (patch[0] + patch[2] > H or patch[1] + patch[3] > W):
+            raise RuntimeError("patch outside the image")
+        rays_flat = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2w_staticcam,
+                                       patch=patch, ndc=ndc)
+        sh = ((H, W) if patch is None else (int(patch[2]), int(patch[3]))) + (3,)
+    else:
+        rays_o, rays_d = rays
+        sh = rays_d.shape
+        rays_flat = ops.rays_pack(rays_o, rays_d, near, far, use_viewdirs=use_viewdirs, ndc=ndc, H=H, W=W, focal=focal)
+    kw = dict(kwargs, need_alpha=need_alpha, detach_weights=detach_weights)
+    params = [p for _, ps in _net_params(kwargs) for p in ps]
+    holder = {}
+    outs = _DeferredRays.apply(rays_flat, int(chunk), kw, holder, *params)
+    all_ret = {k: torch.reshape(v, list(sh[:-1]) + list(v.shape[1:])) for k, v in zip(holder["keys"], outs)}
+    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+# ---------------------------------------------------------------------------------------------------
+# view loops (run.py:1222-1432): render_path / render_path_4view / render_path_projection
+# ---------------------------------------------------------------------------------------------------
+def _write_png(path, img8):
+    """8-bit RGB / grey PNG without imageio (absent in this image): zlib + the four mandatory chunks."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(img8, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, c = a.shape
+    ctype = {1: 0, 3: 2, 4: 6}[c]
+    rows = np.concatenate([np.zeros((h, 1), np.uint8), a.reshape(h, w * c)], 1).tobytes()
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(rows, 6)) + chunk(b"IEND", b""))
+
+
+def _imwrite(path, img8):
+    try:
+        import imageio
+        imageio.imwrite(path, img8)
+    except Exception:
+        _write_png(path, img8)
+
+
+def _scaled_hwf(hwf, render_factor):
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    K = np.array([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1]])
+    return int(H), int(W), focal, K
+
+
+def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                disp_require_grad=False, need_alpha=False, rgb_require_grad=False, detach_weights=False,
+                patch_len=None, masks=None, deferred_backprop=False):
+    """(run.py:1222-1362) renders every pose; -> (rgbs, disps, (Xs, Ys)); with `savedir` writes the reference's layout
+    (intrinsics.txt, rgb/*.png, depth|disp|weight|z|alpha/*.npy, pose/*.txt).  `deferred_backprop` (ours) renders the
+    gradient-carrying views through render_deferred so that whole views fit in memory."""
+    import random
+    to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731
+    H, W, focal, K = _scaled_hwf(hwf, render_factor)
+    if savedir is not None:
+        np.savetxt(os.path.join(savedir, 'intrinsics.txt'), K)
+    rgbs, disps, Xs, Ys = [], [], [], []
+    for i, c2w in enumerate(render_poses):
+        if disp_require_grad or rgb_require_grad:
+            patch = None
+            if patch_len is not None:
+                masked = np.where(masks[i] != 0)
+                masked = (masked[0] // render_factor, masked[1] // render_factor)
+                Xs.append(random.randint(masked[0].min(), max(masked[0].max() - patch_len[0], masked[0].min())))
+                Ys.append(random.randint(masked[1].min(), max(masked[1].max() - patch_len[1], masked[1].min())))
+                patch = (Xs[-1], Ys[-1], patch_len[0], patch_len[1])
+            fn = render_deferred if deferred_backprop else render
+            rgb, disp, acc, depth, extras = fn(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True, need_alpha=need_alpha,
+                                               detach_weights=detach_weights, patch=patch, **render_kwargs)
+        else:
+            with torch.no_grad():
+                rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
+                                                       need_alpha=need_alpha, **render_kwargs)
+        disps.append(disp if disp_require_grad else disp.detach().cpu().numpy())
+        rgbs.append(rgb if rgb_require_grad else rgb.detach().cpu().numpy())
+        if savedir is not None:
+            dirs = {k: os.path.join(savedir, k) for k in ('rgb', 'depth', 'disp', 'weight', 'images', 'z', 'pose')}
+            if need_alpha:
+                dirs['alpha'] = os.path.join(savedir, 'alpha')
+            for d in dirs.values():
+                os.makedirs(d, exist_ok=True)
+            rgb_np = rgbs[-1] if isinstance(rgbs[-1], np.ndarray) else rgbs[-1].detach().cpu().numpy()
+            rgb8 = to8b(np.nan_to_num(rgb_np, nan=0.0))
+            _imwrite(os.path.join(dirs['rgb'], '{:06d}.png'.format(i)), rgb8)
+            if gt_imgs is not None:
+                gt = gt_imgs[i]
+                gt = gt.detach().cpu().numpy() if torch.is_tensor(gt) else np.asarray(gt)
+                _imwrite(os.path.join(dirs['images'], '{:06d}.png'.format(i)), to8b(gt))
+            np.save(os.path.join(dirs['depth'], '{:06d}.npy'.format(i)), depth.detach().cpu().numpy())
+            np.save(os.path.join(dirs['disp'], '{:06d}.npy'.format(i)), disp.detach().cpu().numpy())
+            np.save(os.path.join(dirs['weight'], '{:06d}.npy'.format(i)), extras['weights'].detach().cpu().numpy())
+            np.save(os.path.join(dirs['z'], '{:06d}.npy'.format(i)), extras['z_vals'].detach().cpu().numpy())
+            if need_alpha:
+                np.save(os.path.join(dirs['alpha'], '{:06d}.npy'.format(i)), extras['alpha'].detach().cpu().numpy())
+            pose = torch.as_tensor(render_poses[i])[:3, :4].detach().cpu().numpy()
+            np.savetxt(os.path.join(dirs['pose'], '{:06d}.txt'.format(i)), np.concatenate([pose, np.array([[0, 0, 0, 1]])], 0))
+    disps = torch.stack(disps, 0) if disp_require_grad else np.stack(disps, 0)
+    rgbs = torch.stack(rgbs, 0) if rgb_require_grad else np.stack(rgbs, 0)
+    return rgbs, disps, (Xs, Ys)
+
+
+def render_path_4view(iter, all_masks, render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                      disp_require_grad=False, need_alpha=False, rgb_require_grad=False, detach_weights=False,
+                      patch_len=None, masks=None, deferred_backprop=False):
+    """(run.py:1365-1402) collaborative-guidance views: every second pose of the +-4 neighbourhood of pose `iter % 60`,
+    rendered WITH gradients -> (rgbs [V,H,W,3], disps [V,H,W], selected_masks)."""
+    H, W, focal, _ = _scaled_hwf(hwf, render_factor)
+    neighborhood_size = 4
+    iter = iter % 60
+    sel = slice(max(0, iter - neighborhood_size), min(len(render_poses), iter + neighborhood_size + 1), 2)
+    selected_poses, selected_masks = render_poses[sel], all_masks[sel]
+    fn = render_deferred if deferred_backprop else render
+    rgbs, disps = [], []
+    for c2w in selected_poses:
+        rgb, disp, _, _, _ = fn(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True, need_alpha=need_alpha, **render_kwargs)
+        disps.append(disp)
+        rgbs.append(rgb)
+    return torch.stack(rgbs, 0), torch.stack(disps, 0), selected_masks
+
+
+def convert_pose(C2W):
+    """(run.py:1435-1440)"""
+    flip_yz = np.eye(4)
+    flip_yz[1, 1] = -1
+    flip_yz[2, 2] = -1
+    return np.matmul(C2W, flip_yz)
+
+
+def render_path_projection(render_poses, hwf, chunk, render_kwargs, render_factor=0):
+    """(run.py:1405-1432) -> (z_vals, weights, c2ws, K) per pose, numpy."""
+    H, W, focal, K = _scaled_hwf(hwf, render_factor)
+    z_vals, weights, c2ws = [], [], []
+    for i, c2w in enumerate(render_poses):
+        with torch.no_grad():
+            _, _, _, _, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True, **render_kwargs)
+        z_vals.append(extras['z_vals'].cpu().numpy())
+        weights.append(extras['weights'].cpu().numpy())
+        pose = torch.as_tensor(render_poses[i])[:3, :4].detach().cpu().numpy()
+        c2ws.append(convert_pose(np.concatenate([pose, np.array([[0, 0, 0, 1]])], axis=0)))
+    return z_vals, weights, c2ws, K
+
+
+def save_checkpoint(path, global_step, render_kwargs_train, optimizer):
+    """The `.tar` the reference's train() writes (run.py:1043-1053): same keys, `module.`-prefixed state dicts; create_nerf
+    (ours or the reference's) reloads it."""
+    torch.save({
+        'global_step': global_step,
+        'network_fn_state_dict': render_kwargs_train['network_fn'].state_dict()
+        if render_kwargs_train['network_fn'] is not None else None,
+        'network_fine_state_dict': render_kwargs_train['network_fine'].state_dict()
+        if render_kwargs_train['network_fine'] is not None else None,
+        'optimizer_state_dict': optimizer.state_dict(),
+    }, path)
+
+
+def update_learning_rate(optimizer, args, global_step):
+    """(run.py:1031-1039) exponential decay, 0.1 every lrate_decay*1000 steps."""
+    new_lrate = args.lrate * (0.1 ** (global_step / (args.lrate_decay * 1000)))
+    for param_group in optimizer.param_groups:
+        param_group['lr'] = new_lrate
+    return new_lrate
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,81 @@
+"""Host logic of the deferred back-propagation wrapper (mvip_nerf_b200.run._DeferredRays) on CPU:
+render_rays is replaced by a small differentiable torch stand-in (the real one needs the CUDA library), so what is checked
+is the chunk loop, the gradient slicing / accumulation and the replay of the random streams."""
+import numpy as np
+import torch
+
+from mvip_nerf_b200 import run
+
+
+class TinyField(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(11, 16)
+        self.b = torch.nn.Linear(16, 5)
+
+
+def fake_render_rays(ray_batch, network_fn=None, perturb=0., **kw):
+    h = torch.relu(network_fn.a(ray_batch))
+    if perturb > 0.:
+        h = h * (1. + torch.rand(h.shape))            # a random stream that backward has to replay
+    o = network_fn.b(h)
+    return {"rgb_map": torch.sigmoid(o[:, :3]), "disp_map": o[:, 3], "acc_map": torch.sigmoid(o[:, 4]), "depth_map": o[:, 3] * 2.,
+            "weights": o.detach() * 0., "rgb0": torch.tanh(o[:, :3])}
+
+
+def run_case(monkeypatch, perturb, chunk):
+    monkeypatch.setattr(run, "render_rays", fake_render_rays)
+    torch.manual_seed(0)
+    net = TinyField()
+    rays = torch.randn(37, 11)
+    tgt = torch.rand(37, 3)
+    params = list(net.parameters())
+
+    def loss_of(ret):
+        return ((ret["rgb_map"] - tgt) ** 2).mean() + 0.3 * ((ret["rgb0"] - tgt) ** 2).mean() + 0.1 * ret["depth_map"].abs().mean()
+
+    # direct: everything in one autograd graph, same chunking (the random stream is drawn chunk by chunk)
+    torch.manual_seed(123)
+    direct = run.batchify_rays(rays, chunk, network_fn=net, perturb=perturb)
+    gd = torch.autograd.grad(loss_of(direct), params)
+    # deferred
+    torch.manual_seed(123)
+    holder = {}
+    outs = run._DeferredRays.apply(rays, chunk, dict(network_fn=net, perturb=perturb), holder, *params)
+    ret = dict(zip(holder["keys"], outs))
+    assert not ret["weights"].requires_grad and ret["rgb_map"].requires_grad
+    for k in direct:
+        assert torch.equal(ret[k], direct[k].detach()), k
+    state_before = torch.get_rng_state()
+    gq = torch.autograd.grad(loss_of(ret), params)
+    assert torch.equal(torch.get_rng_state(), state_before)        # the replay does not disturb the caller's stream
+    for a, b in zip(gd, gq):
+        np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_deferred_matches_direct_multi_chunk(monkeypatch):
+    run_case(monkeypatch, 0., 8)
+
+
+def test_deferred_replays_random_streams(monkeypatch):
+    run_case(monkeypatch, 1., 16)
+
+
+def test_deferred_single_chunk(monkeypatch):
+    run_case(monkeypatch, 1., 64)
+
+
+def test_png_writer_roundtrip(tmp_path):
+    import struct
+    import zlib
+    img = (np.random.RandomState(0).rand(9, 13, 3) * 255).astype(np.uint8)
+    p = str(tmp_path / "a.png")
+    run._write_png(p, img)
+    b = open(p, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h, depth, ctype = struct.unpack(">IIBB", b[16:26])
+    assert (w, h, depth, ctype) == (13, 9, 8, 2)
+    n = struct.unpack(">I", b[33:37])[0]
+    assert b[37:41] == b"IDAT"
+    rows = np.frombuffer(zlib.decompress(b[41:41 + n]), np.uint8).reshape(9, 1 + 13 * 3)
+    assert np.array_equal(rows[:, 1:].reshape(9, 13, 3), img) and not rows[:, 0].any()

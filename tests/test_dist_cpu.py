@@ -60,6 +60,27 @@ def _worker(rank, world, port, n):
     red.finish()
     assert torch.equal(flat, torch.full_like(flat, float(sum(range(1, world + 1)))))     # reduced in place, no copies
     assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in ps)
+    # --- guidance batch: V views x H rows sharded as row bands (a rank's range may straddle two views), one gather
+    V, H, W = 3, n, 4
+    poses = [torch.eye(4)[:3, :4] * float(v + 1) for v in range(V)]
+
+    def fake_view(H_, W_, focal, c2w=None, patch=None, near=0., far=1.):
+        i0, j0, h, w_ = patch
+        assert (j0, w_) == (0, W_)
+        rows = torch.arange(i0, i0 + h, dtype=torch.float32)[:, None].expand(h, w_)
+        cols = torch.arange(w_, dtype=torch.float32)[None, :].expand(h, w_)
+        val = c2w[0, 0] * 1000 + rows * 10 + cols
+        return [torch.stack([val, val + .25, val + .5], -1), val * 2, val * 3, val * 4, {}]
+    out = md.render_views_sharded(fake_view, poses, H, W, 50., 1., 6., with_normals=False)
+    bands = [b for r_ in range(world) for b in md.view_row_bands(V, H, r_, world)]
+    assert sum(b[2] for b in bands) == V * H and bands[0][:2] == (0, 0)
+    if rank == 0:
+        for v in range(V):
+            want = fake_view(H, W, 50., c2w=poses[v], patch=(0, 0, H, W))
+            assert torch.equal(out["rgb_map"][v], want[0]) and torch.equal(out["disp_map"][v], want[1])
+            assert torch.equal(out["acc_map"][v], want[2]) and torch.equal(out["depth_map"][v], want[3])
+    else:
+        assert out is None
     dist.barrier()
     dist.destroy_process_group()
 
