@@ -199,6 +199,194 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path for the shapes render_rays produces (S = 64 coarse, S = 128 fine): G lanes per ray, 4 consecutive
+// samples per lane (S == 4 G), so a warp carries 32 / G rays and nothing is predicated on the sample index.
+// Everything a lane needs arrives as 128-bit loads (4 x raw, 1 x z, 1 x noise); weights / alpha / d_raw leave
+// as 128-bit stores.  The generic kernels above spend ~165 instructions per sample (IEEE division and expf
+// slow paths, index predicates); this path spends ~45, which is what lets HBM become the limit.
+// exp / reciprocal are the 2-ulp MUFU forms: the 1e-5 relative tolerance of the path is two orders above them.
+// ---------------------------------------------------------------------------------------------
+// single-MUFU forms (the non-ftz intrinsics wrap each MUFU in a denormal-range test and two scalings)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_exp_neg(float x) { return ex2_ftz(x * -1.4426950408889634f); }   // exp(-x)
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + fast_exp_neg(x)); }
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+struct Fast4 {
+  float a[4], q[4], T[4], w[4], zz[4], e[4], delta[4], sig[4], cr[4], cg[4], cb[4];
+  float D, A, R, G, Bc;
+};
+
+template <int G>
+__device__ __forceinline__ void eval_ray4(Fast4& f, const float4* __restrict__ raw, const float* __restrict__ z,
+                                          const float* __restrict__ noise, const float* __restrict__ d, int sub) {
+  float4 rw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rw[k] = __ldg(raw + k);
+  const float4 z4 = __ldg(reinterpret_cast<const float4*>(z));
+  float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (noise) n4 = __ldg(reinterpret_cast<const float4*>(noise));
+  const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+  const float n2 = dx * dx + dy * dy + dz * dz;
+  const float norm = n2 > 0.f ? n2 * rsqrt_ftz(n2) : 0.f;
+  f.zz[0] = z4.x; f.zz[1] = z4.y; f.zz[2] = z4.z; f.zz[3] = z4.w;
+  f.sig[0] = rw[0].w + n4.x; f.sig[1] = rw[1].w + n4.y; f.sig[2] = rw[2].w + n4.z; f.sig[3] = rw[3].w + n4.w;
+  const float z_next = __shfl_down_sync(FULL_MASK, z4.x, 1, G);
+  float prod = 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float dist = (k < 3) ? (f.zz[(k < 3) ? k + 1 : k] - f.zz[k]) : ((sub == G - 1) ? 1e10f : (z_next - f.zz[3]));
+    f.delta[k] = dist * norm;
+    f.e[k] = fast_exp_neg(fmaxf(f.sig[k], 0.f) * f.delta[k]);
+    f.a[k] = 1.f - f.e[k];
+    f.q[k] = (1.f - f.a[k]) + 1e-10f;
+    f.T[k] = prod;
+    prod *= f.q[k];
+    f.cr[k] = fast_sigmoid(rw[k].x);
+    f.cg[k] = fast_sigmoid(rw[k].y);
+    f.cb[k] = fast_sigmoid(rw[k].z);
+  }
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) {
+    float v = __shfl_up_sync(FULL_MASK, incl, o, G);
+    incl *= (sub >= o) ? v : 1.f;
+  }
+  float excl = __shfl_up_sync(FULL_MASK, incl, 1, G);
+  if (sub == 0) excl = 1.f;
+  float sD = 0.f, sA = 0.f, sR = 0.f, sG = 0.f, sB = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f.T[k] *= excl;
+    f.w[k] = f.a[k] * f.T[k];
+    sD = fmaf(f.w[k], f.zz[k], sD);
+    sA += f.w[k];
+    sR = fmaf(f.w[k], f.cr[k], sR);
+    sG = fmaf(f.w[k], f.cg[k], sG);
+    sB = fmaf(f.w[k], f.cb[k], sB);
+  }
+  f.D = group_sum<G>(sD);
+  f.A = group_sum<G>(sA);
+  f.R = group_sum<G>(sR);
+  f.G = group_sum<G>(sG);
+  f.Bc = group_sum<G>(sB);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kWarps * 32, 5)
+composite_fwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                      int d_stride, const float* __restrict__ noise, int64_t n_rays, int white,
+                      float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
+                      float* __restrict__ weights, float* __restrict__ depth, float* __restrict__ alpha) {
+  constexpr int S = 4 * G, RPW = 32 / G;   // samples per ray, rays per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % G;
+  const int64_t stride = (int64_t)gridDim.x * kWarps * RPW;
+  for (int64_t ray0 = ((int64_t)blockIdx.x * kWarps + warp) * RPW; ray0 < n_rays; ray0 += stride) {
+    int64_t ray = ray0 + lane / G;
+    const bool live = ray < n_rays;
+    if (!live) ray = n_rays - 1;           // keep the shuffles convergent; the duplicate is not stored
+    const int64_t off = ray * S + sub * 4;
+    Fast4 f;
+    eval_ray4<G>(f, raw + off, z + off, noise ? noise + off : nullptr, rays_d + ray * d_stride, sub);
+    if (live) {
+      *reinterpret_cast<float4*>(weights + off) = make_float4(f.w[0], f.w[1], f.w[2], f.w[3]);
+      if (alpha) *reinterpret_cast<float4*>(alpha + off) = make_float4(f.a[0], f.a[1], f.a[2], f.a[3]);
+      if (sub == 0) {
+        float r = f.D / f.A;
+        float m = (r != r) ? r : fmaxf(1e-10f, r);  // torch.max propagates NaN (0/0 when every sigma <= 0)
+        float bg = white ? (1.f - f.A) : 0.f;
+        rgb[ray * 3 + 0] = f.R + bg;
+        rgb[ray * 3 + 1] = f.G + bg;
+        rgb[ray * 3 + 2] = f.Bc + bg;
+        disp[ray] = 1.f / m;
+        acc[ray] = f.A;
+        depth[ray] = f.D;
+      }
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                      int d_stride, const float* __restrict__ noise, int64_t n_rays, int white, int detach_w,
+                      const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
+                      const float* __restrict__ g_depth, const float* __restrict__ g_weights,
+                      const float* __restrict__ g_alpha, float4* __restrict__ d_raw) {
+  constexpr int S = 4 * G, RPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % G;
+  const int64_t stride = (int64_t)gridDim.x * kWarps * RPW;
+  for (int64_t ray0 = ((int64_t)blockIdx.x * kWarps + warp) * RPW; ray0 < n_rays; ray0 += stride) {
+    int64_t ray = ray0 + lane / G;
+    const bool live_ray = ray < n_rays;
+    if (!live_ray) ray = n_rays - 1;
+    const int64_t off = ray * S + sub * 4;
+    // upstream gradients first: their latency overlaps the forward recomputation
+    float gR = 0.f, gG = 0.f, gB = 0.f;
+    if (g_rgb) { gR = __ldg(g_rgb + ray * 3); gG = __ldg(g_rgb + ray * 3 + 1); gB = __ldg(g_rgb + ray * 3 + 2); }
+    const float gdisp = g_disp ? __ldg(g_disp + ray) : 0.f;
+    float gD = g_depth ? __ldg(g_depth + ray) : 0.f;
+    float gA = g_acc ? __ldg(g_acc + ray) : 0.f;
+    float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f), ga4 = gw4;
+    if (g_weights) gw4 = __ldg(reinterpret_cast<const float4*>(g_weights + off));
+    if (g_alpha) ga4 = __ldg(reinterpret_cast<const float4*>(g_alpha + off));
+    Fast4 f;
+    eval_ray4<G>(f, raw + off, z + off, noise ? noise + off : nullptr, rays_d + ray * d_stride, sub);
+    const float r = f.D / f.A;
+    if (!(r <= 1e-10f) && g_disp) {   // NaN keeps the path, as torch.max's backward does
+      gD += -gdisp * f.A / (f.D * f.D);
+      gA += gdisp / f.D;
+    }
+    if (white) gA -= (gR + gG + gB);
+    const float gwv[4] = {gw4.x, gw4.y, gw4.z, gw4.w}, gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+    float Gk[4], Gw[4];
+    float local = 0.f;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      float g = fmaf(f.zz[k], gD, gA) + gwv[k];
+      if (!detach_w) g += gR * f.cr[k] + gG * f.cg[k] + gB * f.cb[k];
+      Gk[k] = g;
+      Gw[k] = local;  // local exclusive suffix
+      local = fmaf(g, f.w[k], local);
+    }
+    float incl = local;   // exclusive suffix scan over the group's lanes
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      float v = __shfl_down_sync(FULL_MASK, incl, o, G);
+      incl += (sub + o < G) ? v : 0.f;
+    }
+    float excl = __shfl_down_sync(FULL_MASK, incl, 1, G);
+    if (sub == G - 1) excl = 0.f;
+    if (live_ray) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float dalpha = Gk[k] * f.T[k] - (Gw[k] + excl) * rcp_ftz(f.q[k]) + gav[k];
+        float4 o;
+        o.x = f.w[k] * gR * f.cr[k] * (1.f - f.cr[k]);
+        o.y = f.w[k] * gG * f.cg[k] * (1.f - f.cg[k]);
+        o.z = f.w[k] * gB * f.cb[k] * (1.f - f.cb[k]);
+        o.w = (f.sig[k] > 0.f) ? dalpha * f.delta[k] * f.e[k] : 0.f;
+        d_raw[off + k] = o;
+      }
+    }
+  }
+}
+
+int grid_for_rays4(int64_t n, int rays_per_warp) {
+  int64_t blocks = (n + (int64_t)kWarps * rays_per_warp - 1) / ((int64_t)kWarps * rays_per_warp);
+  int64_t cap = (int64_t)mvip_num_sms() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
 int grid_for_rays(int64_t n) {
   int64_t blocks = (n + kWarps - 1) / kWarps;
   int64_t cap = (int64_t)mvip_num_sms() * 8;
@@ -229,6 +417,18 @@ int mvip_composite_forward(const float* raw, const float* z_vals, const float* r
   MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(weights, 16) && (!alpha || mvip_aligned(alpha, 16)),
                MVIP_E_INVALID, "mvip_composite_forward: raw/weights/alpha must be 16-byte aligned");
   if (n_rays == 0) return MVIP_OK;
+  const bool vec_ok = mvip_aligned(z_vals, 16) && (!noise || mvip_aligned(noise, 16));
+  if (vec_ok && (n_samples == 64 || n_samples == 128)) {
+    auto* r4 = reinterpret_cast<const float4*>(raw);
+    if (n_samples == 128)
+      composite_fwd4_kernel<32><<<grid_for_rays4(n_rays, 1), kWarps * 32, 0, (cudaStream_t)stream>>>(
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha);
+    else
+      composite_fwd4_kernel<16><<<grid_for_rays4(n_rays, 2), kWarps * 32, 0, (cudaStream_t)stream>>>(
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha);
+    MVIP_LAUNCH_OK("composite_fwd4_kernel");
+    return MVIP_OK;
+  }
   DISPATCH_C(n_samples, (composite_fwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
                             reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
                             n_samples, white_bkgd, rgb, disp, acc, weights, depth, alpha)));
@@ -246,6 +446,22 @@ int mvip_composite_backward(const float* raw, const float* z_vals, const float* 
   MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(d_raw, 16), MVIP_E_INVALID,
                "mvip_composite_backward: raw/d_raw must be 16-byte aligned");
   if (n_rays == 0) return MVIP_OK;
+  const bool vec_ok = mvip_aligned(z_vals, 16) && (!noise || mvip_aligned(noise, 16)) &&
+                      (!g_weights || mvip_aligned(g_weights, 16)) && (!g_alpha || mvip_aligned(g_alpha, 16));
+  if (vec_ok && (n_samples == 64 || n_samples == 128)) {
+    auto* r4 = reinterpret_cast<const float4*>(raw);
+    auto* o4 = reinterpret_cast<float4*>(d_raw);
+    if (n_samples == 128)
+      composite_bwd4_kernel<32><<<grid_for_rays4(n_rays, 1), kWarps * 32, 0, (cudaStream_t)stream>>>(
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
+          g_weights, g_alpha, o4);
+    else
+      composite_bwd4_kernel<16><<<grid_for_rays4(n_rays, 2), kWarps * 32, 0, (cudaStream_t)stream>>>(
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
+          g_weights, g_alpha, o4);
+    MVIP_LAUNCH_OK("composite_bwd4_kernel");
+    return MVIP_OK;
+  }
   DISPATCH_C(n_samples, (composite_bwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
                             reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
                             n_samples, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha,

@@ -44,6 +44,16 @@ __device__ __forceinline__ void emit_ray(float* __restrict__ o, const float ro[3
   }
 }
 
+// block-wide: rows of rays [blk, blk + 256) staged in shared memory -> global, consecutive floats per consecutive thread
+__device__ __forceinline__ void flush_rows(const float* rows, float* __restrict__ out, int64_t blk, int64_t n, int stride) {
+  __syncthreads();
+  const int64_t left = n - blk;
+  const int total = (int)(left < 256 ? left : 256) * stride;
+  float* dst = out + blk * stride;
+  for (int e = threadIdx.x; e < total; e += 256) dst[e] = rows[e];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) rays_kernel(const float* __restrict__ c2w, const float* __restrict__ c2w_static, int H, int W,
                                                    float focal, float near, float far, int i0, int j0, int h, int w,
                                                    int use_viewdirs, Ndc ndc, float* __restrict__ out) {
@@ -53,9 +63,12 @@ __global__ void __launch_bounds__(256) rays_kernel(const float* __restrict__ c2w
     pose[12 + threadIdx.x] = c2w_static ? c2w_static[threadIdx.x] : c2w[threadIdx.x];
   }
   __syncthreads();
+  __shared__ float rows[256 * 11];   // rows are staged here and leave as consecutive 4-byte stores (a lane per float, not per ray)
   const int stride = use_viewdirs ? 11 : 8;
   const int64_t n = (int64_t)h * w;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t blk = (int64_t)blockIdx.x * blockDim.x; blk < n; blk += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = blk + threadIdx.x;
+    if (idx < n) {
     const int i = i0 + (int)(idx / w), j = j0 + (int)(idx % w);
     const float dx = __fdiv_rn(__fsub_rn((float)j, __fmul_rn((float)W, .5f)), focal);
     const float dy = -__fdiv_rn(__fsub_rn((float)i, __fmul_rn((float)H, .5f)), focal);
@@ -69,7 +82,9 @@ __global__ void __launch_bounds__(256) rays_kernel(const float* __restrict__ c2w
       const float* Rv = pose + 4 * k;
       v[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, Rv[0]), __fmul_rn(dy, Rv[1])), __fmul_rn(dz, Rv[2]));
     }
-    emit_ray(out + idx * stride, ro, rd, v, near, far, use_viewdirs, ndc);
+    emit_ray(rows + threadIdx.x * stride, ro, rd, v, near, far, use_viewdirs, ndc);
+    }
+    flush_rows(rows, out, blk, n, stride);
   }
 }
 
@@ -77,16 +92,21 @@ __global__ void __launch_bounds__(256) rays_kernel(const float* __restrict__ c2w
 __global__ void __launch_bounds__(256) rays_pack_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                         const float* __restrict__ view_d, int64_t n, float near, float far,
                                                         int use_viewdirs, Ndc ndc, float* __restrict__ out) {
+  __shared__ float rows[256 * 11];
   const int stride = use_viewdirs ? 11 : 8;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-    float ro[3], rd[3], v[3];
+  for (int64_t blk = (int64_t)blockIdx.x * blockDim.x; blk < n; blk += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t idx = blk + threadIdx.x;
+    if (idx < n) {
+      float ro[3], rd[3], v[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      ro[k] = rays_o[idx * 3 + k];
-      rd[k] = rays_d[idx * 3 + k];
-      v[k] = view_d ? view_d[idx * 3 + k] : rd[k];
+      for (int k = 0; k < 3; ++k) {
+        ro[k] = rays_o[idx * 3 + k];
+        rd[k] = rays_d[idx * 3 + k];
+        v[k] = view_d ? view_d[idx * 3 + k] : rd[k];
+      }
+      emit_ray(rows + threadIdx.x * stride, ro, rd, v, near, far, use_viewdirs, ndc);
     }
-    emit_ray(out + idx * stride, ro, rd, v, near, far, use_viewdirs, ndc);
+    flush_rows(rows, out, blk, n, stride);
   }
 }
 

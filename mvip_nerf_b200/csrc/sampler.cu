@@ -53,6 +53,64 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, int ray_str
   z_out[idx] = z;
 }
 
+// Warp-per-ray form for S = 32 C (C = 1, 2, 4): lane l owns samples [l C, l C + C).  The per-sample table values
+// (t, 1 - t) live in registers across rays, 1/near and 1/far are ONE reciprocal instruction (lane parity picks the
+// operand), every stratum is evaluated once and its neighbours' values arrive by shuffle, t_rand / z move as 4C-byte
+// vectors.  ~1.5 instructions per sample instead of ~120 (three stratum evaluations with five IEEE divisions each).
+// __frcp_rn is the correctly rounded reciprocal == IEEE 1/x == torch's reciprocal.
+template <int C>
+__global__ void __launch_bounds__(256)
+sample_coarse_warp_kernel(const float* __restrict__ rays, int ray_stride, int64_t n_rays, const float* __restrict__ t_vals,
+                          const float* __restrict__ t_rand, int lindisp, float* __restrict__ z_out) {
+  constexpr int S = 32 * C;
+  const int lane = threadIdx.x & 31;
+  float t[C], omt[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    t[k] = __ldg(t_vals + lane * C + k);
+    omt[k] = __fsub_rn(1.0f, t[k]);
+  }
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rays; r += nwarps) {
+    float nf = __ldg(rays + r * ray_stride + 6 + (lane & 1));     // even lanes: near, odd lanes: far
+    if (lindisp) nf = __frcp_rn(nf);
+    const float a = __shfl_sync(FULL_MASK, nf, 0), b = __shfl_sync(FULL_MASK, nf, 1);
+    float z[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      z[k] = __fadd_rn(__fmul_rn(a, omt[k]), __fmul_rn(b, t[k]));
+      if (lindisp) z[k] = __frcp_rn(z[k]);
+    }
+    if (t_rand != nullptr) {
+      const float prev = __shfl_up_sync(FULL_MASK, z[C - 1], 1), next = __shfl_down_sync(FULL_MASK, z[0], 1);
+      float tr[C];
+      if constexpr (C == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(t_rand + r * S) + lane);
+        tr[0] = v.x; tr[1] = v.y; tr[2] = v.z; tr[3] = v.w;
+      } else if constexpr (C == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(t_rand + r * S) + lane);
+        tr[0] = v.x; tr[1] = v.y;
+      } else {
+        tr[0] = __ldg(t_rand + r * S + lane);
+      }
+      float out[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float zp = (k > 0) ? z[(k > 0) ? k - 1 : 0] : prev, zn = (k + 1 < C) ? z[(k + 1 < C) ? k + 1 : k] : next;
+        float lower = __fmul_rn(0.5f, __fadd_rn(z[k], zp)), upper = __fmul_rn(0.5f, __fadd_rn(zn, z[k]));
+        if (k == 0 && lane == 0) lower = z[k];
+        if (k == C - 1 && lane == 31) upper = z[k];
+        out[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[k]));
+      }
+#pragma unroll
+      for (int k = 0; k < C; ++k) z[k] = out[k];
+    }
+    if constexpr (C == 4) reinterpret_cast<float4*>(z_out + r * S)[lane] = make_float4(z[0], z[1], z[2], z[3]);
+    else if constexpr (C == 2) reinterpret_cast<float2*>(z_out + r * S)[lane] = make_float2(z[0], z[1]);
+    else z_out[r * S + lane] = z[0];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // torch.sum over K contiguous floats in ATen's CPU order; every lane returns the same value.
 __device__ float aten_row_sum(const float* x, int K, int lane) {
@@ -283,6 +341,17 @@ int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const 
                "mvip_sample_coarse: bad shape (ray_stride=%d n_samples=%d)", ray_stride, n_samples);
   if (n_rays == 0) return MVIP_OK;  // empty batch: nothing to do (pointers may be null)
   MVIP_REQUIRE(rays && t_vals && z_out, MVIP_E_INVALID, "mvip_sample_coarse: null pointer");
+  if ((n_samples == 32 || n_samples == 64 || n_samples == 128) && mvip_aligned(z_out, 16) && (!t_rand || mvip_aligned(t_rand, 16))) {
+    int64_t blocks = (n_rays + 7) / 8;
+    const int64_t cap = (int64_t)mvip_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    auto st = (cudaStream_t)stream;
+    if (n_samples == 32) sample_coarse_warp_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    else if (n_samples == 64) sample_coarse_warp_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    else sample_coarse_warp_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    MVIP_LAUNCH_OK("sample_coarse_warp_kernel");
+    return MVIP_OK;
+  }
   int64_t total = n_rays * n_samples;
   int threads = 256;
   int64_t blocks = (total + threads - 1) / threads;
