@@ -325,6 +325,164 @@ sample_fine_kernel(const float* __restrict__ z_g, const float* __restrict__ weig
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// sample_fine for the shape render_rays uses (N_samples = 64 coarse depths, N_importance = 64): one warp per ray, lane l
+// owns z[2l..2l+1], the two pdf entries p[2l..2l+1] and the two draws u[2l..2l+1].  Compared with the generic kernel:
+//   * rows move as 8-byte vectors, the weights never round-trip through shared memory except for the ATen-order row sum;
+//   * the fp64 cdf scan works on register values; only cdf / bins (the binary-search tables) live in shared memory;
+//   * the searches are the branch-free 6-step form (no bounds test: 32+16+8+4+2+1-1 = 62 is the last cdf index);
+//   * unsorted draws are ordered by a REGISTER bitonic network (15 shuffle stages on 2 values per lane) instead of a
+//     shared-memory one, and the sorted run is merged with the coarse depths by a 7-stage bitonic MERGE (reverse the
+//     samples, then compare-exchange at distances 64..1) instead of 128 binary searches.
+// Every value written is bit-identical to the generic kernel's (same roundings; sort / merge only permute values).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float invert_cdf64(const float* cdf, const float* bins, float u, int* ind_out) {
+  int pos = 0;
+#pragma unroll
+  for (int step = 32; step > 0; step >>= 1)
+    if (cdf[pos + step - 1] <= u) pos += step;      // #{i < 63 : cdf[i] <= u} == upper_bound
+  *ind_out = pos;
+  const int below = max(0, pos - 1), above = min(62, pos);
+  const float cb = cdf[below];
+  float denom = __fsub_rn(cdf[above], cb);
+  if (denom < 1e-5f) denom = 1.0f;
+  const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  const float bb = bins[below];
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bins[above], bb)));
+}
+
+__device__ __forceinline__ void cmpx(float& lo, float& hi) {
+  const float a = fminf(lo, hi), b = fmaxf(lo, hi);
+  lo = a; hi = b;
+}
+
+template <bool U_ROW>
+__global__ void __launch_bounds__(256)
+sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ weights_g, const float* __restrict__ u_g,
+                     int64_t n_rays, float* __restrict__ samples_g, int64_t* __restrict__ inds_g,
+                     float* __restrict__ merged_g, float* __restrict__ std_g) {
+  __shared__ float sm[8][3][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* w = sm[warp][0];
+  float* cdf = sm[warp][1];
+  float* bins = sm[warp][2];
+  float2 u2 = make_float2(0.f, 0.f);
+  if (U_ROW) u2 = __ldg(reinterpret_cast<const float2*>(u_g) + lane);
+  for (int64_t ray = (int64_t)blockIdx.x * 8 + warp; ray < n_rays; ray += (int64_t)gridDim.x * 8) {
+    const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_g + ray * 64) + lane);
+    const float2 w2 = __ldg(reinterpret_cast<const float2*>(weights_g + ray * 64) + lane);
+    if (!U_ROW) u2 = __ldg(reinterpret_cast<const float2*>(u_g + ray * 64) + lane);
+    // w[i] = weights[i+1] + 1e-5 (i < 62): weights[2l] is w[2l-1], weights[2l+1] is w[2l]
+    const float wa = __fadd_rn(w2.x, 1e-5f), wb = __fadd_rn(w2.y, 1e-5f);
+    if (lane > 0) w[2 * lane - 1] = wa;
+    if (lane < 31) w[2 * lane] = wb;
+    const float z_next = __shfl_down_sync(FULL_MASK, z2.x, 1);
+    bins[2 * lane] = __fmul_rn(0.5f, __fadd_rn(z2.y, z2.x));
+    if (lane < 31) bins[2 * lane + 1] = __fmul_rn(0.5f, __fadd_rn(z_next, z2.y));
+    __syncwarp();
+    // torch.sum in ATen's CPU order for K = 62: 7 vectors of 8 lanes (4 accumulators, vectors 4..6 fold into the first),
+    // then the 6-element tail, then the 8 lanes of the combined vector, all sequential fp32 adds
+    float t = 0.f;
+    if (lane < 8) {
+      float ps0 = w[lane];
+      const float ps1 = w[8 + lane], ps2 = w[16 + lane], ps3 = w[24 + lane];
+      ps0 = __fadd_rn(ps0, w[32 + lane]);
+      ps0 = __fadd_rn(ps0, w[40 + lane]);
+      ps0 = __fadd_rn(ps0, w[48 + lane]);
+      t = __fadd_rn(__fadd_rn(__fadd_rn(ps0, ps1), ps2), ps3);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 56; k < 62; ++k) s = __fadd_rn(s, w[k]);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(FULL_MASK, t, l));
+    // pdf entries of this lane: p[2l] = w[2l] / s (own wb), p[2l+1] = w[2l+1] / s (next lane's wa); lane 31 has none
+    const float wa_next = __shfl_down_sync(FULL_MASK, wa, 1);
+    const float p0 = __fdiv_rn(wb, s), p1 = __fdiv_rn(wa_next, s);
+    bool ok = (lane == 31) || ((p0 >= 7.450580596923828e-09f) && (p0 <= 1.0f) && (p1 >= 7.450580596923828e-09f) && (p1 <= 1.0f));
+    ok = __all_sync(FULL_MASK, ok);
+    __syncwarp();                                   // all reads of w[] are done before the fallback may overwrite it
+    if (ok) {                                       // exact fp64 scan == the sequential CPU cumsum (see warp_build_cdf)
+      const double d0 = (lane < 31) ? (double)p0 : 0.0, d1 = (lane < 31) ? (double)p1 : 0.0;
+      const double local = d0 + d1;
+      double incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+      }
+      double run = incl - local;
+      run += d0;
+      if (lane < 31) cdf[2 * lane + 1] = (float)run;
+      run += d1;
+      if (lane < 31) cdf[2 * lane + 2] = (float)run;
+      if (lane == 0) cdf[0] = 0.f;
+    } else {
+      if (lane < 31) { w[2 * lane] = p0; w[2 * lane + 1] = p1; }
+      __syncwarp();
+      if (lane == 0) {
+        double run = 0.0;
+        cdf[0] = 0.f;
+        for (int i = 0; i < 62; ++i) {
+          run += (double)w[i];
+          cdf[i + 1] = (float)run;
+        }
+      }
+    }
+    __syncwarp();
+    int i0, i1;
+    float s0 = invert_cdf64(cdf, bins, u2.x, &i0);
+    float s1 = invert_cdf64(cdf, bins, u2.y, &i1);
+    if (samples_g) reinterpret_cast<float2*>(samples_g + ray * 64)[lane] = make_float2(s0, s1);
+    if (inds_g) reinterpret_cast<longlong2*>(inds_g + ray * 64)[lane] = make_longlong2((long long)i0, (long long)i1);
+    if (std_g) {  // torch.std(unbiased=False), run.py:1836 (tolerance-checked, not bit-exact)
+      const double mean = warp_sum((double)s0 + (double)s1) * (1.0 / 64.0);
+      const double e0 = (double)s0 - mean, e1 = (double)s1 - mean;
+      const double sq = warp_sum(e0 * e0 + e1 * e1);
+      if (lane == 0) std_g[ray] = (float)sqrt(sq * (1.0 / 64.0));
+    }
+    // ---- order the 64 samples (element e = 2 lane + r) if the draws were not sorted
+    const float s_next = __shfl_down_sync(FULL_MASK, s0, 1);
+    const bool sorted = (s0 <= s1) && (lane == 31 || s1 <= s_next);
+    if (!__all_sync(FULL_MASK, sorted)) {
+#pragma unroll
+      for (int k = 2; k <= 64; k <<= 1) {
+        const bool up = ((2 * lane) & k) == 0;
+#pragma unroll
+        for (int j = k >> 1; j > 1; j >>= 1) {
+          const bool keep_min = ((((2 * lane) & j) == 0) == up);
+          const float o0 = __shfl_xor_sync(FULL_MASK, s0, j >> 1), o1 = __shfl_xor_sync(FULL_MASK, s1, j >> 1);
+          s0 = keep_min ? fminf(s0, o0) : fmaxf(s0, o0);
+          s1 = keep_min ? fminf(s1, o1) : fmaxf(s1, o1);
+        }
+        const float a = fminf(s0, s1), b = fmaxf(s0, s1);   // j == 1: the pair inside the lane
+        s0 = up ? a : b;
+        s1 = up ? b : a;
+      }
+    }
+    // ---- bitonic merge of (z ascending, samples descending): element E = 2 lane + r for z, 64 + 2 lane + r for samples
+    float a0 = z2.x, a1 = z2.y;
+    float b0 = __shfl_sync(FULL_MASK, s1, 31 - lane), b1 = __shfl_sync(FULL_MASK, s0, 31 - lane);
+    cmpx(a0, b0);
+    cmpx(a1, b1);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const bool keep_min = (lane & m) == 0;
+      const float o0 = __shfl_xor_sync(FULL_MASK, a0, m), o1 = __shfl_xor_sync(FULL_MASK, a1, m);
+      const float o2 = __shfl_xor_sync(FULL_MASK, b0, m), o3 = __shfl_xor_sync(FULL_MASK, b1, m);
+      a0 = keep_min ? fminf(a0, o0) : fmaxf(a0, o0);
+      a1 = keep_min ? fminf(a1, o1) : fmaxf(a1, o1);
+      b0 = keep_min ? fminf(b0, o2) : fmaxf(b0, o2);
+      b1 = keep_min ? fminf(b1, o3) : fmaxf(b1, o3);
+    }
+    cmpx(a0, a1);
+    cmpx(b0, b1);
+    reinterpret_cast<float2*>(merged_g + ray * 128)[lane] = make_float2(a0, a1);
+    reinterpret_cast<float2*>(merged_g + ray * 128 + 64)[lane] = make_float2(b0, b1);
+    __syncwarp();                                   // the next ray overwrites w / cdf / bins
+  }
+}
+
 int grid_for_rows(int64_t rows) {
   int64_t blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = (int64_t)mvip_num_sms() * 16;
@@ -386,6 +544,20 @@ int mvip_sample_fine(const float* z_vals, const float* weights, const float* u, 
                "mvip_sample_fine: need 10 <= n_samples <= %d and n_out <= %d (got %d, %d)", kMaxBins + 1, kMaxOut,
                n_samples, n_out);
   if (n_rays == 0) return MVIP_OK;
+  if (n_samples == 64 && n_out == 64 && mvip_aligned(z_vals, 8) && mvip_aligned(weights, 8) && mvip_aligned(u, 8) &&
+      mvip_aligned(z_merged, 8) && (!z_samples || mvip_aligned(z_samples, 8)) && (!inds || mvip_aligned(inds, 16))) {
+    int64_t blocks = (n_rays + 7) / 8;
+    const int64_t cap = (int64_t)mvip_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (u_is_row)
+      sample_fine64_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z_vals, weights, u, n_rays, z_samples, inds,
+                                                                                     z_merged, z_std);
+    else
+      sample_fine64_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z_vals, weights, u, n_rays, z_samples, inds,
+                                                                                      z_merged, z_std);
+    MVIP_LAUNCH_OK("sample_fine64_kernel");
+    return MVIP_OK;
+  }
   int P2 = 1;
   while (P2 < n_out) P2 <<= 1;
   int B = n_samples - 1;

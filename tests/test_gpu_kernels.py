@@ -83,6 +83,59 @@ def test_sample_fine_merge_vs_reference(ops, golden):
     assert np.array_equal(npy(out["inds"]), want["inds"])
 
 
+@pytest.mark.parametrize("mode", ["rand", "det", "rand_sorted_rows"])
+def test_sample_fine_64x64_fast_path_vs_oracle(ops, mode):
+    """The register kernel of the render_rays shape (64 depths, 64 draws): samples / inds / merged depths bit-exact against the
+    oracle on 20k fuzzed rays, including rows whose tiny pdf entries take the sequential-scan fallback, ties (u = 0, u = 1,
+    repeated draws) and all-zero weights; and equal to the generic kernel on the same inputs."""
+    rng = np.random.RandomState(11)
+    N = 20000
+    z = np.sort(1.2 + 6.5 * rng.rand(N, 64).astype(np.float32), -1)
+    z[::11, 5] = z[::11, 4]                                 # repeated depths
+    w = (rng.rand(N, 64) ** 8).astype(np.float32)
+    w[::7] *= (rng.rand(*w[::7].shape) > 0.9)
+    w[::13] = 0
+    w[5::17] *= 1e-12                                       # tiny pdf entries exercise the sequential-scan fallback
+    w[5::17, 3] = 1.0
+    if mode == "det":
+        u = orc.linspace_f32(0, 1, 64)
+    else:
+        u = rng.rand(N, 64).astype(np.float32)
+        u[:, 0] = 0.0
+        u[:, 1] = 1.0
+        u[::5, 7] = u[::5, 6]
+        if mode == "rand_sorted_rows":
+            u = np.sort(u, -1)
+    want = orc.fine_samples(z, w, u)
+    out = ops.sample_fine(cu(z), cu(w), cu(u), want_inds=True)
+    assert np.array_equal(npy(out["inds"]), want["inds"])
+    assert np.array_equal(npy(out["z_samples"]), want["z_samples"])
+    assert np.array_equal(npy(out["z_merged"]), want["z_merged"])
+    np.testing.assert_allclose(npy(out["z_std"]), want["z_std"], rtol=2e-5, atol=1e-6)
+    # the generic kernel (taken for any other shape) on an embedding of the same problem: 64 draws -> 65 with a duplicate
+    if mode != "det":
+        u65 = np.concatenate([u, u[:, -1:]], -1)
+        gen = ops.sample_fine(cu(z[:512]), cu(w[:512]), cu(u65[:512]), want_inds=True)
+        assert np.array_equal(npy(gen["z_samples"])[:, :64], npy(out["z_samples"])[:512])
+
+
+def test_sample_coarse_shapes_vs_oracle(ops):
+    """warp-per-ray kernels (S = 32 / 64 / 128) and the generic one (S = 48) against the oracle, both lindisp modes"""
+    rng = np.random.RandomState(5)
+    N = 3001
+    rays = rng.randn(N, 11).astype(np.float32)
+    rays[:, 6] = 0.5 + rng.rand(N)
+    rays[:, 7] = rays[:, 6] + 0.1 + 6 * rng.rand(N)
+    for S in (32, 48, 64, 128):
+        t = orc.linspace_f32(0, 1, S)
+        tr = rng.rand(N, S).astype(np.float32)
+        for lindisp in (False, True):
+            for use_tr in (False, True):
+                want = orc.sample_coarse(rays, t, tr if use_tr else None, lindisp)
+                got = ops.sample_coarse(cu(rays), cu(t), cu(tr) if use_tr else None, lindisp)
+                assert np.array_equal(npy(got), want), (S, lindisp, use_tr)
+
+
 def test_sample_shapes_rejected(ops):
     z = torch.zeros(4, 8, device="cuda")
     with pytest.raises(RuntimeError, match="n_samples"):
