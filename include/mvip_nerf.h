@@ -152,6 +152,11 @@ int mvip_embed(const float* in, int64_t in_stride, int64_t n, int dims, int num_
 int mvip_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
                    float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, float lr, float beta1,
                    float beta2, float eps, int64_t step, void* stream);
+/* Same update with the learning rate (1 float) and the 1-based step number (1 int64) read from DEVICE memory at execution
+ * time: the form a CUDA graph of the training step captures (both change between replays). */
+int mvip_adam_step_dev(float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, const float* lr_dev, float beta1,
+                       float beta2, float eps, const int64_t* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused positional encoding + 8x256 NeRF MLP (use_viewdirs, skip at 4).

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "mvip_normal_backward_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mvip_adam_step": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int,
                                c_float, c_float, c_float, c_float, c_int64, c_void_p]),
+    "mvip_adam_step_dev": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int,
+                                   c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
     "mvip_embed": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "mvip_mlp_packed_bytes": (c_size_t, []),
     "mvip_mlp_pack_weights": (c_int, [POINTER(c_void_p), c_void_p, c_void_p]),

@@ -13,6 +13,19 @@
 // ------------------------------------------------------------------------------------------------
 void mvip_set_error(const char* fmt, ...);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device): keeps the call out of the steady state
+// and out of CUDA-graph capture (the first, un-captured warm-up call has already made it)
+#define MVIP_SMEM_OPT_IN(kernel, bytes)                                                                              \
+  do {                                                                                                               \
+    static unsigned long long done__ = 0ull;                                                                         \
+    int dev__ = 0;                                                                                                   \
+    MVIP_CUDA_OK(cudaGetDevice(&dev__));                                                                             \
+    if (dev__ >= 64 || !((done__ >> dev__) & 1ull)) {                                                                \
+      MVIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      if (dev__ < 64) done__ |= 1ull << dev__;                                                                       \
+    }                                                                                                                \
+  } while (0)
+
 #define MVIP_REQUIRE(cond, code, ...)        \
   do {                                       \
     if (!(cond)) {                           \

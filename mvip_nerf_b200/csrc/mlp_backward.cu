@@ -969,53 +969,104 @@ struct ReduceParams {
   int accumulate;
 };
 
+constexpr int kReduceGridX = 80;     // 256 x 320 floats / 4 per thread / 256 threads
+
+// Fixed summation order everywhere (slot order; for the heads: stripe-of-8 order, then stripe order) => bitwise
+// reproducible gradients.  Every thread keeps 8 independent 16-byte (weights) / 4-byte (heads) loads in flight: the
+// first version walked ~30 slots (weights) and up to 1184 partials (heads) with a dependent add per load and took
+// 70 us per launch at 0.5 TB/s.
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ int slots[2 * kMaxCtas];
   __shared__ int nslots;
+  __shared__ float hred[8][32];
   const int item = blockIdx.y;
   if (item == kRealItems) {
-    // heads: alpha_linear / rgb_linear
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kHeadFloats; e += gridDim.x * blockDim.x) {
+    // heads: alpha_linear / rgb_linear.  Block x owns elements [32x, 32x+32); warp w sums partials w, w+8, ... (lane = element)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e0 = blockIdx.x * 32; e0 < kHeadFloats; e0 += gridDim.x * 32) {
+      const int e = e0 + lane;
       float s = 0.f;
-      for (int b = 0; b < p.head_grid; ++b) s += p.head_partials[(size_t)b * kHeadFloats + e];
-      float* dst = nullptr;
-      if (e < 256) dst = p.grads.p[kPAlphaW] + e;
-      else if (e == 256) dst = p.grads.p[kPAlphaB];
-      else if (e >= 260 && e < 644) dst = p.grads.p[kPRgbW] + (e - 260);
-      else if (e >= 644 && e < 647) dst = p.grads.p[kPRgbB] + (e - 644);
-      if (dst) *dst = p.accumulate ? *dst + s : s;
+      if (e < kHeadFloats) {
+        int b = warp;
+        for (; b + 56 < p.head_grid; b += 64) {
+          float a[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[k] = p.head_partials[(size_t)(b + 8 * k) * kHeadFloats + e];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += a[k];
+        }
+        for (; b < p.head_grid; b += 8) s += p.head_partials[(size_t)b * kHeadFloats + e];
+      }
+      hred[warp][lane] = s;
+      __syncthreads();
+      if (warp == 0 && e < kHeadFloats) {
+        float t = hred[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += hred[k][lane];
+        float* dst = nullptr;
+        if (e < 256) dst = p.grads.p[kPAlphaW] + e;
+        else if (e == 256) dst = p.grads.p[kPAlphaB];
+        else if (e >= 260 && e < 644) dst = p.grads.p[kPRgbW] + (e - 260);
+        else if (e >= 644 && e < 647) dst = p.grads.p[kPRgbB] + (e - 644);
+        if (dst) *dst = p.accumulate ? *dst + t : t;
+      }
+      __syncthreads();
     }
     return;
   }
+  // slots of this item, in slot order: the segment table is read by all threads at once (one thread walking the 296
+  // entries in global memory was 15 us of latency), then compacted from shared memory
+  __shared__ unsigned char mine[2 * kMaxCtas];
+  for (int i = threadIdx.x; i < 2 * p.w_grid; i += blockDim.x) {
+    const Segment sg = p.segs[i];
+    mine[i] = (sg.item == item && sg.t1 > sg.t0) ? 1 : 0;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int n = 0;
     for (int i = 0; i < 2 * p.w_grid; ++i)
-      if (p.segs[i].item == item && p.segs[i].t1 > p.segs[i].t0) slots[n++] = i;
+      if (mine[i]) slots[n++] = i;
     nslots = n;
   }
   __syncthreads();
   const WItem& itm = kItems[item];
   const int rows = 128 * itm.m_blocks, ntot = 64 * itm.nb;
   const size_t slot_floats = kPartialSlotBytes / sizeof(float);
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * ntot; e += gridDim.x * blockDim.x) {
-    const int row = e / ntot, n = e % ntot;
+  for (int e = 4 * (blockIdx.x * blockDim.x + threadIdx.x); e < rows * ntot; e += 4 * gridDim.x * blockDim.x) {
+    const int row = e / ntot, n = e % ntot;     // ntot is a multiple of 64: the four elements share a B chunk
     const int j = n >> 6, w = n & 63;
     if (w >= itm.valid[j]) continue;
-    float s = 0.f;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int k = 0;
-    for (; k + 4 <= nslots; k += 4) {   // four loads in flight, summed in slot order (deterministic)
-      const float a0 = p.partials[(size_t)slots[k] * slot_floats + e], a1 = p.partials[(size_t)slots[k + 1] * slot_floats + e];
-      const float a2 = p.partials[(size_t)slots[k + 2] * slot_floats + e], a3 = p.partials[(size_t)slots[k + 3] * slot_floats + e];
-      s += a0; s += a1; s += a2; s += a3;
+    for (; k + 8 <= nslots; k += 8) {   // eight loads in flight, summed in slot order (deterministic)
+      float4 a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = *reinterpret_cast<const float4*>(p.partials + (size_t)slots[k + q] * slot_floats + e);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { s.x += a[q].x; s.y += a[q].y; s.z += a[q].z; s.w += a[q].w; }
     }
-    for (; k < nslots; ++k) s += p.partials[(size_t)slots[k] * slot_floats + e];
-    float* dst = p.grads.p[itm.dst] + (size_t)row * itm.ld + itm.col[j] + w;
-    *dst = p.accumulate ? *dst + s : s;
+    for (; k < nslots; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(p.partials + (size_t)slots[k] * slot_floats + e);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    float* dst = p.grads.p[itm.dst] + (size_t)row * itm.ld + itm.col[j] + w;   // ld = 63 / 283 / 319: scalar stores
+    const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (w + q < itm.valid[j]) dst[q] = p.accumulate ? dst[q] + v[q] : v[q];
   }
-  if (itm.bias >= 0) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows; e += gridDim.x * blockDim.x) {
+  if (itm.bias >= 0 && blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < rows; e += blockDim.x) {
       float s = 0.f;
-      for (int k = 0; k < nslots; ++k) s += p.bias_partials[(size_t)slots[k] * 256 + e];
+      int k = 0;
+      for (; k + 8 <= nslots; k += 8) {
+        float a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = p.bias_partials[(size_t)slots[k + q] * 256 + e];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += a[q];
+      }
+      for (; k < nslots; ++k) s += p.bias_partials[(size_t)slots[k] * 256 + e];
       float* dst = p.grads.p[itm.bias] + e;
       *dst = p.accumulate ? *dst + s : s;
     }
@@ -1129,7 +1180,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     cp.flags = flags;
     wp.flags = flags;
     const size_t smem = (kDSmemBytes > kWSmemBytes ? kDSmemBytes : kWSmemBytes) + 1024;
-    MVIP_CUDA_OK(cudaFuncSetAttribute(backward_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
     backward_fused_kernel<<<sms, kDThreads, smem, st>>>(cp, wp, n_dgrad);
     MVIP_LAUNCH_OK("backward_fused_kernel");
   }
@@ -1141,14 +1192,14 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
       const int max_clusters = sms / 2;
       const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
       const size_t smem2 = kDSmemBytes + 1024;
-      MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      MVIP_SMEM_OPT_IN(dgrad_pair_kernel, smem2);
       dgrad_pair_kernel<<<grid2, kDThreads, smem2, st>>>(cp);
       MVIP_LAUNCH_OK("dgrad_pair_kernel");
     } else {
       const int64_t n_pairs = (n_tiles + 1) / 2;
       const int grid = (int)(n_pairs < sms ? n_pairs : sms);
       const size_t smem = kCSmemBytes + 2560 + 128;
-      MVIP_CUDA_OK(cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MVIP_SMEM_OPT_IN(dgrad_chain_kernel, smem);
       dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
       MVIP_LAUNCH_OK("dgrad_chain_kernel");
     }
@@ -1156,7 +1207,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   // 2. wgrad
   if (!fused && (phase_mask & 2)) {
     const size_t smem = kWSmemBytes + 1024;
-    MVIP_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVIP_SMEM_OPT_IN(wgrad_kernel, smem);
     wgrad_kernel<<<w_grid, kWThreads, smem, st>>>(wp);
     MVIP_LAUNCH_OK("wgrad_kernel");
   }
@@ -1179,7 +1230,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     rp.head_grid = head_grid;
     rp.grads = gp;
     rp.accumulate = accumulate;
-    reduce_kernel<<<dim3(32, kRealItems + 1), 256, 0, st>>>(rp);
+    reduce_kernel<<<dim3(kReduceGridX, kRealItems + 1), 256, 0, st>>>(rp);
     MVIP_LAUNCH_OK("reduce_kernel");
   }
   return MVIP_OK;

@@ -969,10 +969,10 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
     const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
     const size_t smem2 = (stash ? kSmemBytes2Train : kSmemBytes2Infer) + 1024;
     if (stash) {
-      MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<true>, smem2);
       mlp_forward_pair_kernel<true><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
     } else {
-      MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<false>, smem2);
       mlp_forward_pair_kernel<false><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
     }
     MVIP_LAUNCH_OK("mlp_forward_pair_kernel");
@@ -982,10 +982,10 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
   const int grid = (int)(n_pairs < mvip_num_sms() ? n_pairs : mvip_num_sms());
   const size_t smem = kSmemBytes + 1024;
   if (stash) {
-    MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVIP_SMEM_OPT_IN(mlp_forward_kernel<true>, smem);
     mlp_forward_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   } else {
-    MVIP_CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVIP_SMEM_OPT_IN(mlp_forward_kernel<false>, smem);
     mlp_forward_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   }
   MVIP_LAUNCH_OK("mlp_forward_kernel");

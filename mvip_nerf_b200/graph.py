@@ -1,0 +1,122 @@
+"""One training step as CUDA graphs (B200: launch-bound glue replaced by graph replays).
+
+A cfg-2 step is ~45 kernel launches, 16 of them ours; the three MLP kernels take 90 % of the GPU time and everything else
+(random draws, the loss and its autograd, ray packing, sampling, compositing, Adam, the bf16 re-pack) is a string of
+5-20 us kernels whose launch gaps — and, end to end, the Python that issues them after every `loss.item()` — add up to
+~10 % of the step.  GraphedTrainStep captures
+
+    graph A: rays -> render() -> loss -> backward                      (fresh random draws on every replay: torch registers the
+                                                                        CUDA generator with the graph and advances its offset)
+    eager  : gradient allreduce (N > 1 only; NCCL stays outside the graphs)
+    graph B: Adam (lr and step number read from device memory) -> re-pack of the bf16 weight blobs
+
+once, after warm-up, and replays them.  Inputs live in static buffers; `__call__(rays, target)` copies into them (from pinned
+host memory for the end-to-end path) and returns the loss as a device scalar.  Same arithmetic as the eager step: the captured
+launches ARE the eager step's launches.
+"""
+import torch
+
+from . import dist as mdist
+from . import ops, run
+from .run_nerf_helpers import img2mse
+
+
+def default_loss(rgb, disp, acc, depth, extras, target, scale):
+    """img2mse(rgb, target) + img2mse(rgb0, target)   (run.py:1000, 1024-1026), scaled for data-parallel averaging"""
+    loss = img2mse(rgb, target)
+    if "rgb0" in extras:
+        loss = loss + img2mse(extras["rgb0"], target)
+    return loss * scale
+
+
+class GraphedTrainStep:
+    def __init__(self, render_kwargs_train, optimizer, H, W, focal, n_rays, near, far, chunk=1024 * 32, loss_fn=default_loss,
+                 target_shape=None, warmup=3, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphedTrainStep needs a CUDA device (no CPU fallback)")
+        self.kw = dict(render_kwargs_train)
+        self.opt = optimizer
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.args = (H, W, focal)
+        self.chunk, self.near, self.far = chunk, near, far
+        self.loss_fn = loss_fn
+        self.scale = 1.0 / mdist.world()
+        self.rays = torch.zeros((2, n_rays, 3), device=self.dev)
+        self.target = torch.zeros(tuple(target_shape or (n_rays, 3)), device=self.dev)
+        self.nets = [n for n, _ in run._net_params(self.kw)]
+        self.groups = [ps for _, ps in reversed(run._net_params(self.kw))]      # fine first: its gradients exist first
+        self.warmup = warmup
+        self.graph_a = self.graph_b = None
+        self.loss = None
+
+    # -- the two halves of the step, exactly as the eager loop runs them -----------------------------------------------
+    def _forward_backward(self):
+        self.opt.zero_grad(set_to_none=True)
+        H, W, focal = self.args
+        rgb, disp, acc, depth, extras = run.render(H, W, focal, chunk=self.chunk, rays=self.rays, near=self.near, far=self.far,
+                                                   **self.kw)
+        loss = self.loss_fn(rgb, disp, acc, depth, extras, self.target, self.scale)
+        loss.backward()
+        return loss.detach()
+
+    def _update(self):
+        self.opt.step_captured()
+        for net in self.nets:                 # refresh the bf16 operand blobs the next forward reads
+            net._packed = ops.mlp_pack(net._ordered_params(), out=net._packed)
+
+    def _mark_packed_fresh(self):
+        for net in self.nets:
+            net._packed_key = (ops.param_epoch,) + tuple((p.data_ptr(), p._version) for p in net._ordered_params())
+
+    def capture(self):
+        """Warm-up on a side stream (allocator pools, lazy module loads, smem opt-ins), then capture both graphs.  Parameters,
+        Adam moments and the step count are snapshotted before and restored after the warm-up, so capturing trains nothing."""
+        self.opt.graph_begin(self.dev)
+        self.opt.graph_set_lr()
+        for net in self.nets:
+            net.packed()
+        params = [p for ps in self.groups for p in ps]
+        snap = [(p.detach().clone(), self.opt.state[p]["exp_avg"].clone(), self.opt.state[p]["exp_avg_sq"].clone()) for p in params]
+        step0 = self.opt._g_step.clone()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup):
+                self._forward_backward()
+                mdist.allreduce_grads(self.groups)
+                self._update()
+                self._mark_packed_fresh()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.loss = self._forward_backward()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self._update()
+        with torch.no_grad():       # capture executes nothing; undo the warm-up steps
+            for p, (w, m, v) in zip(params, snap):
+                p.copy_(w)
+                self.opt.state[p]["exp_avg"].copy_(m)
+                self.opt.state[p]["exp_avg_sq"].copy_(v)
+            self.opt._g_step.copy_(step0)
+            for net in self.nets:
+                net._packed = ops.mlp_pack(net._ordered_params(), out=net._packed)
+        self._mark_packed_fresh()
+        return self
+
+    def __call__(self, rays=None, target=None):
+        """One optimisation step; rays [2,N,3] / target may be host (pinned) or device tensors, or None to reuse the buffers.
+        Returns the loss of this step as a 0-dim device tensor (valid until the next call)."""
+        if rays is not None:
+            self.rays.copy_(rays, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        if self.graph_a is None:
+            self.capture()
+        self.opt.graph_set_lr()
+        self.graph_a.replay()
+        mdist.allreduce_grads(self.groups)
+        self.graph_b.replay()
+        self.opt._g_dirty = True        # python-side step counts are refreshed lazily (FusedAdam.sync_graph_steps)
+        return self.loss

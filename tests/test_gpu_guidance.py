@@ -153,3 +153,80 @@ def test_guidance_views_with_normal_maps(nerf):
     K = [[focal, 0., W / 2], [0., focal, H / 2], [0., 0., 1.]]
     assert torch.equal(out["normal"][2:3], (depth2normal(want[3].contiguous(), K, 31) + 1) / 2)
     assert torch.isfinite(out["normal"]).all()
+
+
+def fresh_nerf(run):
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "exp"))
+        kw_train, kw_test, start, grad_vars, opt = run.create_nerf(nerf_args(td))
+    load_seeded(kw_train["network_fn"], 200)
+    load_seeded(kw_train["network_fine"], 201)
+    return kw_train, kw_test, grad_vars, opt
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (two CUDA graphs per step) == the eager step: with the deterministic kwargs (no random draws) the
+    parameters after 4 steps with a decaying learning rate agree to fp32 round-off, capture itself trains nothing, and the
+    optimizer state / step counts interchange with the eager path."""
+    from mvip_nerf_b200 import run
+    from mvip_nerf_b200.graph import GraphedTrainStep, default_loss
+    g = torch.Generator().manual_seed(3)
+    N = 512
+    ro = torch.zeros(N, 3)
+    rd = torch.nn.functional.normalize(torch.randn(N, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.]), dim=-1)
+    rays = torch.stack([ro, rd], 0).cuda()
+    tgt = torch.rand(N, 3, generator=g).cuda()
+    lrs = [5e-4, 4e-4, 3e-4, 2e-4]
+
+    kw_a, _, gv_a, opt_a = fresh_nerf(run)
+    kw_a = dict(kw_a, perturb=0., raw_noise_std=0.)
+    losses_a = []
+    for lr in lrs:
+        opt_a.param_groups[0]["lr"] = lr
+        opt_a.zero_grad(set_to_none=True)
+        out = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=1.2, far=7.7, **kw_a)
+        loss = default_loss(*out, tgt, 1.0)
+        loss.backward()
+        opt_a.step()
+        losses_a.append(float(loss.detach()))
+
+    kw_b, _, gv_b, opt_b = fresh_nerf(run)
+    kw_b = dict(kw_b, perturb=0., raw_noise_std=0.)
+    before = [p.detach().clone() for p in gv_b]
+    step = GraphedTrainStep(kw_b, opt_b, 756, 1008, 767.2935, N, 1.2, 7.7)
+    step.rays.copy_(rays)
+    step.target.copy_(tgt)
+    step.capture()
+    assert all(torch.equal(a, b) for a, b in zip(before, gv_b))            # capture trains nothing
+    losses_b = []
+    for lr in lrs:
+        opt_b.param_groups[0]["lr"] = lr
+        losses_b.append(float(step(rays, tgt)))
+    np.testing.assert_allclose(losses_b, losses_a, rtol=1e-5)
+    for a, b in zip(gv_a, gv_b):
+        assert float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(a.abs().max())
+    sd = opt_b.state_dict()
+    assert float(sd["state"][0]["step"]) == 4.0
+    # and back to the eager path: the fifth step continues from the graphed four
+    opt_b.zero_grad(set_to_none=True)
+    out = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=1.2, far=7.7, **kw_b)
+    default_loss(*out, tgt, 1.0).backward()
+    opt_b.step()
+    assert float(opt_b.state_dict()["state"][0]["step"]) == 5.0
+
+
+def test_graphed_train_step_random_draws_and_learning():
+    """train kwargs (perturb = 1, raw_noise_std = 1): every replay draws fresh randoms (losses differ step to step on fixed
+    rays) and the loss goes down."""
+    from mvip_nerf_b200 import run
+    from mvip_nerf_b200.graph import GraphedTrainStep
+    g = torch.Generator().manual_seed(4)
+    N = 1024
+    rd = torch.nn.functional.normalize(torch.randn(N, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.]), dim=-1)
+    rays = torch.stack([torch.zeros(N, 3), rd], 0).pin_memory()
+    tgt = torch.full((N, 3), 0.2).pin_memory()
+    kw, _, gv, opt = fresh_nerf(run)
+    step = GraphedTrainStep(kw, opt, 756, 1008, 767.2935, N, 1.2, 7.7)
+    losses = [float(step(rays, tgt)) for _ in range(30)]
+    assert len(set(losses[:5])) == 5
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5])
