@@ -435,11 +435,11 @@ sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ we
     float s1 = invert_cdf64(cdf, bins, u2.y, &i1);
     if (samples_g) reinterpret_cast<float2*>(samples_g + ray * 64)[lane] = make_float2(s0, s1);
     if (inds_g) reinterpret_cast<longlong2*>(inds_g + ray * 64)[lane] = make_longlong2((long long)i0, (long long)i1);
-    if (std_g) {  // torch.std(unbiased=False), run.py:1836 (tolerance-checked, not bit-exact)
-      const double mean = warp_sum((double)s0 + (double)s1) * (1.0 / 64.0);
-      const double e0 = (double)s0 - mean, e1 = (double)s1 - mean;
-      const double sq = warp_sum(e0 * e0 + e1 * e1);
-      if (lane == 0) std_g[ray] = (float)sqrt(sq * (1.0 / 64.0));
+    if (std_g) {  // torch.std(unbiased=False), run.py:1836: fp32 two-pass like the reference's (tolerance-checked, not bit-exact)
+      const float mean = warp_sum(s0 + s1) * (1.0f / 64.0f);
+      const float e0 = s0 - mean, e1 = s1 - mean;
+      const float sq = warp_sum(e0 * e0 + e1 * e1);
+      if (lane == 0) std_g[ray] = sqrtf(sq * (1.0f / 64.0f));
     }
     // ---- order the 64 samples (element e = 2 lane + r) if the draws were not sorted
     const float s_next = __shfl_down_sync(FULL_MASK, s0, 1);

@@ -14,7 +14,7 @@ open(os.path.join(P, tag + "_launches.csv"), "w").writelines(lines)
 r = csv.reader(lines); hdr = next(r)
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 seq = [(short(row[ki]), float(row[vi].replace(",", "")) / 1000.0) for row in r]
-idx = [i for i, (k, _) in enumerate(seq) if k.startswith("sample_coarse_kernel")]
+idx = [i for i, (k, _) in enumerate(seq) if k.startswith("sample_coarse")]
 step = seq[idx[-2]:idx[-1]]
 agg = collections.OrderedDict()
 for k, v in step:
@@ -22,7 +22,7 @@ for k, v in step:
     agg.setdefault(k, [0, 0.0]); agg[k][0] += 1; agg[k][1] += v
 tot = sum(v for _, v in agg.values())
 with open(os.path.join(P, tag + "_launches_summary.md"), "w") as f:
-    f.write("# %s - ncu launch list of `python bench.py --steps 2 --warmup 3` (first 400 launches), ONE training step\n\n" % tag)
+    f.write("# %s - ncu launch list of `python bench.py --steps 2 --warmup 3 --no-graph` (first 400 launches), ONE training step\n\n" % tag)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` on one B200 (scripts/profile.sh); times are cold-cache and "
             "serialised - compare SHARES.  The step shown is the last complete one in the capture (%d launches, %.1f us).\n\n" % (len(step), tot))
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
