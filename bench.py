@@ -227,6 +227,8 @@ def hbm_stage_times(ops, dev, hbm_peak):
 # our arm
 # =====================================================================================================
 def run_ours(a):
+    global N_RAND
+    N_RAND = int(a.rays_per_gpu)
     from mvip_nerf_b200 import dist as md
     from mvip_nerf_b200 import ops, run
     from mvip_nerf_b200.run_nerf_helpers import img2mse
@@ -412,7 +414,8 @@ def run_ours(a):
         e = per_kernel[top]
         if e.get("frac_of_hbm_peak", 0.0) >= e.get("frac_of_tensor_peak", 0.0):
             roofline = {"kernel": top, "bound": "hbm", "achieved": e["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": e["frac_of_hbm_peak"], "traffic": NCU_TRAFFIC.get(top),
+                        "frac": e["frac_of_hbm_peak"],
+                        "traffic": NCU_TRAFFIC[top] * N_RAND / 4096 if top in NCU_TRAFFIC else None,   # captured at 4096 rays
                         "algorithmic_bytes_per_launch": hbm_bytes[top][0] * npts / 2,
                         "peak_source": "%s hbm_gbs (STREAM-style copy; this kernel's traffic is %s-only, for which "
                                        "the same box measures ~3.9 TB/s write / ~5.9 TB/s read, scripts/hbm_write_bw.py)"
@@ -437,7 +440,7 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "cfg2: one training step, N_rand=%d rays per GPU (global %d), N_samples=64, N_importance=64, "
+        "config": {"workload": ("cfg4" if N_RAND * world == 65536 else "cfg2") + ": one training step, N_rand=%d rays per GPU (global %d), N_samples=64, N_importance=64, "
                                "coarse+fine 8x256 NeRF (random init), lindisp, white_bkgd, perturb=1, raw_noise_std=1, "
                                "loss=mse(rgb)+mse(rgb0), grad allreduce, fused Adam" % (N_RAND, N_RAND * world),
                    "parallelism": "rays sharded, dp%d" % world,
@@ -477,6 +480,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays-per-gpu", type=int, default=N_RAND,
+                    help="N_rand per GPU: 4096 = BASELINE cfg 2 (default, the configuration `metric` is quoted on); 8192 with "
+                         "--gpus 8 = cfg 4 (65,536 rays per step)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
