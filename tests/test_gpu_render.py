@@ -208,3 +208,65 @@ def test_training_reduces_loss(nerf):
         for p, s in zip(grad_vars, sd):
             p.copy_(s)
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_cfg1_real_view_vs_reference(golden):
+    """BASELINE cfg 1 (config_1.txt on data/1, factor 4, random-init network, render-only forward of one training view):
+    render(c2w=pose, patch=...) and render(rays=...) against the reference's own render() on CPU
+    (tests/golden/cfg1_view.npz, oracle/make_golden_cfg1.py)."""
+    from mvip_nerf_b200 import ops, run
+    fx = golden("cfg1_view")
+    H, W, focal, near, far = int(fx["H"]), int(fx["W"]), float(fx["focal"]), float(fx["near"]), float(fx["far"])
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "exp"))
+        kw_train, kw_test, _, _, _ = run.create_nerf(nerf_args(td))
+    load_seeded(kw_train["network_fn"], int(fx["coarse_seed"]))
+    load_seeded(kw_train["network_fine"], int(fx["fine_seed"]))
+    c2w = cu(fx["c2w"])
+    # the ray batch of the real pose is bit-exact
+    batch = ops.rays_from_pose(H, W, focal, c2w, near, far).cpu().numpy().reshape(H, W, 11)
+    assert np.array_equal(batch[::40, ::41, 3:6].reshape(-1, 3), fx["rays_d"])
+    assert np.array_equal(batch[::40, ::41, 0:3].reshape(-1, 3), fx["rays_o"])
+    # raw2outputs gives the last sample dist = 1e10, so its alpha jumps 0 -> 1 where the predicted density crosses zero: rays whose
+    # reference density at z = far is within 10x the bf16 error of the MLP (4e-4) of zero are ill-conditioned for any
+    # reduced-precision network and are left out (a handful; the fixture stores the reference's value)
+    ok_p = np.abs(fx["patch_sigma_far_fine"]) > 5e-3
+    ok_r = np.abs(fx["rays_sigma_far_fine"]) > 5e-3
+    assert ok_p.mean() > 0.95 and ok_r.mean() > 0.95
+    assert (np.abs(fx["patch_sigma_far_coarse"]) > 5e-3).all()
+    patch = tuple(int(v) for v in fx["patch"])
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = run.render(H, W, focal, chunk=32768, c2w=c2w, patch=patch, near=near, far=far, **kw_test)
+    np.testing.assert_allclose(extras["rgb0"].cpu().numpy(), fx["patch_rgb0"], atol=RGB_ATOL)
+    np.testing.assert_allclose(rgb.cpu().numpy()[ok_p], fx["patch_rgb"][ok_p], atol=RGB_ATOL)
+    np.testing.assert_allclose(acc.cpu().numpy()[ok_p], fx["patch_acc"][ok_p], atol=ACC_ATOL)
+    np.testing.assert_allclose(disp.cpu().numpy()[ok_p], fx["patch_disp"][ok_p], atol=DISP_ATOL)
+    np.testing.assert_allclose(depth.cpu().numpy()[ok_p], fx["patch_depth"][ok_p], rtol=DEPTH_RTOL)
+    with torch.no_grad():
+        rgb, disp, acc, depth, _ = run.render(H, W, focal, chunk=32768, rays=torch.stack([cu(fx["rays_o"]), cu(fx["rays_d"])], 0),
+                                              near=near, far=far, **kw_test)
+    np.testing.assert_allclose(rgb.cpu().numpy()[ok_r], fx["rays_rgb"][ok_r], atol=RGB_ATOL)
+    np.testing.assert_allclose(depth.cpu().numpy()[ok_r], fx["rays_depth"][ok_r], rtol=DEPTH_RTOL)
+    np.testing.assert_allclose(disp.cpu().numpy()[ok_r], fx["rays_disp"][ok_r], atol=DISP_ATOL)
+
+
+def test_full_image_render_is_chunk_and_shard_invariant(nerf):
+    """BASELINE cfg 3 at full size (1008 x 756 = 762,048 rays): the image does not depend on the chunking (run.py:1153) nor on
+    how the rays are split into shards (what dist.render_sharded does across GPUs); outputs finite, acc in [0, 1]."""
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    from mvip_nerf_b200 import ops
+    H, W, focal = 756, 1008, 767.2935
+    c2w = torch.eye(4, device="cuda")[:3, :4]
+    with torch.no_grad():
+        a = run.render(H, W, focal, chunk=1 << 17, c2w=c2w, near=1.2, far=7.7369, **kw_test)
+        b = run.render(H, W, focal, chunk=100000, c2w=c2w, near=1.2, far=7.7369, **kw_test)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert torch.isfinite(a[0]).all() and float(a[2].min()) >= 0 and float(a[2].max()) <= 1 + 1e-5
+    # three uneven shards of the flattened ray list == the whole image
+    rays = ops.rays_from_pose(H, W, focal, c2w, 1.2, 7.7369)
+    kw = {k: v for k, v in kw_test.items() if k not in ("ndc", "use_viewdirs")}
+    cuts = [0, 250001, 500003, H * W]
+    with torch.no_grad():
+        parts = [run.batchify_rays(rays[lo:hi], 1 << 17, **kw)["rgb_map"] for lo, hi in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(torch.cat(parts, 0).view(H, W, 3), a[0])

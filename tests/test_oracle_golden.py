@@ -210,3 +210,21 @@ def test_ray_batch_bit_exact(golden, name):
         got = orc.make_ray_batch(g[name + "_rays_o"], g[name + "_rays_d"], c["near"], c["far"], c["use_viewdirs"], None, c["ndc"],
                                  c["H"], c["W"], c["focal"])
         assert np.array_equal(got, g[name + "_rays_batch"])
+
+
+def test_cfg1_real_view_oracle(golden):
+    """BASELINE cfg 1: a training view of data/1 (pose pipeline of load_llff.py replayed by the reference's own functions,
+    oracle/make_golden_cfg1.py), render kwargs: oracle vs the reference's render() on a 16 x 24 patch and on strided rays."""
+    fx = golden("cfg1_view")
+    H, W, focal, near, far = int(fx["H"]), int(fx["W"]), float(fx["focal"]), float(fx["near"]), float(fx["far"])
+    pc, pf = orc.init_params(int(fx["coarse_seed"])), orc.init_params(int(fx["fine_seed"]))
+    t_vals = orc.linspace_f32(0, 1, 64)
+    ro, rd = orc.get_rays(H, W, focal, fx["c2w"])
+    assert np.array_equal(rd[::40, ::41].reshape(-1, 3), fx["rays_d"])            # get_rays on the real pose: bit-exact
+    i0, j0, h, w = [int(v) for v in fx["patch"]]
+    rays = orc.make_ray_batch(ro[i0:i0 + h, j0:j0 + w], rd[i0:i0 + h, j0:j0 + w], near, far)
+    out = orc.render_rays(rays, pc, pf, t_vals, lindisp=True, white_bkgd=True)
+    np.testing.assert_allclose(out["rgb0"].reshape(h, w, 3), fx["patch_rgb0"], atol=2e-5)
+    np.testing.assert_allclose(out["rgb_map"].reshape(h, w, 3), fx["patch_rgb"], atol=5e-5)
+    np.testing.assert_allclose(out["depth_map"].reshape(h, w), fx["patch_depth"], rtol=2e-4)
+    np.testing.assert_allclose(out["acc_map"].reshape(h, w), fx["patch_acc"], atol=2e-5)
