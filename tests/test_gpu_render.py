@@ -270,3 +270,32 @@ def test_full_image_render_is_chunk_and_shard_invariant(nerf):
     with torch.no_grad():
         parts = [run.batchify_rays(rays[lo:hi], 1 << 17, **kw)["rgb_map"] for lo, hi in zip(cuts[:-1], cuts[1:])]
     assert torch.equal(torch.cat(parts, 0).view(H, W, 3), a[0])
+
+
+def test_ndc_configuration_vs_reference(golden):
+    """The reference's forward-facing configuration (no_ndc unset: ndc_rays, near 0 / far 1, linear-in-depth sampling, black
+    background) end to end against the reference's render() on CPU (tests/golden/render_ndc.npz, oracle/make_golden_ndc.py).
+    Rays whose reference density at the last sample (dist = 1e10) is within 5e-3 of zero are ill-conditioned (see the cfg-1
+    test) and left out per network."""
+    from mvip_nerf_b200 import run
+    fx = golden("render_ndc")
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "exp"))
+        kw_train, kw_test, _, _, _ = run.create_nerf(nerf_args(td, no_ndc=False, white_bkgd=False, lindisp=False))
+    assert kw_test["ndc"] is True and "lindisp" not in kw_test
+    load_seeded(kw_train["network_fn"], int(fx["coarse_seed"]))
+    load_seeded(kw_train["network_fine"], int(fx["fine_seed"]))
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = run.render(int(fx["H"]), int(fx["W"]), float(fx["focal"]), chunk=4096, c2w=cu(fx["c2w"]),
+                                                   **kw_test)
+    ok = np.abs(fx["sigma_far_fine"]) > 5e-3
+    ok0 = np.abs(fx["sigma_far_coarse"]) > 5e-3
+    assert ok.mean() > 0.95 and ok0.mean() > 0.5
+    np.testing.assert_allclose(rgb.cpu().numpy()[ok], fx["rgb"][ok], atol=RGB_ATOL)
+    np.testing.assert_allclose(acc.cpu().numpy()[ok], fx["acc"][ok], atol=ACC_ATOL)
+    np.testing.assert_allclose(depth.cpu().numpy()[ok], fx["depth"][ok], rtol=DEPTH_RTOL, atol=1e-3)
+    np.testing.assert_allclose(extras["rgb0"].cpu().numpy()[ok0], fx["rgb0"][ok0], atol=RGB_ATOL)
+    np.testing.assert_allclose(extras["acc0"].cpu().numpy()[ok0], fx["acc0"][ok0], atol=ACC_ATOL)
+    z = extras["z_vals"].cpu().numpy()
+    assert z.min() >= 0 and z.max() <= 1 and np.all(np.diff(z, axis=-1) >= 0)
+    assert np.array_equal(z[..., 0], fx["z_vals"][..., 0]) and np.array_equal(z[..., -1], fx["z_vals"][..., -1])

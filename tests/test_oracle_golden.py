@@ -228,3 +228,19 @@ def test_cfg1_real_view_oracle(golden):
     np.testing.assert_allclose(out["rgb_map"].reshape(h, w, 3), fx["patch_rgb"], atol=5e-5)
     np.testing.assert_allclose(out["depth_map"].reshape(h, w), fx["patch_depth"], rtol=2e-4)
     np.testing.assert_allclose(out["acc_map"].reshape(h, w), fx["patch_acc"], atol=2e-5)
+
+
+def test_ndc_configuration_oracle(golden):
+    """forward-facing configuration (ndc_rays, near 0 / far 1, linear sampling, black background): oracle vs the reference's render()"""
+    fx = golden("render_ndc")
+    H, W, focal = int(fx["H"]), int(fx["W"]), float(fx["focal"])
+    pc, pf = orc.init_params(int(fx["coarse_seed"])), orc.init_params(int(fx["fine_seed"]))
+    ro, rd = orc.get_rays(H, W, focal, fx["c2w"])
+    rays = orc.make_ray_batch(ro, rd, 0., 1., True, None, True, H, W, focal)
+    out = orc.render_rays(rays, pc, pf, orc.linspace_f32(0, 1, 64), lindisp=False, white_bkgd=False)
+    ok = (np.abs(fx["sigma_far_fine"]) > 1e-4).reshape(-1)
+    ok0 = (np.abs(fx["sigma_far_coarse"]) > 1e-4).reshape(-1)
+    np.testing.assert_allclose(out["rgb_map"][ok], fx["rgb"].reshape(-1, 3)[ok], atol=5e-5)
+    np.testing.assert_allclose(out["acc_map"][ok], fx["acc"].reshape(-1)[ok], atol=2e-5)
+    np.testing.assert_allclose(out["rgb0"][ok0], fx["rgb0"].reshape(-1, 3)[ok0], atol=5e-5)
+    np.testing.assert_allclose(out["depth_map"][ok], fx["depth"].reshape(-1)[ok], rtol=2e-4, atol=1e-5)
