@@ -372,6 +372,17 @@ def run_ours(a):
     ms_guid = timed(guidance, g_steps) / g_steps
     guid_value = GV * GH * GW / (ms_guid * 1e-3)
 
+    # ---- secondary: one guidance view WITH gradients at full resolution (deferred back-propagation) --------
+    # every rank renders its own 512 x 512 view (render kwargs), image loss on rgb + depth, backward through render_deferred
+    def guidance_train():
+        optimizer.zero_grad(set_to_none=True)
+        rgb, disp, acc, depth, _ = run.render_deferred(GH, GW, gfocal, chunk=8192, c2w=gposes[rank % GV], near=NEAR, far=FAR, **kw_test)
+        loss = ((rgb - 0.5) ** 2).mean() + 0.1 * depth.mean()
+        loss.backward()
+    guidance_train()
+    ms_gtrain = timed(guidance_train, 1)
+    gtrain_value = world * GH * GW / (ms_gtrain * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -462,6 +473,9 @@ def run_ours(a):
         "guidance": {"value": guid_value, "unit": "rays/s", "ms_per_batch": ms_guid,
                      "workload": "cfg5: %d views of %dx%d (rgb + disp + acc + depth), image rows sharded over %d GPU(s), one gather, "
                                  "normal maps (k=31) of all views on rank 0" % (GV, GH, GW, world)},
+        "guidance_train": {"value": gtrain_value, "unit": "rays/s", "ms_per_view": ms_gtrain,
+                           "workload": "one 512x512 view per GPU, forward + image loss + deferred back-propagation "
+                                       "(re-render in 8192-ray chunks), parameter gradients of both networks"},
         "hbm_stages": hbm_stages,
         "train_tflops": world * N_RAND * 192 * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) / (ms_step * 1e-3) / 1e12,
     }

@@ -103,6 +103,8 @@ class GraphedTrainStep:
             for net in self.nets:
                 net._packed = ops.mlp_pack(net._ordered_params(), out=net._packed)
         self._mark_packed_fresh()
+        self._params = params
+        self._static_grads = [p.grad for p in params]      # the buffers graph A writes and graph B / the allreduce read
         return self
 
     def __call__(self, rays=None, target=None):
@@ -114,6 +116,9 @@ class GraphedTrainStep:
             self.target.copy_(target, non_blocking=True)
         if self.graph_a is None:
             self.capture()
+        for p, g in zip(self._params, self._static_grads):   # an eager backward in between may have re-pointed .grad
+            if p.grad is not g:
+                p.grad = g
         self.opt.graph_set_lr()
         self.graph_a.replay()
         mdist.allreduce_grads(self.groups)

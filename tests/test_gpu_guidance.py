@@ -207,6 +207,7 @@ def test_graphed_train_step_matches_eager():
         assert float((a - b).abs().max()) <= 1e-6 + 1e-4 * float(a.abs().max())
     sd = opt_b.state_dict()
     assert float(sd["state"][0]["step"]) == 4.0
+    assert all(p.grad is g for p, g in zip(step._params, step._static_grads))
     # and back to the eager path: the fifth step continues from the graphed four
     opt_b.zero_grad(set_to_none=True)
     out = run.render(756, 1008, 767.2935, chunk=32768, rays=rays, near=1.2, far=7.7, **kw_b)
