@@ -183,8 +183,10 @@ class NeRF(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-# Ray helpers (run_nerf_helpers.py:249-300) — elementwise torch glue; fusing them into the sampler is
-# SURVEY.md §8 row f1 ("next").
+# Ray helpers (run_nerf_helpers.py:249-300) under the reference's names, as torch ops on whatever device the pose is on
+# (callers such as the training loop's ray precomputation, run.py:620, :869, use them directly).  render() itself does not
+# call them: it gets the whole [N, 8|11] ray batch from ONE kernel (ops.rays_from_pose / ops.rays_pack, csrc/rays.cu),
+# bit-exact against these formulas evaluated by torch on the CPU.
 # ------------------------------------------------------------------------------------------------
 def get_rays(H, W, focal, c2w):
     dev = c2w.device if torch.is_tensor(c2w) else None
