@@ -316,7 +316,7 @@ composite_fwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
 }
 
 template <int G>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                       int d_stride, const float* __restrict__ noise, int64_t n_rays, int white, int detach_w,
                       const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,

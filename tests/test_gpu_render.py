@@ -299,3 +299,25 @@ def test_ndc_configuration_vs_reference(golden):
     z = extras["z_vals"].cpu().numpy()
     assert z.min() >= 0 and z.max() <= 1 and np.all(np.diff(z, axis=-1) >= 0)
     assert np.array_equal(z[..., 0], fx["z_vals"][..., 0]) and np.array_equal(z[..., -1], fx["z_vals"][..., -1])
+
+
+def test_render_other_sample_counts_vs_oracle(nerf):
+    """N_samples = 48, N_importance = 32 (none of the specialised 64 / 128 kernels applies: generic sampler, sample_fine and
+    compositing kernels end to end) against the fp32 oracle on well-conditioned rays."""
+    run, kw_train, kw_test, grad_vars, opt, fx = nerf
+    kw = dict(kw_test, N_samples=48, N_importance=32)
+    ro, rd = cu(fx["rays_o"]), cu(fx["rays_d"])
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = run.render(756, 1008, 767.2935, chunk=32768, rays=torch.stack([ro, rd], 0),
+                                                   near=float(fx["near"]), far=float(fx["far"]), retraw=True, **kw)
+    assert extras["z_vals"].shape == (64, 80) and extras["raw"].shape == (64, 80, 4)
+    pc, pf = orc.init_params(int(fx["coarse_seed"])), orc.init_params(int(fx["fine_seed"]))
+    rays = orc.make_ray_batch(fx["rays_o"], fx["rays_d"], fx["near"], fx["far"])
+    want = orc.render_rays(rays, pc, pf, orc.linspace_f32(0, 1, 48), lindisp=True, white_bkgd=True, N_importance=32)
+    ok = (np.abs(want["raw"][:, -1, 3]) > 5e-3) & (np.abs(want["raw0"][:, -1, 3]) > 5e-3)
+    assert ok.mean() > 0.8
+    np.testing.assert_allclose(rgb.cpu().numpy()[ok], want["rgb_map"][ok], atol=RGB_ATOL)
+    np.testing.assert_allclose(extras["rgb0"].cpu().numpy()[ok], want["rgb0"][ok], atol=RGB_ATOL)
+    np.testing.assert_allclose(depth.cpu().numpy()[ok], want["depth_map"][ok], rtol=DEPTH_RTOL, atol=1e-3)
+    z = extras["z_vals"].cpu().numpy()
+    assert np.all(np.diff(z, axis=-1) >= 0) and np.array_equal(z[:, 0], want["z_vals"][:, 0])
