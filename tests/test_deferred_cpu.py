@@ -79,3 +79,36 @@ def test_png_writer_roundtrip(tmp_path):
     assert b[37:41] == b"IDAT"
     rows = np.frombuffer(zlib.decompress(b[41:41 + n]), np.uint8).reshape(9, 1 + 13 * 3)
     assert np.array_equal(rows[:, 1:].reshape(9, 13, 3), img) and not rows[:, 0].any()
+
+
+def test_view_loop_host_helpers():
+    """hwf scaling / intrinsics (run.py:1225-1236), pose convention flip (run.py:1435-1440), learning-rate decay (run.py:1031-1039)"""
+    import argparse
+    H, W, focal, K = run._scaled_hwf([567, 1008, 767.2935], 4)
+    assert (H, W) == (141, 252) and abs(focal - 767.2935 / 4) < 1e-12
+    assert np.allclose(K, [[focal, 0, 126.0], [0, focal, 70.5], [0, 0, 1]])
+    assert run._scaled_hwf([567, 1008, 767.2935], 0)[:3] == (567, 1008, 767.2935)
+    c = run.convert_pose(np.arange(16, dtype=np.float64).reshape(4, 4))
+    assert np.array_equal(c[:, 0], [0, 4, 8, 12]) and np.array_equal(c[:, 1], [-1, -5, -9, -13]) and np.array_equal(c[:, 2], [-2, -6, -10, -14])
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=5e-4)
+    lr = run.update_learning_rate(opt, argparse.Namespace(lrate=5e-4, lrate_decay=250), 250000)
+    assert abs(lr - 5e-5) < 1e-15 and opt.param_groups[0]["lr"] == lr
+
+
+def test_render_path_4view_pose_selection(monkeypatch):
+    """every second pose of the +-4 neighbourhood of pose iter % 60 (run.py:1388-1392), rendered through render()"""
+    seen = []
+
+    def fake_render(H, W, focal, chunk=0, c2w=None, **kw):
+        seen.append(float(c2w[0, 3]))
+        z = torch.zeros(H, W)
+        return [torch.zeros(H, W, 3), z, z, z, {}]
+    monkeypatch.setattr(run, "render", fake_render)
+    poses = torch.zeros(70, 3, 4)
+    poses[:, 0, 3] = torch.arange(70, dtype=torch.float32)
+    masks = np.arange(70)
+    rgbs, disps, sel = run.render_path_4view(62, masks, poses, [8, 12, 10.0], 64, {}, render_factor=2)
+    assert seen == [0.0, 2.0, 4.0, 6.0] and list(sel) == [0, 2, 4, 6] and rgbs.shape == (4, 4, 6, 3)     # iter = 2
+    seen.clear()
+    run.render_path_4view(127, masks, poses, [8, 12, 10.0], 64, {})
+    assert seen == [3.0, 5.0, 7.0, 9.0, 11.0]                                                          # iter = 7
