@@ -139,6 +139,102 @@ def _gather_uneven(local, sizes, dst=0):
     return torch.cat([out[r * max_rows:r * max_rows + sizes[r]] for r in range(w)], 0)
 
 
+def _scatter_uneven(full, sizes, like, src=0):
+    """inverse of _gather_uneven: rank src holds `full` [sum(sizes), ...]; every rank gets its rows (one padded scatter)."""
+    if world() == 1:
+        return full
+    w = world()
+    max_rows = max(sizes)
+    out = like.new_empty((max_rows,) + tuple(like.shape[1:]))
+    chunks = None
+    if rank() == src:
+        chunks, off = [], 0
+        for n in sizes:
+            c = like.new_zeros((max_rows,) + tuple(like.shape[1:]))
+            c[:n] = full[off:off + n]
+            chunks.append(c)
+            off += n
+    dist.scatter(out, chunks, src=src)
+    return out[:sizes[rank()]]
+
+
+class ShardedGuidanceViews:
+    """Guidance views WITH gradients across the GPUs of one box (BASELINE cfg 5 in its training role: the collaborative /
+    normal-map branches of train(), DS_NeRF/run.py:948-984, render their views with autograd on).
+
+        g = ShardedGuidanceViews(render_kwargs, poses, H, W, focal, near, far)
+        out = g.forward()            # all ranks; rank 0 gets {'rgb_map' [V,H,W,3], 'disp_map', 'acc_map', 'depth_map'} as
+                                     # gradient-carrying leaves (+ 'normal' [V,3,H,W] built from depth_map with autograd), others None
+        loss(out).backward()         # rank 0 only: stock-PyTorch guidance loss (SDS, ...) on the gathered images
+        g.backward()                 # all ranks: image gradients scattered back (24 B/ray), every rank back-propagates ITS rows
+                                     # with deferred re-rendering (run._DeferredRays), then one gradient allreduce per network
+
+    Communication: one gather (24 B/ray), one scatter (24 B/ray), one 4.77 MB allreduce.  Every rank ends with the full
+    parameter gradient in .grad, exactly as after dist.allreduce_grads in the ray-batch step."""
+
+    def __init__(self, render_kwargs, poses, H, W, focal, near, far, chunk=8192, with_normals=True, normal_k=31):
+        from . import run as mrun
+        self.run = mrun
+        self.kw = dict(render_kwargs)
+        self.poses, self.H, self.W, self.focal, self.near, self.far = poses, int(H), int(W), focal, near, far
+        self.chunk, self.with_normals, self.normal_k = int(chunk), with_normals, normal_k
+        self.nets = mrun._net_params(self.kw)
+        self.outs = self.leaf = None
+
+    def _sizes(self):
+        V = len(self.poses)
+        return [(b[1] - b[0]) * self.W for b in (shard_bounds(V * self.H, r, world()) for r in range(world()))]
+
+    def forward(self):
+        from . import ops
+        from .run_nerf_helpers import depth2normal
+        V, H, W = len(self.poses), self.H, self.W
+        use_viewdirs = self.kw.get("use_viewdirs", False)
+        ndc = self.kw.get("ndc", True)
+        pieces = [ops.rays_from_pose(H, W, self.focal, self.poses[v][:3, :4], self.near, self.far, use_viewdirs=use_viewdirs,
+                                     patch=(i0, 0, n, W), ndc=ndc) for v, i0, n in view_row_bands(V, H)]
+        kw = {k: v for k, v in self.kw.items() if k not in ("ndc", "use_viewdirs", "near", "far")}
+        params = [p for _, ps in self.nets for p in ps]
+        if pieces:
+            rays = torch.cat(pieces, 0) if len(pieces) > 1 else pieces[0]
+            holder = {}
+            outs = self.run._DeferredRays.apply(rays, self.chunk, kw, holder, *params)
+            ret = dict(zip(holder["keys"], outs))
+            self.outs = [ret["rgb_map"], ret["disp_map"], ret["acc_map"], ret["depth_map"]]
+            packed = torch.cat([self.outs[0].detach(), self.outs[1].detach()[:, None], self.outs[2].detach()[:, None],
+                                self.outs[3].detach()[:, None]], -1)
+        else:       # more ranks than image rows
+            self.outs = None
+            packed = params[0].new_empty((0, 6))
+        full = _gather_uneven(packed.contiguous(), self._sizes())
+        if full is None:
+            return None
+        self.leaf = full.detach().requires_grad_(True)
+        img = self.leaf.view(V, H, W, 6)
+        out = {"rgb_map": img[..., 0:3], "disp_map": img[..., 3], "acc_map": img[..., 4], "depth_map": img[..., 5]}
+        if self.with_normals:
+            K = [[self.focal, 0., W / 2], [0., self.focal, H / 2], [0., 0., 1.]]
+            out["normal"] = torch.cat([(depth2normal(out["depth_map"][v].contiguous(), K, self.normal_k) + 1) / 2 for v in range(V)], 0)
+        return out
+
+    def backward(self):
+        sizes = self._sizes()
+        like = self.outs[0].new_empty((0, 6)) if self.outs is not None else self.nets[0][1][0].new_empty((0, 6))
+        g_full = None
+        if rank() == 0:
+            g_full = self.leaf.grad if self.leaf.grad is not None else torch.zeros_like(self.leaf)
+        g = _scatter_uneven(g_full, sizes, like)
+        if self.outs is not None and g.shape[0] > 0:
+            torch.autograd.backward(self.outs, [g[:, 0:3].contiguous(), g[:, 3].contiguous(), g[:, 4].contiguous(),
+                                                g[:, 5].contiguous()])
+        for _, ps in self.nets:        # ranks whose rows carried no gradient still take part in the collective
+            for p in ps:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+        allreduce_grads([ps for _, ps in reversed(self.nets)])
+        self.outs = self.leaf = None
+
+
 def _flat_view(grads):
     """If the gradient tensors are consecutive views of ONE contiguous buffer (what ops.mlp_backward returns: 24 views of
     one flat fp32 tensor per network), returns that buffer as a 1-D tensor sharing their memory; otherwise None."""

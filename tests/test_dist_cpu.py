@@ -85,6 +85,71 @@ def _worker(rank, world, port, n):
     dist.destroy_process_group()
 
 
+class _Field(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(11, 12)
+        self.b = torch.nn.Linear(12, 6)
+
+    def _ordered_params(self):
+        return list(self.parameters())
+
+
+def _fake_rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=True, c2w_staticcam=None, patch=None, device=None, ndc=False,
+                         ndc_near=1.):
+    i0, j0, h, w = patch
+    ii, jj = torch.meshgrid(torch.arange(i0, i0 + h, dtype=torch.float32), torch.arange(j0, j0 + w, dtype=torch.float32), indexing="ij")
+    cols = [c2w[0, 3] + 0 * ii, ii / H, jj / W, torch.sin(ii + c2w[0, 3]), torch.cos(jj), ii * 0 + focal / 100, ii * 0 + near, ii * 0 + far,
+            ii * jj / (H * W), ii * 0 + 1, jj * 0 - 1]
+    return torch.stack(cols, -1).reshape(-1, 11)
+
+
+def _fake_render_rays(ray_batch, network_fn=None, **kw):
+    o = network_fn.b(torch.tanh(network_fn.a(ray_batch)))
+    return {"rgb_map": torch.sigmoid(o[:, :3]), "disp_map": o[:, 3], "acc_map": torch.sigmoid(o[:, 4]), "depth_map": o[:, 5] + 3.}
+
+
+def _image_loss(out):
+    V, H, W = out["disp_map"].shape
+    wgt = torch.linspace(0.5, 1.5, V * H * W).view(V, H, W)
+    return ((out["rgb_map"] - 0.3) ** 2 * wgt[..., None]).mean() + 0.2 * (out["depth_map"] * wgt).mean() + 0.1 * (out["disp_map"] ** 2).mean()
+
+
+def _guidance_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from mvip_nerf_b200 import dist as md
+    from mvip_nerf_b200 import ops, run
+    md.init_from_env(backend="gloo")
+    ops.rays_from_pose = _fake_rays_from_pose
+    run.render_rays = _fake_render_rays
+    torch.manual_seed(0)
+    net = _Field()
+    V, H, W = 3, 7, 5                       # 21 rows over 2 ranks: 11 + 10, rank 0's range straddles views 0 and 1
+    poses = [torch.eye(4)[:3, :4] * 1.0 + v for v in range(V)]
+    kw = {"network_fn": net, "use_viewdirs": True, "ndc": False}
+    g = md.ShardedGuidanceViews(kw, poses, H, W, 50., 1., 6., chunk=16, with_normals=False)
+    out = g.forward()
+    if rank == 0:
+        assert out["rgb_map"].shape == (V, H, W, 3)
+        _image_loss(out).backward()
+    else:
+        assert out is None
+    g.backward()
+    # single-process reference: all rows at once, plain autograd
+    rays = torch.cat([_fake_rays_from_pose(H, W, 50., poses[v], 1., 6., patch=(0, 0, H, W)) for v in range(V)], 0)
+    ret = _fake_render_rays(rays, network_fn=net)
+    full = {k: v.view(V, H, W, *v.shape[1:]) for k, v in ret.items()}
+    want = torch.autograd.grad(_image_loss(full), list(net.parameters()))
+    for p, gw in zip(net.parameters(), want):
+        torch.testing.assert_close(p.grad, gw, rtol=1e-5, atol=1e-7)          # every rank holds the FULL gradient
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_guidance_views_with_gradients():
+    mp.spawn(_guidance_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("n", [10, 7])
 def test_world2_gloo_shard_gather_allreduce(n):
     mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)

@@ -231,3 +231,42 @@ def test_graphed_train_step_random_draws_and_learning():
     losses = [float(step(rays, tgt)) for _ in range(30)]
     assert len(set(losses[:5])) == 5
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5])
+
+
+def guidance_loss(out):
+    V, H, W = out["disp_map"].shape
+    wgt = torch.linspace(0.5, 1.5, V * H * W, device=out["disp_map"].device).view(V, H, W)
+    loss = ((out["rgb_map"] - 0.4) ** 2 * wgt[..., None]).mean() + 0.02 * (out["depth_map"] * wgt).mean()
+    if "normal" in out:
+        loss = loss + 0.05 * ((out["normal"] - 0.5) ** 2).mean()
+    return loss
+
+
+def test_sharded_guidance_views_gradients_match_direct(nerf):
+    """dist.ShardedGuidanceViews (gather -> loss on rank 0 -> scatter -> deferred backward -> allreduce), world size 1:
+    images, normal maps and parameter gradients equal the direct render() + depth2normal autograd graph."""
+    run, kw_train, kw_test, grad_vars, opt = nerf
+    from mvip_nerf_b200 import dist as md
+    from mvip_nerf_b200.run_nerf_helpers import depth2normal
+    poses = [pose(0.05 * i, 0.02 * i) for i in range(2)]
+    H, W, focal = 20, 28, 26.0
+    K = [[focal, 0., W / 2], [0., focal, H / 2], [0., 0., 1.]]
+    # direct
+    outs = [run.render(H, W, focal, chunk=4096, c2w=p, near=1.2, far=7.7, **kw_test) for p in poses]
+    direct = {"rgb_map": torch.stack([o[0] for o in outs]), "disp_map": torch.stack([o[1] for o in outs]),
+              "acc_map": torch.stack([o[2] for o in outs]), "depth_map": torch.stack([o[3] for o in outs])}
+    direct["normal"] = torch.cat([(depth2normal(direct["depth_map"][v].contiguous(), K, 31) + 1) / 2 for v in range(2)], 0)
+    gd = torch.autograd.grad(guidance_loss(direct), grad_vars, allow_unused=True)
+    # sharded (deferred)
+    for v in grad_vars:
+        v.grad = None
+    g = md.ShardedGuidanceViews(kw_test, poses, H, W, focal, 1.2, 7.7, chunk=256)
+    out = g.forward()
+    assert torch.equal(out["rgb_map"], direct["rgb_map"].detach()) and torch.equal(out["normal"], direct["normal"].detach())
+    guidance_loss(out).backward()
+    g.backward()
+    for p, a in zip(grad_vars, gd):
+        if a is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+        else:
+            assert float((p.grad - a).abs().max()) <= 2e-4 * float(a.abs().max()) + 1e-12
