@@ -101,6 +101,7 @@ def render_views_sharded(render_fn, poses, H, W, focal, near, far, normal_k=31, 
     (n + 1) / 2 as in run.py:965); None on the other ranks."""
     from .run_nerf_helpers import depth2normal
     V = len(poses)
+    kwargs = {k: v for k, v in kwargs.items() if k not in ("near", "far")}     # bounds merged into the kwargs (run.py:554-559)
     pieces = []
     for v, i0, n in view_row_bands(V, H):
         rgb, disp, acc, depth, _ = render_fn(H, W, focal, c2w=poses[v][:3, :4], patch=(i0, 0, n, W), near=near, far=far, **kwargs)

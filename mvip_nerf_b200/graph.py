@@ -30,11 +30,17 @@ def default_loss(rgb, disp, acc, depth, extras, target, scale):
 
 
 class GraphedTrainStep:
-    def __init__(self, render_kwargs_train, optimizer, H, W, focal, n_rays, near, far, chunk=1024 * 32, loss_fn=default_loss,
+    def __init__(self, render_kwargs_train, optimizer, H, W, focal, n_rays, near=None, far=None, chunk=1024 * 32, loss_fn=default_loss,
                  target_shape=None, warmup=3, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a CUDA device (no CPU fallback)")
         self.kw = dict(render_kwargs_train)
+        # train() merges the scene bounds into the kwargs (run.py:554-559): accept both forms
+        kw_near, kw_far = self.kw.pop("near", None), self.kw.pop("far", None)
+        near = kw_near if near is None else near
+        far = kw_far if far is None else far
+        if near is None or far is None:
+            raise ValueError("GraphedTrainStep: near / far must be given (as arguments or inside render_kwargs_train)")
         self.opt = optimizer
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.args = (H, W, focal)

@@ -227,7 +227,7 @@ def test_graphed_train_step_random_draws_and_learning():
     rays = torch.stack([torch.zeros(N, 3), rd], 0).pin_memory()
     tgt = torch.full((N, 3), 0.2).pin_memory()
     kw, _, gv, opt = fresh_nerf(run)
-    step = GraphedTrainStep(kw, opt, 756, 1008, 767.2935, N, 1.2, 7.7)
+    step = GraphedTrainStep(dict(kw, near=1.2, far=7.7), opt, 756, 1008, 767.2935, N)     # bounds merged as train() does
     losses = [float(step(rays, tgt)) for _ in range(30)]
     assert len(set(losses[:5])) == 5
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5])
