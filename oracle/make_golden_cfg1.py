@@ -12,7 +12,6 @@ training poses = poses[40:] (:427), hwf from the images_4 size 567 x 1008 and fo
 near = bds.min() * .9, far = bds.max() (run.py:417-418, no_ndc).  The view is rendered with render_kwargs_test on a
 16 x 24 patch and on a strided set of rays through the reference's render(); inputs + outputs are stored.
 """
-import argparse
 import importlib
 import os
 import sys
@@ -24,7 +23,6 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from oracle import ref_import  # noqa: E402
-from oracle import nerf_oracle as orc  # noqa: E402
 from oracle.make_golden import load_seeded, nerf_args  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
