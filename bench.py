@@ -37,11 +37,26 @@ FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 1186816, 1114112, 1185536       # per point, 
 # HBM bytes per point: stash 40 chunk images x 128 B + 288 B masks; dZ stash 38 x 128 B (+ masks read, + 16 B d_raw);
 # wgrad reads both sets of images; head grads read hidden (2) + h8 (4) images + d_raw
 HBM_FWD_TRAIN, HBM_DGRAD, HBM_WGRAD, HBM_HEADS = 40 * 128 + 288 + 16, 38 * 128 + 288 + 16, 78 * 128, 6 * 128 + 16
-# measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch, mean of the coarse (262,144 points) and the
-# fine (524,288 points) launch of one step, from the ncu --set full capture committed as profiles/r01_kernels_ncu.md
-NCU_TRAFFIC = {"wgrad_kernel": (2.713 + 0.009 + 5.430 + 0.040) / 2 * 1e9,
-               "mvip_mlp_forward": (0.018 + 1.389 + 0.033 + 2.834) / 2 * 1e9,
-               "dgrad_chain_kernel": (0.087 + 1.216 + 0.175 + 2.491) / 2 * 1e9}
+
+
+def ncu_traffic(kernel, n_rand):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture of one
+    cfg-2 step (profiles/ncu_traffic.json: written by scripts/summarize_profiles.py from the .ncu-rep; mean of the coarse
+    and the fine launch), scaled to this run's rays per GPU.  None when the capture has no such kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t["kernels"][kernel]
+        return e["dram_bytes_per_launch"] * n_rand / t["rays_per_gpu"], t["source"]
+    except Exception:
+        return None, None
+
+
+def workload_config(n_rand, world):
+    """The `config` object: identical for the product arm and the reference arm (the driver compares them)."""
+    return {"workload": ("cfg4" if n_rand * world == 65536 else "cfg2") +
+            ": one training step, N_rand=%d rays per GPU, N_samples=64, N_importance=64, coarse+fine 8x256 NeRF (random init), "
+            "lindisp, white_bkgd, perturb=1, raw_noise_std=1, loss=mse(rgb)+mse(rgb0), Adam" % n_rand,
+            "rays_per_gpu": n_rand, "n_gpus": world, "parallelism": "rays sharded, dp%d, grad allreduce" % world}
 
 
 def peaks():
@@ -133,47 +148,93 @@ class ClockSampler:
 
 
 # =====================================================================================================
-# reference arm: CPU port of the reference path on the host cores
+# reference arm: the UNMODIFIED reference (oracle/_ref or /root/reference) on the host cores; the CPU port only if the
+# reference tree is not present
 # =====================================================================================================
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_train_rays_per_s(n_rays, steps, warmup):
-    from oracle import nerf_oracle as orc
-    from oracle import torch_cpu_port as port
-    pc = port.params_from_numpy(orc.init_params(1), True)
-    pf = port.params_from_numpy(orc.init_params(2), True)
+    """-> (rays/s, s/step, kind, threads): `steps` timed training steps of n_rays rays each, fp32, all host threads."""
+    threads = host_threads()
+    torch.set_num_threads(threads)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core it may
+    from oracle import ref_import
     o, d, target = synth_rays_np(n_rays, 1)
-    rays = torch.from_numpy(orc.make_ray_batch(o, d, NEAR, FAR))
-    tv = torch.linspace(0., 1., 64)
-    g = torch.Generator().manual_seed(0)
-    args = (torch.rand(n_rays, 64, generator=g), torch.rand(n_rays, 64, generator=g),
-            torch.randn(n_rays, 64, generator=g), torch.randn(n_rays, 128, generator=g), torch.from_numpy(target))
-    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4)
+    if ref_import.available():
+        run, helpers = ref_import.load()    # stock create_nerf + render + backward + torch.optim.Adam (run.py:914-1029)
+        with tempfile.TemporaryDirectory() as td:
+            os.makedirs(os.path.join(td, "bench"))
+            torch.manual_seed(0)
+            kw_train, _, _, _, opt = run.create_nerf(nerf_args(td))
+        rays = torch.from_numpy(np.stack([o, d], 0))
+        tgt = torch.from_numpy(target)
+
+        def step():
+            rgb, _, _, _, extras = run.render(H, W, FOCAL, chunk=32768, rays=rays, near=NEAR, far=FAR, **kw_train)
+            opt.zero_grad()
+            loss = helpers.img2mse(rgb, tgt) + helpers.img2mse(extras["rgb0"], tgt)
+            loss.backward()
+            opt.step()
+        kind = "reference"
+    else:
+        from oracle import nerf_oracle as orc
+        from oracle import torch_cpu_port as port
+        pc = port.params_from_numpy(orc.init_params(1), True)
+        pf = port.params_from_numpy(orc.init_params(2), True)
+        rays = torch.from_numpy(orc.make_ray_batch(o, d, NEAR, FAR))
+        tv = torch.linspace(0., 1., 64)
+        g = torch.Generator().manual_seed(0)
+        args = (torch.rand(n_rays, 64, generator=g), torch.rand(n_rays, 64, generator=g),
+                torch.randn(n_rays, 64, generator=g), torch.randn(n_rays, 128, generator=g), torch.from_numpy(target))
+        opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4)
+
+        def step():
+            port.train_step(rays, pc, pf, tv, *args)
+            opt.step()
+        kind = "port"
     for _ in range(warmup):
-        port.train_step(rays, pc, pf, tv, *args); opt.step()
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        port.train_step(rays, pc, pf, tv, *args); opt.step()
+        step()
     dt = time.perf_counter() - t0
-    return n_rays * steps / dt, dt / steps
+    return n_rays * steps / dt, dt / steps, kind, threads
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 512
-    steps = max(1, min(a.steps, 6))
-    warm = max(1, min(a.warmup, 1))
-    val, sec = cpu_train_rays_per_s(sample, steps, warm)
-    cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": a.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "cfg2 train step (N_rand=4096/GPU), timed on a %d-ray sample per step" % sample},
-            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": "%d rays x %d steps, PyTorch-CPU port of the reference path (oracle/torch_cpu_port.py)"
-                                       % (sample, steps)},
+    sample = int(a.sample)
+    val, sec, kind, threads = cpu_train_rays_per_s(sample, a.steps, a.warmup)
+    what = ("the unmodified reference (DS_NeRF/run.py create_nerf + render + backward + torch.optim.Adam)" if kind == "reference"
+            else "PyTorch-CPU port of the reference path (oracle/torch_cpu_port.py)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(int(a.rays_per_gpu), a.gpus),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
+                             "sample": "%d of the %d rays per step x %d steps, %s, fp32, %d threads"
+                                       % (sample, int(a.rays_per_gpu), a.steps, what, threads)},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(sample, steps, warmup):
+    """The same CPU arm from inside the product run: a child process with the GPUs hidden (the reference picks
+    `cuda` when it sees one, run.py:46)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+                        "--sample", str(sample)], capture_output=True, text=True, timeout=900, env=env)
+    for ln in p.stdout.splitlines():
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"value": None, "unit": "rays/s", "cores": 0, "kind": "unavailable", "sample": (p.stderr or "")[-200:]}
 
 
 def hbm_stage_times(ops, dev, hbm_peak):
@@ -226,6 +287,16 @@ def hbm_stage_times(ops, dev, hbm_peak):
 # =====================================================================================================
 # our arm
 # =====================================================================================================
+# kernel label (ops.kernel_timer) -> (FLOP per point, algorithmic HBM bytes per point, direction)
+def kernel_table():
+    return {"mvip_mlp_forward": (FLOP_FWD, HBM_FWD_TRAIN, "write"),
+            "dgrad_pair_kernel": (FLOP_DGRAD, HBM_DGRAD, "write"),
+            "wgrad_kernel": (FLOP_WGRAD, HBM_WGRAD, "read"),
+            # fused backward: dZ is written once (and re-read out of L2 by the wgrad role), the forward stash is read once
+            "backward_fused_kernel": (FLOP_DGRAD + FLOP_WGRAD, HBM_DGRAD + 40 * 128, "read+write"),
+            "head_grads_kernel": (0, HBM_HEADS, "read")}
+
+
 def run_ours(a):
     global N_RAND
     N_RAND = int(a.rays_per_gpu)
@@ -245,20 +316,15 @@ def run_ours(a):
         kw_train, kw_test, _, grad_vars, optimizer = run.create_nerf(nerf_args(td))   # optimizer: FusedAdam (one launch)
     coarse, fine = kw_train["network_fn"], kw_train["network_fine"]
     groups = [list(fine.parameters()), list(coarse.parameters())]
-
-    o, d, target = synth_rays_np(N_RAND, 100 + rank)
-    pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
-    h_o, h_d, h_t = pin(o), pin(d), pin(target)
-    d_rays = torch.stack([h_o.to(dev), h_d.to(dev)], 0)
-    d_target = h_t.to(dev)
     inv_world = 1.0 / world
+    sync = md.GradSync(groups)         # per-network allreduce issued from autograd hooks: overlaps the rest of the backward
 
     def step(rays, tgt):
         optimizer.zero_grad(set_to_none=True)
         rgb, disp, acc, depth, extras = run.render(H, W, FOCAL, chunk=32768, rays=rays, near=NEAR, far=FAR, **kw_train)
         loss = (img2mse(rgb, tgt) + img2mse(extras["rgb0"], tgt)) * inv_world     # mean over the GLOBAL batch
         loss.backward()
-        md.allreduce_grads(groups)
+        sync.finish()
         optimizer.step()
         return loss
 
@@ -280,24 +346,43 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- the step as the product runs it: two CUDA graphs per step (graph.GraphedTrainStep); eager fallback if capture fails
-    h_rays = torch.stack([h_o, h_d], 0).pin_memory()
-    gstep, graph_note = None, "eager launches"
-    if not a.no_graph:
-        try:
-            from mvip_nerf_b200.graph import GraphedTrainStep
-            gstep = GraphedTrainStep(kw_train, optimizer, H, W, FOCAL, N_RAND, NEAR, FAR)
-            gstep.rays.copy_(d_rays)
-            gstep.target.copy_(d_target)
-            gstep.capture()
-            graph_note = "CUDA graphs: (render + loss + backward) | eager NCCL allreduce | (Adam + bf16 re-pack)"
-        except Exception as e:      # noqa: BLE001
-            gstep, graph_note = None, "eager launches (graph capture failed: %s)" % str(e)[:120]
+    def make_batch(n_rand):
+        o, d, target = synth_rays_np(n_rand, 100 + rank)
+        pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
+        h_rays, h_t = pin(np.stack([o, d], 0)), pin(target)
+        return h_rays, h_t, h_rays.to(dev), h_t.to(dev)
+
+    def make_graphed(n_rand, d_rays, d_target):
+        """the step as the product runs it (graph.GraphedTrainStep): ONE CUDA graph incl. the NCCL buckets; if NCCL refuses to be
+        captured: two graphs with the eager allreduce between them; eager launches if capture fails altogether"""
+        if a.no_graph:
+            return None, "eager launches"
+        from mvip_nerf_b200.graph import GraphedTrainStep
+        for in_graph, note in ((True, "one CUDA graph per step: render + loss + backward + per-network NCCL allreduce (overlapped) + Adam + bf16 re-pack"),
+                               (False, "two CUDA graphs per step: (render + loss + backward) | eager NCCL allreduce | (Adam + bf16 re-pack)")):
+            if not in_graph and world == 1:
+                break
+            try:
+                g = GraphedTrainStep(kw_train, optimizer, H, W, FOCAL, n_rand, NEAR, FAR, nccl_in_graph=in_graph)
+                g.rays.copy_(d_rays)
+                g.target.copy_(d_target)
+                g.capture()
+                return g, note
+            except Exception as e:      # noqa: BLE001
+                err = str(e)[:160]
+                torch.cuda.synchronize()
+        return None, "eager launches (graph capture failed: %s)" % err
+
+    h_rays, h_t, d_rays, d_target = make_batch(N_RAND)
+    sync.remove()                       # GraphedTrainStep installs its own hooks; the eager region below re-installs these
+    gstep, graph_note = make_graphed(N_RAND, d_rays, d_target)
 
     def resident_step():
         return gstep() if gstep is not None else step(d_rays, d_target)
 
     # ---- device-resident arm ---------------------------------------------------------------------
+    if gstep is None:
+        sync = md.GradSync(groups)
     for _ in range(a.warmup):
         resident_step()
     clocks = ClockSampler(local)
@@ -316,15 +401,32 @@ def run_ours(a):
     def e2e_step():
         if gstep is not None:
             return float(gstep(h_rays, h_t).item())
-        rays = torch.stack([h_o.to(dev, non_blocking=True), h_d.to(dev, non_blocking=True)], 0)
-        tgt = h_t.to(dev, non_blocking=True)
-        return float(step(rays, tgt).item())
+        return float(step(h_rays.to(dev, non_blocking=True), h_t.to(dev, non_blocking=True)).item())
     for _ in range(max(1, a.warmup // 2)):
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps) / a.steps
     e2e_value = world * N_RAND / (ms_e2e * 1e-3)
 
+    # ---- secondary (8 GPUs): BASELINE cfg 4, N_rand = 65,536 rays per step = 8,192 per GPU ------------------------
+    cfg4 = None
+    if world == 8 and N_RAND != 8192:
+        if gstep is not None and gstep.sync is not None:
+            gstep.sync.remove()
+        b4 = make_batch(8192)
+        g4, _ = make_graphed(8192, b4[2], b4[3])
+        if g4 is not None:
+            for _ in range(3):
+                g4()
+            ms4 = timed(g4, a.steps) / a.steps
+            cfg4 = {"rays_s": world * 8192 / (ms4 * 1e-3), "ms_per_step": ms4, "global_rays": 65536}
+            if g4.sync is not None:
+                g4.sync.remove()
+            del g4
+    elif gstep is not None and gstep.sync is not None:
+        gstep.sync.remove()
+
     # ---- the same K steps launched eagerly with a CUDA-event bracket around every library call: per-kernel times --------
+    sync = md.GradSync(groups)
     for _ in range(3):
         step(d_rays, d_target)
     ops.kernel_timer.enable(True)
@@ -333,15 +435,12 @@ def run_ours(a):
     launches = ops.launch_count - l0
     ktimes = ops.kernel_timer.collect()
     ops.kernel_timer.enable(False)
+    sync.remove()
 
     # ---- secondary: full-image render (cfg 3), rays sharded, one gather ------------------------------
     n_img = H * W
     c2w = torch.eye(4, device=dev)[:3, :4]
-    from mvip_nerf_b200.run_nerf_helpers import get_rays
-    ro, rd = get_rays(H, W, FOCAL, c2w)
-    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
-    ones = torch.ones(n_img, 1, device=dev)
-    rays_flat = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), NEAR * ones, FAR * ones, vd.reshape(-1, 3)], -1).contiguous()
+    rays_flat = ops.rays_from_pose(H, W, FOCAL, c2w, NEAR, FAR, use_viewdirs=True, ndc=False)
     kw_r = {k: v for k, v in kw_test.items() if k not in ("ndc", "use_viewdirs")}
 
     def render_image():
@@ -391,95 +490,89 @@ def run_ours(a):
     # ---- HBM-bound stages at image-sized batches (rank 0, CUDA events per launch, L2 flushed between launches) ---------
     hbm_stages = hbm_stage_times(ops, dev, pk["hbm_gbs"])
 
-    # ---- roofline of the dominant kernel (CUDA events around each launch, inside the timed region) -----
-    pts = {"coarse": N_RAND * 64, "fine": N_RAND * 128}
+    # ---- per-kernel rooflines (CUDA events around each launch of the eager region) -----------------------------------------
+    # Tensor denominators: the cuBLAS bf16 burst peak for a timed region under 1 s (the clocks have not settled under the
+    # power cap: this is the honest roof for a 20-step run), the sustained peak for a longer one; both fractions are printed.
+    npts = N_RAND * 192
+    tf_burst, tf_sust = pk["bf16_tflops"], pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    short = ms_total < 1000.0
+    peak_tf = tf_burst if short else tf_sust
+    table = kernel_table()
     per_kernel = {}
-    tot_kernel_ms = sum(sum(v) for v in ktimes.values())
     for name, vals in ktimes.items():
-        per_kernel[name] = {"launches_per_step": len(vals) / a.steps, "ms_per_step": sum(vals) / a.steps,
-                            "share_of_step": sum(vals) / a.steps / ms_eager}
-    npts = pts["coarse"] + pts["fine"]
-    flops = {"mvip_mlp_forward": FLOP_FWD * npts, "dgrad_chain_kernel": FLOP_DGRAD * npts, "wgrad_kernel": FLOP_WGRAD * npts,
-             "backward_fused_kernel": (FLOP_DGRAD + FLOP_WGRAD) * npts}
-    # algorithmic HBM bytes per point of the training kernels: forward writes the activation stash,
-    # the dgrad chain reads the ReLU masks and writes the dZ stash, wgrad reads both stashes (bf16 chunk images only)
-    hbm_bytes = {"mvip_mlp_forward": (HBM_FWD_TRAIN, "write"), "dgrad_chain_kernel": (HBM_DGRAD, "write"),
-                 "wgrad_kernel": (HBM_WGRAD, "read"), "head_grads_kernel": (HBM_HEADS, "read"),
-                 # fused backward: the dZ stash is written once and re-read by the concurrent wgrad CTAs out of L2
-                 "backward_fused_kernel": (HBM_DGRAD + 40 * 128, "read+write")}
-    top = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
-    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    for k in flops:
-        if k in per_kernel:
-            per_kernel[k]["tflops"] = flops[k] / (per_kernel[k]["ms_per_step"] * 1e-3) / 1e12
-            per_kernel[k]["frac_of_tensor_peak"] = per_kernel[k]["tflops"] / peak_tf
-    for k, (b, kind) in hbm_bytes.items():
-        if k in per_kernel:
-            per_kernel[k]["hbm_gbs"] = b * npts / (per_kernel[k]["ms_per_step"] * 1e-3) / 1e9
-            per_kernel[k]["frac_of_hbm_peak"] = per_kernel[k]["hbm_gbs"] / pk["hbm_gbs"]
-            per_kernel[k]["hbm_direction"] = kind
+        ms_k = sum(vals) / a.steps
+        e = {"launches_per_step": len(vals) / a.steps, "ms_per_step": ms_k, "share_of_step": ms_k / ms_eager}
+        if name in table:
+            fl, by, kind = table[name]
+            if fl:
+                e["tflops"] = fl * npts / (ms_k * 1e-3) / 1e12
+                e["frac_of_tensor_burst"], e["frac_of_tensor_sustained"] = e["tflops"] / tf_burst, e["tflops"] / tf_sust
+            e["hbm_gbs"] = by * npts / (ms_k * 1e-3) / 1e9
+            e["frac_of_hbm_peak"] = e["hbm_gbs"] / pk["hbm_gbs"]
+            e["hbm_direction"] = kind
+        per_kernel[name] = e
+    mlp_kernels = [k for k in per_kernel if k in table and table[k][0]]
+    top = max(mlp_kernels, key=lambda k: per_kernel[k]["ms_per_step"]) if mlp_kernels else None
     roofline = None
-    if top in per_kernel and (top in flops or top in hbm_bytes):
-        # every training kernel moves ~5-10 KB per point at < 130 FLOP/B (machine balance ~210): HBM is the binding roof;
-        # the tensor-pipe fraction is kept beside it (and is the roof of the render-only forward, see "render")
+    if top:
         e = per_kernel[top]
-        if e.get("frac_of_hbm_peak", 0.0) >= e.get("frac_of_tensor_peak", 0.0):
-            roofline = {"kernel": top, "bound": "hbm", "achieved": e["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": e["frac_of_hbm_peak"],
-                        "traffic": NCU_TRAFFIC[top] * N_RAND / 4096 if top in NCU_TRAFFIC else None,   # captured at 4096 rays
-                        "algorithmic_bytes_per_launch": hbm_bytes[top][0] * npts / 2,
-                        "peak_source": "%s hbm_gbs (STREAM-style copy; this kernel's traffic is %s-only, for which "
-                                       "the same box measures ~3.9 TB/s write / ~5.9 TB/s read, scripts/hbm_write_bw.py)"
-                                       % (pk["_source"], e["hbm_direction"]),
-                        "tensor_frac": e.get("frac_of_tensor_peak"), "share_of_step": e["share_of_step"]}
-        else:
-            roofline = {"kernel": top, "bound": "tensor", "achieved": e["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": e["frac_of_tensor_peak"], "traffic": None,
-                        "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["_source"],
-                        "share_of_step": e["share_of_step"]}
+        traffic, traffic_src = ncu_traffic(top, N_RAND)
+        roofline = {"kernel": top, "bound": "tensor", "achieved": e["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": e["tflops"] / peak_tf, "frac_burst": e["frac_of_tensor_burst"], "frac_sustained": e["frac_of_tensor_sustained"],
+                    "peak_source": "%s cuBLAS bf16 %s peak (timed region %.0f ms)" % (pk["_source"], "burst" if short else "sustained", ms_total),
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "share_of_step": e["share_of_step"],
+                    "hbm": {"achieved": e["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": e["frac_of_hbm_peak"],
+                            "direction": e["hbm_direction"], "algorithmic_bytes_per_launch": table[top][1] * npts / 2,
+                            "note": "the design moves the activation / dZ stash through HBM (DESIGN.md §3); §8(d)'s algorithmic "
+                                    "work of the MLP is FLOPs, hence bound=tensor and this figure beside it"}}
+    train_tf = world * N_RAND * 192 * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) / (ms_step * 1e-3) / 1e12
+    render_tf = n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12
+    if roofline is not None:     # compact secondaries: the driver keeps `roofline` / `e2e` / `config` of the line, not extra keys
+        roofline["step"] = {"train_tflops": train_tf, "frac_burst": train_tf / (tf_burst * world), "frac_sustained": train_tf / (tf_sust * world)}
+        roofline["secondary"] = {
+            "render_cfg3_rays_s": render_value, "render_tflops": render_tf, "render_frac_burst": render_tf / (tf_burst * world),
+            "render_frac_sustained": render_tf / (tf_sust * world), "guidance_cfg5_rays_s": guid_value,
+            "guidance_train_rays_s": gtrain_value, "train_cfg4_rays_s": cfg4["rays_s"] if cfg4 else None,
+            "composite_fwd_S128_frac_hbm": hbm_stages["composite_fwd_S128"]["frac_of_hbm_peak"],
+            "composite_bwd_S128_frac_hbm": hbm_stages["composite_bwd_S128"]["frac_of_hbm_peak"],
+            "sample_fine_frac_hbm": hbm_stages["sample_fine_rand_u"]["frac_of_hbm_peak"],
+            "sample_coarse_frac_hbm": hbm_stages["sample_coarse_perturb"]["frac_of_hbm_peak"]}
 
-    # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------------
+    # ---- CPU baseline on the host cores (bounded sample; child process with the GPUs hidden) ----------------------------
     cpu_base = None
     if world == 1 and not a.no_cpu_baseline:
-        sample, csteps = 512, 4
-        cval, _ = cpu_train_rays_per_s(sample, csteps, 1)
-        cpu_base = {"value": cval, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": "%d rays x %d steps of the same train step, PyTorch-CPU port of the reference path" % (sample, csteps)}
+        cpu_base = cpu_baseline_subprocess(1024, 8, 1)
 
-    bytes_in = (h_o.numel() + h_d.numel() + h_t.numel()) * 4
+    bytes_in = (h_rays.numel() + h_t.numel()) * 4
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": ("cfg4" if N_RAND * world == 65536 else "cfg2") + ": one training step, N_rand=%d rays per GPU (global %d), N_samples=64, N_importance=64, "
-                               "coarse+fine 8x256 NeRF (random init), lindisp, white_bkgd, perturb=1, raw_noise_std=1, "
-                               "loss=mse(rgb)+mse(rgb0), grad allreduce, fused Adam" % (N_RAND, N_RAND * world),
-                   "parallelism": "rays sharded, dp%d" % world,
-                   "launch": graph_note,
-                   "kernel_times": "CUDA events around every library call in a second timed region of the same %d steps launched "
-                                   "eagerly (%.3f ms/step); gpu_launches counts that region" % (a.steps, ms_eager),
-                   "l2": "no explicit flush: each step streams ~8 GB of activation stash per GPU (>> 126 MB L2)"},
+        "config": workload_config(N_RAND, world),
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
+        "notes": {"launch": graph_note,
+                  "kernel_times": "CUDA events around every library call in a second timed region of the same %d steps launched "
+                                  "eagerly (%.3f ms/step); gpu_launches counts that region" % (a.steps, ms_eager),
+                  "l2": "no explicit flush: each step streams ~8 GB of activation stash per GPU (>> 126 MB L2)"},
         "kernels": per_kernel,
         "render": {"value": render_value, "unit": "rays/s", "ms_per_image": ms_render,
                    "workload": "cfg3: 1008x756 image (762,048 rays), render kwargs, rays sharded over %d GPU(s), one gather" % world,
-                   "tflops": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12,
-                   "bound": "tensor", "peak": peak_tf * world,
-                   "frac_of_peak": n_img * 192 * FLOP_FWD / (ms_render * 1e-3) / 1e12 / (peak_tf * world)},
+                   "tflops": render_tf, "bound": "tensor"},
         "guidance": {"value": guid_value, "unit": "rays/s", "ms_per_batch": ms_guid,
                      "workload": "cfg5: %d views of %dx%d (rgb + disp + acc + depth), image rows sharded over %d GPU(s), one gather, "
                                  "normal maps (k=31) of all views on rank 0" % (GV, GH, GW, world)},
         "guidance_train": {"value": gtrain_value, "unit": "rays/s", "ms_per_view": ms_gtrain,
                            "workload": "one 512x512 view per GPU, forward + image loss + deferred back-propagation "
                                        "(re-render in 8192-ray chunks), parameter gradients of both networks"},
+        "train_cfg4": cfg4,
         "hbm_stages": hbm_stages,
-        "train_tflops": world * N_RAND * 192 * (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) / (ms_step * 1e-3) / 1e12,
+        "train_tflops": train_tf,
     }
-    line["train_frac_of_peak"] = line["train_tflops"] / (peak_tf * world)
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
@@ -496,13 +589,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-gpu", type=int, default=N_RAND,
                     help="N_rand per GPU: 4096 = BASELINE cfg 2 (default, the configuration `metric` is quoted on); 8192 with "
-                         "--gpus 8 = cfg 4 (65,536 rays per step)")
+                         "--gpus 8 = cfg 4 (65,536 rays per step; also measured as a secondary entry of every 8-GPU run)")
+    ap.add_argument("--sample", type=int, default=1024,
+                    help="reference arm: rays per timed step (a bounded sample of the N_rand batch; 1024 = the reference's own N_rand)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""      # the reference picks `cuda` when it sees one (run.py:46): this arm is its CPU path
         run_reference(a)
     else:
+        a.warmup = max(a.warmup, 3)
         run_ours(a)
 
 

@@ -23,17 +23,6 @@ int mvip_num_sms() {
   return cached[dev];
 }
 
-namespace mlp {
-bool use_cta_pairs() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MVIP_MLP_CTA_PAIRS");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-}  // namespace mlp
-
 extern "C" {
 
 int mvip_abi_version(void) { return MVIP_ABI_VERSION; }

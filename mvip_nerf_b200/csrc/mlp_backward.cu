@@ -23,11 +23,6 @@ using namespace mlp;
 // =================================================================================================
 // 1. dgrad chain
 // =================================================================================================
-constexpr int kCThreads = 384;
-constexpr int kCStages = 3;
-constexpr uint32_t kCSmemAct = 0;                        // act[2]: 2 x 64 KB
-constexpr uint32_t kCSmemW = 2 * 4 * kActChunk;          // weight ring 3 x 32 KB
-constexpr uint32_t kCSmemBytes = kCSmemW + kCStages * kW256;  // 229,376
 constexpr int kCSteps = 9;
 
 struct ChainParams {
@@ -42,223 +37,6 @@ struct ChainParams {
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
 
 __device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
-
-__global__ void __launch_bounds__(kCThreads, 1) dgrad_chain_kernel(const ChainParams p) {
-  // No static shared memory in this kernel: the dynamic segment then starts 1024-byte aligned (checked below),
-  // which the 128-byte-swizzled operand tiles need, and every byte of the 227 KB is usable:
-  //   [act 128 KB][weight ring 96 KB][w_alpha, W_rgb fp32 2.5 KB][mbarriers]
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float* heads_s = reinterpret_cast<float*>(smem + kCSmemBytes);          // read per row by every epilogue thread
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kCSmemBytes + 2560);
-  uint64_t* bar_empty = bar_full + kCStages;
-  uint64_t* bar_acc = bar_empty + kCStages;
-  uint64_t* bar_act = bar_acc + 2;
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bar_act + 2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if ((smem_u32(smem) & 1023u) != 0) {
-    if (tid == 0) printf("mvip: dgrad_chain_kernel dynamic smem base %u not 1024-aligned\n", smem_u32(smem));
-    __trap();
-  }
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
-  const uint8_t* wT = p.packed + kFwdBytes;
-  {
-    const float* sm = reinterpret_cast<const float*>(p.packed + kSmallOff);
-    for (int i = tid; i < 256; i += kCThreads) heads_s[i] = __ldg(sm + kSmWAlpha + i);
-    for (int i = tid; i < 384; i += kCThreads) heads_s[256 + i] = __ldg(sm + kSmWRgb + i);
-  }
-
-  if (tid == 0) {
-    for (int i = 0; i < kCStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 1); }
-    mbar_fence_init();
-  }
-  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-        int cidx = 0;
-        for (int s = 0; s < kCSteps; ++s) {
-          const int nch = chain_nchunks(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            for (int ci = 0; ci < nch; ++ci) {
-              mbar_wait(&bar_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&bar_full[stage], kW256);
-              tma_load_1d(smem + kCSmemW + stage * kW256, wT + (size_t)(cidx + ci) * kW256, kW256, &bar_full[stage]);
-              if (++stage == kCStages) { stage = 0; phase ^= 1; }
-            }
-          }
-          cidx += nch;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      int stage = 0; uint32_t phase = 0; uint32_t act_phase[2] = {0, 0};
-      const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
-      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-        for (int s = 0; s < kCSteps; ++s) {
-          const int nch = chain_nchunks(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait(&bar_act[slot], act_phase[slot]);
-            act_phase[slot] ^= 1;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            for (int ci = 0; ci < nch; ++ci) {
-              const uint32_t a_addr = smem_u32(smem) + kCSmemAct + slot * 4 * kActChunk + ci * kActChunk;
-              const uint32_t b_addr = smem_u32(smem) + kCSmemW + stage * kW256;
-              mbar_wait(&bar_full[stage], phase);
-              tc_fence_after();
-              if (elect_one_sync()) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                  uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                  umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
-                }
-                umma_commit(&bar_empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kCStages) { stage = 0; phase ^= 1; }
-            }
-            if (elect_one_sync()) umma_commit(&bar_acc[slot]);
-            __syncwarp();
-          }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    const int slot = (warp - 4) >> 2;
-    const int r = tid - 128 - slot * 128;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t bar_id = 1 + slot;
-    uint8_t* act = smem + kCSmemAct + slot * 4 * kActChunk;
-    uint32_t acc_phase = 0;
-
-    for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-      const int64_t tile = 2 * it + slot;
-      const bool tile_valid = tile < p.n_tiles;
-      const int64_t g = tile * kTile + r;
-      const bool valid = tile_valid && g < p.n_points;
-      const uint8_t* stash_tile = p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes;
-      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
-      const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
-
-      // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0]  -> A operand of step 0
-      float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r == 0) tma_store_wait_read0();
-      named_bar_sync(bar_id, 128);
-      {
-        const uint4 m4 = *reinterpret_cast<const uint4*>(masks + ((size_t)8 * 128 + r) * 8);
-        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          float v[32];
-          const uint32_t m = valid ? mw[c0 >> 5] : 0u;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 w0 = *(reinterpret_cast<const float4*>(heads_s + 256 + c0) + j4);
-            const float4 w1 = *(reinterpret_cast<const float4*>(heads_s + 256 + 128 + c0) + j4);
-            const float4 w2 = *(reinterpret_cast<const float4*>(heads_s + 256 + 256 + c0) + j4);
-            v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
-            v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
-            v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
-            v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((m >> mask_bit_of_column(j)) & 1u) ? v[j] : 0.f;
-          uint8_t* img = act + (c0 >> 6) * kActChunk;
-          const int g0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
-                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(bar_id, 128);
-      if (r == 0) {
-        mbar_arrive(&bar_act[slot]);
-        if (tile_valid) {
-          for (int j = 0; j < 2; ++j)
-            tma_store_1d(dz_tile + (size_t)(kDzHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
-          tma_store_commit();
-        }
-      }
-
-      for (int s = 0; s < kCSteps; ++s) {
-        mbar_wait(&bar_acc[slot], acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (r == 0) tma_store_wait_read0();
-        named_bar_sync(bar_id, 128);
-        // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
-        uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
-        if (s >= 1) {
-          const uint4* mp = reinterpret_cast<const uint4*>(masks + ((size_t)(8 - s) * 128 + r) * 8);
-          const uint4 a = mp[0], b = mp[1];
-          mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
-        }
-#pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {
-          const int c0 = cb * 32;
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + lane_base + slot * 256 + c0, acc);
-          tmem_ld_wait();
-          float v[32];
-          const uint32_t m = valid ? mw[cb] : 0u;
-          if (s == 1) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = *(reinterpret_cast<const float4*>(heads_s + c0) + j4);
-              v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + dr.w * w.x;
-              v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + dr.w * w.y;
-              v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + dr.w * w.z;
-              v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + dr.w * w.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((m >> mask_bit_of_column(j)) & 1u) ? v[j] : 0.f;
-          uint8_t* img = act + (c0 >> 6) * kActChunk;
-          const int g0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
-                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (r == 0) {
-          if (s < kCSteps - 1) mbar_arrive(&bar_act[slot]);
-          if (tile_valid) {
-            const int first = (s == 0) ? kDzFeat : kDzTrunk + 4 * (s - 1);
-            for (int j = 0; j < 4; ++j)
-              tma_store_1d(dz_tile + (size_t)(first + j) * kActChunk, act + j * kActChunk, kActChunk);
-            tma_store_commit();
-          }
-        }
-      }
-    }
-    if (r == 0) tma_store_wait_all0();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
 
 // =================================================================================================
 // 1b. dgrad chain, CTA pairs (cta_group::2) with the gradient tiles resident in tensor memory - same skeleton as
@@ -867,21 +645,6 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) { wgrad_body(p, blockIdx.x, gridDim.x); }
 
 // =================================================================================================
-// 2b. fused backward: the dgrad chain (CTA pairs 0 .. n_dgrad_ctas/2 - 1) and the weight-gradient GEMMs (remaining CTAs) run
-//     CONCURRENTLY in one launch of one CTA per SM.  wgrad is tile-major here: every wgrad CTA is bound to one item (layer)
-//     and consumes that layer's dZ of tile after tile as soon as the chain has stored it (per (tile, group) flags in global
-//     memory), i.e. while the 128 B/point/chunk images are still in the 126 MB L2.  Stand-alone, wgrad re-reads the
-//     whole dZ stash (4.9 KB/point) from HBM after the chain has written it; fused, that read is served by L2 and HBM sees the
-//     chain's writes overlapped with wgrad's reads of the forward stash.  The chain never waits for wgrad (dZ has its
-//     own full-size buffer), wgrad only waits for flags, and all CTAs are resident (grid <= #SMs): no deadlock.
-// =================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
-backward_fused_kernel(const ChainParams cp, const WParams wp, const int n_dgrad_ctas) {
-  if ((int)blockIdx.x < n_dgrad_ctas) dgrad_pair_body(cp, blockIdx.x >> 1, n_dgrad_ctas >> 1);
-  else wgrad_body(wp, (int)blockIdx.x - n_dgrad_ctas, (int)gridDim.x - n_dgrad_ctas);
-}
-
-// =================================================================================================
 // 3. alpha / rgb head grads on CUDA cores
 // =================================================================================================
 constexpr int kHeadFloats = 256 + 4 + 384 + 4;   // dW_alpha, db_alpha(+pad), dW_rgb, db_rgb(+pad)
@@ -1147,65 +910,18 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   for (int i = 0; i <= kNumItems; ++i) wp.item_first[i] = 0;
   int w_grid = sms;
 
-  // 1+2 fused: chain on n_dgrad SMs, tile-major wgrad on the others (needs both phases in one call and enough tiles to fill both)
-  static int fused_env = -1, dgrad_sms_env = 0;
-  if (fused_env < 0) {
-    const char* e = getenv("MVIP_BWD_FUSED");
-    fused_env = (e && e[0] == '1') ? 1 : 0;   // opt-in: see DESIGN.md (measured 1.74 ms fused vs 1.64 ms separate at P = 524,288)
-    const char* d = getenv("MVIP_BWD_DGRAD_SMS");
-    dgrad_sms_env = d ? atoi(d) : 0;
-  }
-  const bool fused = fused_env && mlp::use_cta_pairs() && (phase_mask & 3) == 3 && sms >= 64 && sms % 2 == 0 && n_tiles >= 2 * sms;
-  if (fused) {
-    int n_dgrad = dgrad_sms_env > 0 ? dgrad_sms_env : (sms * 46 / 100);
-    n_dgrad &= ~1;
-    if (n_dgrad < 2) n_dgrad = 2;
-    if (n_dgrad > sms - kNumItems) n_dgrad = (sms - kNumItems) & ~1;
-    w_grid = sms - n_dgrad;
-    // CTAs per item proportional to its cost (largest remainder)
-    int total_cost = 0, assigned = 0, n_i[kNumItems];
-    WItem items_h[kNumItems];
-    MVIP_CUDA_OK(cudaMemcpyFromSymbol(items_h, kItems, sizeof(items_h)));
-    for (int i = 0; i < kNumItems; ++i) total_cost += items_h[i].cost;
-    for (int i = 0; i < kNumItems; ++i) { n_i[i] = w_grid * items_h[i].cost / total_cost; if (n_i[i] < 1) n_i[i] = 1; assigned += n_i[i]; }
-    while (assigned < w_grid) {   // give the next CTA to the item with the largest cost per CTA
-      int best = 0;
-      for (int i = 1; i < kNumItems; ++i)
-        if ((long long)items_h[i].cost * n_i[best] > (long long)items_h[best].cost * n_i[i]) best = i;
-      ++n_i[best]; ++assigned;
-    }
-    for (int i = 0; i < kNumItems; ++i) wp.item_first[i + 1] = wp.item_first[i] + n_i[i];
-    uint32_t* flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
-    MVIP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t), st));
-    cp.flags = flags;
-    wp.flags = flags;
-    const size_t smem = (kDSmemBytes > kWSmemBytes ? kDSmemBytes : kWSmemBytes) + 1024;
-    MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
-    backward_fused_kernel<<<sms, kDThreads, smem, st>>>(cp, wp, n_dgrad);
-    MVIP_LAUNCH_OK("backward_fused_kernel");
-  }
-
   // 1. dgrad chain
-  if (!fused && (phase_mask & 1)) {
-    if (mlp::use_cta_pairs()) {
-      const int64_t n_quads = (n_tiles + 3) / 4;
-      const int max_clusters = sms / 2;
-      const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
-      const size_t smem2 = kDSmemBytes + 1024;
-      MVIP_SMEM_OPT_IN(dgrad_pair_kernel, smem2);
-      dgrad_pair_kernel<<<grid2, kDThreads, smem2, st>>>(cp);
-      MVIP_LAUNCH_OK("dgrad_pair_kernel");
-    } else {
-      const int64_t n_pairs = (n_tiles + 1) / 2;
-      const int grid = (int)(n_pairs < sms ? n_pairs : sms);
-      const size_t smem = kCSmemBytes + 2560 + 128;
-      MVIP_SMEM_OPT_IN(dgrad_chain_kernel, smem);
-      dgrad_chain_kernel<<<grid, kCThreads, smem, st>>>(cp);
-      MVIP_LAUNCH_OK("dgrad_chain_kernel");
-    }
+  if (phase_mask & 1) {
+    const int64_t n_quads = (n_tiles + 3) / 4;
+    const int max_clusters = sms / 2;
+    const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
+    const size_t smem2 = kDSmemBytes + 1024;
+    MVIP_SMEM_OPT_IN(dgrad_pair_kernel, smem2);
+    dgrad_pair_kernel<<<grid2, kDThreads, smem2, st>>>(cp);
+    MVIP_LAUNCH_OK("dgrad_pair_kernel");
   }
   // 2. wgrad
-  if (!fused && (phase_mask & 2)) {
+  if (phase_mask & 2) {
     const size_t smem = kWSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(wgrad_kernel, smem);
     wgrad_kernel<<<w_grid, kWThreads, smem, st>>>(wp);

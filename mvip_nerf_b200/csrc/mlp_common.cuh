@@ -72,7 +72,4 @@ __host__ __device__ inline int mask_bit_of_column(int j) { return 16 * (j & 1) +
 
 inline int64_t num_tiles(int64_t n_points) { return (n_points + kTile - 1) / kTile; }
 
-// kernel variant switch (api.cu): CTA pairs (cta_group::2) unless MVIP_MLP_CTA_PAIRS=0
-bool use_cta_pairs();
-
 }  // namespace mlp

@@ -2,34 +2,18 @@
 //   replaces DS_NeRF/run.py:1108-1124 (run_network), run_nerf_helpers.py:22-52 (Embedder.embed) and
 //   run_nerf_helpers.py:104-127 (NeRF.forward)
 //
-// Two kernels:
-//   mlp_forward_pair_kernel  (default) CTA pairs (cta_group::2), activations resident in TENSOR MEMORY: the A operand of
-//                            every layer is read from TMEM ("TS" tcgen05.mma), the epilogue writes the next layer's
-//                            bf16 activations straight back to TMEM.  1,443 TFLOP/s at inference on one B200
-//                            (87 % of the cuBLAS bf16 burst peak).  Described in the comment block above the kernel.
-//   mlp_forward_kernel       the first version, kept as an A/B reference behind MVIP_MLP_CTA_PAIRS=0: one CTA per SM,
-//                            384 threads, activations as swizzled bf16 tiles in SHARED memory ("SS" MMAs, 868 TFLOP/s):
-//     warp 0      TMA producer: streams the packed bf16 weight chunks (cp.async.bulk -> 2-stage smem ring)
-//     warp 1      MMA issuer:   tcgen05.mma 128xNx16 (bf16 x bf16 -> fp32 in TMEM), one elected thread
-//     warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
-//     warps 4-7   epilogue of tile slot 0 (TMEM lanes = the 128 points of the tile)
-//     warps 8-11  epilogue of tile slot 1
-//   Two 128-point tiles ping-pong through the layer sequence, so one tile's epilogue overlaps the other tile's MMAs.
-// In both, activations never leave the SM; the only HBM traffic at inference is 16..28 B/point in (rays+z) and
-// 16 B/point out (raw).  With a stash pointer (training) every layer's input tile image is also bulk-stored for the
-// backward pass (mlp_common.cuh, kStash*).
+// ONE kernel, mlp_forward_pair_kernel<kTrain>: CTA pairs (cta_group::2), activations resident in TENSOR MEMORY: the A
+// operand of every layer is read from TMEM ("TS" tcgen05.mma), the epilogue writes the next layer's bf16 activations
+// straight back to TMEM.  1,443 TFLOP/s at inference on one B200 (87 % of the cuBLAS bf16 burst peak).  Described in the
+// comment block above the kernel.  Activations never leave the SM; the only HBM traffic at inference is 16..28 B/point in
+// (rays+z) and 16 B/point out (raw).  With a stash pointer (training) every layer's input tile image is also bulk-stored
+// for the backward pass (mlp_common.cuh, kStash*).
 #include "mlp_pair.cuh"
 #include <stdlib.h>
 
 namespace {
 using namespace mlp;
 
-constexpr int kThreads = 384;
-constexpr int kStages = 2;
-constexpr uint32_t kSmemAct = 0;                         // act[2]: 2 x 64 KB
-constexpr uint32_t kSmemPE = 2 * 4 * kActChunk;          // pe[2]:  2 x 16 KB
-constexpr uint32_t kSmemW = kSmemPE + 2 * kActChunk;     // weight ring
-constexpr uint32_t kSmemBytes = kSmemW + kStages * kW256;  // 229,376
 constexpr int kNumSteps = 10;
 
 // cycle counters of CTA 0 (debug aid, read with mvip_debug_profile): [0] mma: act wait, [1] mma: weight wait,
@@ -69,14 +53,8 @@ struct Params {
   int64_t n_tiles;
 };
 
-// step s: number of K chunks, A source of each (0 = PE buffer, 1..4 = act chunk), N, K-steps of last chunk
+// step s: number of 64-wide K chunks of its weight block
 __device__ __forceinline__ int step_nchunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
-__device__ __forceinline__ int step_asrc(int s, int ci) {
-  if (s == 0) return 0;
-  if (s == 5) return ci;            // PE, a0..a3
-  if (s == 9) return ci == 4 ? 0 : ci + 1;
-  return ci + 1;
-}
 
 // ---- positional encoding ---------------------------------------------------------------------
 // sin/cos(x * 2^k): the phase is reduced in "turns" with a two-float product x/(2 pi) (power-of-two
@@ -97,33 +75,6 @@ __device__ __forceinline__ void pe_axis(float x, int L, float* s, float* c) {
       c[k] = __cosf(ang);
       scale *= 2.f;
     }
-  }
-}
-
-// writes one 64-wide bf16 row (3 + 6L channels, zero padded) of a chunk image
-template <int L>
-__device__ __forceinline__ void write_pe_row(uint8_t* img, int row, float x, float y, float z) {
-  float s[3][10], c[3][10];
-  pe_axis(x, L, s[0], c[0]);
-  pe_axis(y, L, s[1], c[1]);
-  pe_axis(z, L, s[2], c[2]);
-  const float in[3] = {x, y, z};
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = g * 8 + e;
-      float val = 0.f;
-      if (i < 3) val = in[i];
-      else if (i < 3 + 6 * L) {
-        const int t = i - 3, k = t / 6, r6 = t % 6, d = r6 % 3;
-        val = (r6 >= 3) ? c[d][k] : s[d][k];
-      }
-      v[e] = val;
-    }
-    *reinterpret_cast<uint4*>(img + chunk_off16(row, g)) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -168,9 +119,6 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   return d;
 }
 
-
-// ===================== epilogue warpgroups (shared by the 1-CTA and the CTA-pair kernels) =====================
-// Warps 4..11: warpgroup `slot` owns tile slot `slot`; thread r <-> row r of the tile <-> TMEM lane r.
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -180,278 +128,6 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
-}
-
-// small_smem != 0: the fp32 tail of the packed blob (biases, alpha / rgb heads) was staged in shared memory at
-// that shared-space address (CTA-pair kernel); otherwise it is read from global memory.
-template <bool kTrain, int kCta>
-__device__ __forceinline__ void forward_epilogue(const Params& p, uint8_t* smem, uint64_t* bar_acc, uint64_t* bar_act,
-                                                 uint32_t tmem_base, int warp, int tid, uint32_t cta_rank,
-                                                 int64_t first_it, int64_t n_iters, int64_t it_stride,
-                                                 uint32_t small_smem) {
-  auto small4 = [&](int float_index) -> float4 {   // 4 consecutive floats of the small-parameter block
-    if (kCta == 2) return lds_f4(small_smem + float_index * 4);
-    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.packed + kSmallOff) + float_index));
-  };
-  auto small1 = [&](int float_index) -> float {
-    if (kCta == 2) return lds_f1(small_smem + float_index * 4);
-    return __ldg(reinterpret_cast<const float*>(p.packed + kSmallOff) + float_index);
-  };
-  // "A operand ready + accumulator drained" goes to the MMA issuer: local barrier, or the leader CTA's in a pair
-  auto act_arrive = [&](uint64_t* bar) {
-    if (kCta == 1 || cta_rank == 0) mbar_arrive(bar);
-    else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
-  };
-  {
-    const int slot = (warp - 4) >> 2;
-    const int r = tid - 128 - slot * 128;                     // row of the tile == TMEM lane
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t bar_id = 1 + slot;
-    uint8_t* act = smem + kSmemAct + slot * 4 * kActChunk;
-    uint8_t* pe = smem + kSmemPE + slot * kActChunk;
-    uint32_t acc_phase = 0;
-    long long t_accw = 0, t_work = 0, t_begin = clock64();
-
-    for (int64_t it = first_it; it < n_iters; it += it_stride) {
-      const int64_t tile = (kCta == 1) ? 2 * it + slot : 4 * it + 2 * slot + (int64_t)cta_rank;
-      const bool tile_valid = tile < p.n_tiles;
-      const int64_t g = tile * kTile + r;
-      const bool valid = tile_valid && g < p.pts.n_points;
-      uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
-
-      // ---- inputs: point and view direction of this row -----------------------------------
-      float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
-      if (valid) {
-        if (p.pts.rays) {
-          const int64_t ray = g / p.pts.n_samples;
-          const float* rp = p.pts.rays + ray * p.pts.ray_stride;
-          const float zv = __ldg(p.pts.z_vals + g);
-          px = __fadd_rn(__ldg(rp + 0), __fmul_rn(__ldg(rp + 3), zv));   // pts = o + d*z   run.py:1783
-          py = __fadd_rn(__ldg(rp + 1), __fmul_rn(__ldg(rp + 4), zv));
-          pz = __fadd_rn(__ldg(rp + 2), __fmul_rn(__ldg(rp + 5), zv));
-          vx = __ldg(rp + p.pts.viewdir_offset);
-          vy = __ldg(rp + p.pts.viewdir_offset + 1);
-          vz = __ldg(rp + p.pts.viewdir_offset + 2);
-        } else {
-          const float* pp = p.pts.pts + g * p.pts.pts_stride;
-          const float* dp = p.pts.dirs + g * p.pts.dirs_stride;
-          px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
-          vx = __ldg(dp); vy = __ldg(dp + 1); vz = __ldg(dp + 2);
-        }
-      }
-      if (kTrain) {
-        if (r == 0) tma_store_wait_read0();
-        named_bar_sync(bar_id, 128);
-      }
-      write_pe_row<10>(pe, r, px, py, pz);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(bar_id, 128);
-      if (r == 0) {
-        act_arrive(&bar_act[slot]);
-        if (kTrain && tile_valid) {
-          tma_store_1d(stash_tile + (size_t)kStashPE * kActChunk, pe, kActChunk);
-          tma_store_commit();
-        }
-      }
-
-      float alpha_acc = 0.f;
-      float rgb_acc[3] = {0.f, 0.f, 0.f};
-
-      for (int s = 0; s < kNumSteps; ++s) {
-        long long t0 = clock64();
-        mbar_wait(&bar_acc[slot], acc_phase);
-        long long t1 = clock64();
-        t_accw += t1 - t0;
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (kTrain) {
-          if (r == 0) tma_store_wait_read0();   // earlier bulk stores finished reading act / pe
-          named_bar_sync(bar_id, 128);
-        }
-        const int ncols = (s == 9) ? 128 : 256;
-        const int bias_i = (s < 8 ? kSmBiasTrunk + 256 * s : (s == 8 ? kSmBiasFeat : kSmBiasViews));
-        uint32_t* mrow = kTrain ? reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff +
-                                                               ((size_t)(s == 9 ? 8 : s) * 128 + r) * 32)
-                                : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + lane_base + slot * 256 + c0, acc);
-          tmem_ld_wait();
-          float v[32];
-          uint32_t mword = 0;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = small4(bias_i + c0 + 4 * j4);
-            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
-            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
-            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
-            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
-          }
-          if (s != 8) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (kTrain) mword |= (v[j] > 0.f ? 1u : 0u) << mask_bit_of_column(j);
-              v[j] = fmaxf(v[j], 0.f);
-            }
-          }
-          if (kTrain && s != 8 && tile_valid) mrow[c0 >> 5] = mword;
-          if (s == 7) {  // alpha head on CUDA cores, from the fp32 activations (run_nerf_helpers.py:114)
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = small4(kSmWAlpha + c0 + 4 * j4);
-              alpha_acc += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
-            }
-          }
-          if (s == 9) {  // rgb head (run_nerf_helpers.py:122)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w = small4(kSmWRgb + ch * 128 + c0 + 4 * j4);
-                rgb_acc[ch] += v[4 * j4] * w.x + v[4 * j4 + 1] * w.y + v[4 * j4 + 2] * w.z + v[4 * j4 + 3] * w.w;
-              }
-            }
-          }
-          if (s != 9 || kTrain) {
-            // next layer's A operand (and the stash image): 32 columns = 4 x 16-byte groups of chunk c0/64
-            uint8_t* img = act + (c0 >> 6) * kActChunk;
-            const int g0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<uint4*>(img + chunk_off16(r, g0 + q)) =
-                  make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-            }
-          }
-        }
-        if (s == 8) write_pe_row<4>(pe, r, vx, vy, vz);  // PE(viewdir) replaces PE(pts): L5 has consumed it
-        if (s == 9 && valid) {
-          p.raw[g] = make_float4(rgb_acc[0] + small1(kSmBRgb), rgb_acc[1] + small1(kSmBRgb + 1),
-                                 rgb_acc[2] + small1(kSmBRgb + 2), alpha_acc + small1(kSmBAlpha));
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        t_work += clock64() - t1;
-        if (r == 0) {
-          if (s < 9) act_arrive(&bar_act[slot]);
-          if (kTrain && tile_valid) {
-            if (s < 8) {
-              for (int j = 0; j < 4; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashH + 4 * s + j) * kActChunk, act + j * kActChunk, kActChunk);
-            } else if (s == 8) {
-              for (int j = 0; j < 4; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashFeat + j) * kActChunk, act + j * kActChunk, kActChunk);
-              tma_store_1d(stash_tile + (size_t)kStashVPE * kActChunk, pe, kActChunk);
-            } else {
-              for (int j = 0; j < 2; ++j)
-                tma_store_1d(stash_tile + (size_t)(kStashHidden + j) * kActChunk, act + j * kActChunk, kActChunk);
-            }
-            tma_store_commit();
-          }
-        }
-      }
-    }
-    if (kTrain && r == 0) tma_store_wait_all0();
-    if (blockIdx.x == 0 && tid == 128) { g_prof[3] = t_accw; g_prof[4] = t_work; g_prof[5] = clock64() - t_begin; }
-  }
-}
-
-template <bool kTrain>
-__global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_acc[2], bar_act[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
-
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 1); }
-    mbar_fence_init();
-  }
-  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-        int cidx = 0;
-        for (int s = 0; s < kNumSteps; ++s) {
-          const int nch = step_nchunks(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            for (int ci = 0; ci < nch; ++ci) {
-              const int c = cidx + ci;
-              const uint32_t bytes = fwd_chunk_bytes(c);
-              mbar_wait(&bar_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&bar_full[stage], bytes);
-              tma_load_1d(smem + kSmemW + stage * kW256, p.packed + fwd_chunk_off(c), bytes, &bar_full[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-          }
-          cidx += nch;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    {
-      int stage = 0; uint32_t phase = 0; uint32_t act_phase[2] = {0, 0};
-      const uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
-      const uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
-      for (int64_t it = blockIdx.x; it < n_pairs; it += gridDim.x) {
-        for (int s = 0; s < kNumSteps; ++s) {
-          const int nch = step_nchunks(s);
-          const uint32_t idesc = (s == 9) ? idesc128 : idesc256;
-          for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait(&bar_act[slot], act_phase[slot]);
-            act_phase[slot] ^= 1;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            for (int ci = 0; ci < nch; ++ci) {
-              const int src = step_asrc(s, ci);
-              const uint32_t a_addr = smem_u32(smem) + (src == 0 ? kSmemPE + slot * kActChunk
-                                                                 : kSmemAct + slot * 4 * kActChunk + (src - 1) * kActChunk);
-              const uint32_t b_addr = smem_u32(smem) + kSmemW + stage * kW256;
-              const int ksteps = (s == 9 && ci == 4) ? 2 : 4;  // viewdir PE has 27 (<32) channels
-              mbar_wait(&bar_full[stage], phase);
-              tc_fence_after();
-              if (elect_one_sync()) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  if (kk < ksteps) {
-                    uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                    uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                    umma_bf16(d_tmem, da, db, idesc, (ci > 0 || kk > 0) ? 1u : 0u);
-                  }
-                }
-                umma_commit(&bar_empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-            if (elect_one_sync()) umma_commit(&bar_acc[slot]);
-            __syncwarp();
-          }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    forward_epilogue<kTrain, 1>(p, smem, bar_acc, bar_act, tmem_base, warp, tid, 0, blockIdx.x, n_pairs, gridDim.x, 0u);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 
@@ -963,32 +639,18 @@ int mvip_mlp_forward(const void* packed, const mvip_points* pts, float* raw, voi
   p.raw = reinterpret_cast<float4*>(raw);
   p.stash = static_cast<uint8_t*>(stash);
   p.n_tiles = mlp::num_tiles(pts->n_points);
-  if (mlp::use_cta_pairs()) {
-    const int64_t n_quads = (p.n_tiles + 3) / 4;
-    const int max_clusters = mvip_num_sms() / 2;
-    const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
-    const size_t smem2 = (stash ? kSmemBytes2Train : kSmemBytes2Infer) + 1024;
-    if (stash) {
-      MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<true>, smem2);
-      mlp_forward_pair_kernel<true><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
-    } else {
-      MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<false>, smem2);
-      mlp_forward_pair_kernel<false><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
-    }
-    MVIP_LAUNCH_OK("mlp_forward_pair_kernel");
-    return MVIP_OK;
-  }
-  const int64_t n_pairs = (p.n_tiles + 1) / 2;
-  const int grid = (int)(n_pairs < mvip_num_sms() ? n_pairs : mvip_num_sms());
-  const size_t smem = kSmemBytes + 1024;
+  const int64_t n_quads = (p.n_tiles + 3) / 4;
+  const int max_clusters = mvip_num_sms() / 2;
+  const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
+  const size_t smem2 = (stash ? kSmemBytes2Train : kSmemBytes2Infer) + 1024;
   if (stash) {
-    MVIP_SMEM_OPT_IN(mlp_forward_kernel<true>, smem);
-    mlp_forward_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<true>, smem2);
+    mlp_forward_pair_kernel<true><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
   } else {
-    MVIP_SMEM_OPT_IN(mlp_forward_kernel<false>, smem);
-    mlp_forward_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    MVIP_SMEM_OPT_IN(mlp_forward_pair_kernel<false>, smem2);
+    mlp_forward_pair_kernel<false><<<grid2, kThreads2, smem2, (cudaStream_t)stream>>>(p);
   }
-  MVIP_LAUNCH_OK("mlp_forward_kernel");
+  MVIP_LAUNCH_OK("mlp_forward_pair_kernel");
   return MVIP_OK;
 }
 

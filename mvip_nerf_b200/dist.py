@@ -6,9 +6,10 @@ renders its contiguous slice of the ray batch with no data-path communication, a
 
   * a render ends with ONE gather of (rgb, disp, acc, depth) = 24 B/ray to rank 0;
   * a training step ends with ONE sum-allreduce per network of the flattened fp32 parameter gradients
-    (2 x 595,844 x 4 B = 4.77 MB) over NCCL/NVLink; the fine network's allreduce is issued as soon as
-    its gradients exist, so it overlaps the coarse network's backward when autograd runs them in
-    sequence (the two branches are independent: z_samples is detached, run.py:1812).
+    (2 x 595,844 x 4 B = 4.77 MB) over NCCL/NVLink.  allreduce_grads() issues both after the backward pass;
+    GradSync issues each network's bucket from a post-accumulate-grad hook the moment its 24 gradients exist, so
+    the fine network's allreduce overlaps the coarse network's backward (autograd runs the fine branch first and the
+    two branches are independent: z_samples is detached, run.py:1812) — also inside a captured CUDA graph.
 
 The host logic is backend-agnostic (gloo on CPU tensors in tests/, nccl on the GPU box).
 """
@@ -288,6 +289,49 @@ class GradAllReducer:
                     p.grad.copy_(g)
                 off += n
         self.handle, self.flat = None, None
+
+
+class GradSync:
+    """Gradient allreduce overlapped with the backward pass: one bucket per network, started from
+    post-accumulate-grad hooks as soon as ALL gradients of that network have been accumulated; finish() joins them
+    (and starts the buckets of networks that received no gradient, so every rank issues the same collectives).
+
+        sync = GradSync([fine_params, coarse_params])
+        loss.backward(); sync.finish(); optimizer.step()
+    """
+
+    def __init__(self, param_groups):
+        self.groups = [list(ps) for ps in param_groups]
+        self.reducers = [GradAllReducer(ps) for ps in self.groups]
+        self.count = [0] * len(self.groups)
+        self.started = [False] * len(self.groups)
+        self.hooks = []
+        for gi, ps in enumerate(self.groups):
+            for p in ps:
+                self.hooks.append(p.register_post_accumulate_grad_hook(lambda _p, gi=gi: self._on_grad(gi)))
+
+    def _on_grad(self, gi):
+        self.count[gi] += 1
+        if self.count[gi] == len(self.groups[gi]):
+            self.count[gi] = 0
+            if world() > 1 and not self.started[gi]:
+                self.reducers[gi].start()
+                self.started[gi] = True
+
+    def finish(self):
+        if world() > 1:
+            for gi, r in enumerate(self.reducers):
+                if not self.started[gi]:
+                    r.start()
+            for r in self.reducers:
+                r.finish()
+        self.count = [0] * len(self.groups)
+        self.started = [False] * len(self.groups)
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
 
 
 def allreduce_grads(param_groups):

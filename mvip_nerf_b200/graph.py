@@ -5,12 +5,15 @@ A cfg-2 step is ~45 kernel launches, 16 of them ours; the three MLP kernels take
 5-20 us kernels whose launch gaps — and, end to end, the Python that issues them after every `loss.item()` — add up to
 ~10 % of the step.  GraphedTrainStep captures
 
-    graph A: rays -> render() -> loss -> backward                      (fresh random draws on every replay: torch registers the
-                                                                        CUDA generator with the graph and advances its offset)
-    eager  : gradient allreduce (N > 1 only; NCCL stays outside the graphs)
-    graph B: Adam (lr and step number read from device memory) -> re-pack of the bf16 weight blobs
+    rays -> render() -> loss -> backward      (fresh random draws on every replay: torch registers the CUDA generator with
+                                               the graph and advances its offset)
+         -> gradient allreduce (N > 1)        one NCCL bucket per network, issued by dist.GradSync from a post-accumulate-grad
+                                               hook the moment a network's gradients exist: the fine network's bucket runs on
+                                               NCCL's stream while the coarse network's backward is still computing
+         -> Adam (lr and step number read from device memory) -> re-pack of the bf16 weight blobs
 
-once, after warm-up, and replays them.  Inputs live in static buffers; `__call__(rays, target)` copies into them (from pinned
+as ONE graph, once, after warm-up, and replays it.  (`nccl_in_graph=False` keeps the collectives out of the capture: graph A =
+render + loss + backward, eager allreduce, graph B = Adam + re-pack.)  Inputs live in static buffers; `__call__(rays, target)` copies into them (from pinned
 host memory for the end-to-end path) and returns the loss as a device scalar.  Same arithmetic as the eager step: the captured
 launches ARE the eager step's launches.
 """
@@ -31,7 +34,7 @@ def default_loss(rgb, disp, acc, depth, extras, target, scale):
 
 class GraphedTrainStep:
     def __init__(self, render_kwargs_train, optimizer, H, W, focal, n_rays, near=None, far=None, chunk=1024 * 32, loss_fn=default_loss,
-                 target_shape=None, warmup=3, device=None):
+                 target_shape=None, warmup=3, device=None, nccl_in_graph=True):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a CUDA device (no CPU fallback)")
         self.kw = dict(render_kwargs_train)
@@ -54,6 +57,8 @@ class GraphedTrainStep:
         self.warmup = warmup
         self.graph_a = self.graph_b = None
         self.loss = None
+        self.one_graph = bool(nccl_in_graph) or mdist.world() == 1
+        self.sync = mdist.GradSync(self.groups) if (self.one_graph and mdist.world() > 1) else None
 
     # -- the two halves of the step, exactly as the eager loop runs them -----------------------------------------------
     def _forward_backward(self):
@@ -62,17 +67,19 @@ class GraphedTrainStep:
         rgb, disp, acc, depth, extras = run.render(H, W, focal, chunk=self.chunk, rays=self.rays, near=self.near, far=self.far,
                                                    **self.kw)
         loss = self.loss_fn(rgb, disp, acc, depth, extras, self.target, self.scale)
-        loss.backward()
+        loss.backward()                 # GradSync hooks (if any) start each network's allreduce as its gradients complete
+        if self.sync is not None:
+            self.sync.finish()
         return loss.detach()
 
     def _update(self):
         self.opt.step_captured()
         for net in self.nets:                 # refresh the bf16 operand blobs the next forward reads
-            net._packed = ops.mlp_pack(net._ordered_params(), out=net._packed)
+            net.repack()
 
     def _mark_packed_fresh(self):
         for net in self.nets:
-            net._packed_key = (ops.param_epoch,) + tuple((p.data_ptr(), p._version) for p in net._ordered_params())
+            net._packed_key = net._pack_key(net._ordered_params())
 
     def capture(self):
         """Warm-up on a side stream (allocator pools, lazy module loads, smem opt-ins), then capture both graphs.  Parameters,
@@ -89,17 +96,25 @@ class GraphedTrainStep:
         with torch.cuda.stream(s):
             for _ in range(self.warmup):
                 self._forward_backward()
-                mdist.allreduce_grads(self.groups)
+                if self.sync is None:
+                    mdist.allreduce_grads(self.groups)
                 self._update()
                 self._mark_packed_fresh()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.graph_a = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
-            self.loss = self._forward_backward()
-        self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
-            self._update()
+        if self.one_graph:
+            # NCCL's watchdog thread polls CUDA events while we capture: keep the capture thread-local
+            mode = {"capture_error_mode": "thread_local"} if mdist.world() > 1 else {}
+            with torch.cuda.graph(self.graph_a, **mode):
+                self.loss = self._forward_backward()
+                self._update()
+        else:
+            with torch.cuda.graph(self.graph_a):
+                self.loss = self._forward_backward()
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+                self._update()
         with torch.no_grad():       # capture executes nothing; undo the warm-up steps
             for p, (w, m, v) in zip(params, snap):
                 p.copy_(w)
@@ -107,7 +122,7 @@ class GraphedTrainStep:
                 self.opt.state[p]["exp_avg_sq"].copy_(v)
             self.opt._g_step.copy_(step0)
             for net in self.nets:
-                net._packed = ops.mlp_pack(net._ordered_params(), out=net._packed)
+                net.repack()
         self._mark_packed_fresh()
         self._params = params
         self._static_grads = [p.grad for p in params]      # the buffers graph A writes and graph B / the allreduce read
@@ -127,7 +142,8 @@ class GraphedTrainStep:
                 p.grad = g
         self.opt.graph_set_lr()
         self.graph_a.replay()
-        mdist.allreduce_grads(self.groups)
-        self.graph_b.replay()
+        if self.graph_b is not None:
+            mdist.allreduce_grads(self.groups)
+            self.graph_b.replay()
         self.opt._g_dirty = True        # python-side step counts are refreshed lazily (FusedAdam.sync_graph_steps)
         return self.loss

@@ -67,6 +67,14 @@ def _f32(t, name):
     return t.contiguous()
 
 
+def _rows3(t, name):
+    """[N, >=3] fp32 CUDA rows read through a row stride (e.g. the rays_d columns of the ray batch): no copy."""
+    if t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] > 0:
+        return t, t.stride(0)
+    t = _f32(t, name)
+    return t, t.shape[-1]
+
+
 def _call(name, *args):
     global launch_count
     lib = _lib.load()
@@ -176,7 +184,7 @@ def sample_fine(z_vals, weights, u, want_samples=True, want_inds=False, want_std
 def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_alpha=False):
     raw = _f32(raw, "raw")
     z_vals = _f32(z_vals, "z_vals")
-    rays_d = _f32(rays_d, "rays_d")
+    rays_d, d_stride = _rows3(rays_d, "rays_d")
     noise = _f32(noise, "noise")
     N, S = z_vals.shape
     dev = raw.device
@@ -186,7 +194,7 @@ def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_al
     depth = torch.empty((N,), device=dev, dtype=torch.float32)
     weights = torch.empty((N, S), device=dev, dtype=torch.float32)
     alpha = torch.empty((N, S), device=dev, dtype=torch.float32) if need_alpha else None
-    _call("mvip_composite_forward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), rays_d.shape[-1], _ptr(noise), N, S,
+    _call("mvip_composite_forward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(noise), N, S,
           int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(weights), _ptr(depth), _ptr(alpha), _stream())
     return rgb, disp, acc, weights, depth, alpha
 
@@ -195,11 +203,11 @@ def composite_backward(raw, z_vals, rays_d, noise, white_bkgd, detach_weights, g
                        g_weights=None, g_alpha=None):
     raw = _f32(raw, "raw")
     z_vals = _f32(z_vals, "z_vals")
-    rays_d = _f32(rays_d, "rays_d")
+    rays_d, d_stride = _rows3(rays_d, "rays_d")
     N, S = z_vals.shape
     d_raw = torch.empty((N, S, 4), device=raw.device, dtype=torch.float32)
     args = [_f32(t, "grad") for t in (g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha)]
-    _call("mvip_composite_backward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), rays_d.shape[-1], _ptr(_f32(noise, "noise")),
+    _call("mvip_composite_backward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(_f32(noise, "noise")),
           N, S, int(bool(white_bkgd)), int(bool(detach_weights)), *[_ptr(a) for a in args], _ptr(d_raw), _stream())
     return d_raw
 
@@ -340,9 +348,10 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
     P = d_raw.shape[0]
     dev = d_raw.device
     if grads is None:
-        # one flat buffer, 24 views; the reduce kernel overwrites every element when accumulate == 0
+        # one flat buffer, 24 views
         sizes = [int(torch.Size(shp).numel()) for shp in PARAM_SHAPES]
-        flat = torch.empty((sum(sizes),), device=dev, dtype=torch.float32)
+        # the reduce kernel overwrites every element — except for an empty batch, which launches nothing
+        flat = (torch.zeros if P == 0 else torch.empty)((sum(sizes),), device=dev, dtype=torch.float32)
         grads, off = [], 0
         for shp, n in zip(PARAM_SHAPES, sizes):
             grads.append(flat[off:off + n].view(shp))
@@ -350,10 +359,8 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-    if kernel_timer.on:   # one bracket per launch: fused dgrad chain + wgrad (or the two separately), head grads, reduce
-        fused = os.environ.get("MVIP_BWD_FUSED", "0") == "1" and os.environ.get("MVIP_MLP_CTA_PAIRS", "1") != "0"
-        first = ((3, "backward_fused_kernel"),) if fused else ((1, "dgrad_chain_kernel"), (2, "wgrad_kernel"))
-        for bit, label in first + ((4, "head_grads_kernel"), (8, "reduce_kernel")):
+    if kernel_timer.on:   # one bracket per launch: dgrad chain, wgrad, head grads, reduce
+        for bit, label in ((1, "dgrad_pair_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
             _call(("mvip_mlp_backward_phases", label), _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr,
                   int(bool(accumulate)), bit, _stream())
     else:

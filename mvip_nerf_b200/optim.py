@@ -69,6 +69,9 @@ class FusedAdam(torch.optim.Adam):
 
     def graph_begin(self, device):
         """Before capture: materialise the state tensors and seed the device step counter from the python-side count."""
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedAdam CUDA-graph form keeps ONE device-resident (lr, step) pair: use a single param group "
+                               "(create_nerf builds one, run.py:1536)")
         steps = set()
         for group in self.param_groups:
             for p in group["params"]:

@@ -96,31 +96,29 @@ def _is_number(x):
     return isinstance(x, (int, float)) or (isinstance(x, np.generic) and np.ndim(x) == 0)
 
 
-def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
-           c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
-    """(run.py:1143-1219) -> [rgb_map, disp_map, acc_map, depth_map, extras].
+def _clip_patch(patch, H, W):
+    """(i, j, len1, len2) clipped to the image the way the reference's slicing rays_o[i:i+len1, j:j+len2] clips (run.py:1174)."""
+    i, j, len1, len2 = [int(v) for v in patch]
+    i, j = max(0, min(i, H)), max(0, min(j, W))
+    return i, j, max(0, min(i + len1, H) - i), max(0, min(j + len2, W) - j)
 
-    The ray batch [N, 8|11] is written by ONE kernel (get_rays / patch / viewdir normalisation / ndc_rays / near / far /
-    cat): mvip_rays_from_pose for `c2w=`, mvip_rays_pack for `rays=`.  Only the `depths=` column (used by the out-of-scope
-    sigma loss) and non-scalar near / far / focal take the elementwise torch route below."""
+
+def _assemble_rays(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, depths, patch):
+    """The ray-batch assembly of render() (run.py:1171-1207) -> (rays_flat [N, 8|9|11|12], sh).
+
+    The batch is written by ONE kernel (get_rays / patch / viewdir normalisation / ndc_rays / near / far / cat):
+    mvip_rays_from_pose for `c2w=`, mvip_rays_pack for `rays=`.  Only the `depths=` column (used by the out-of-scope sigma
+    loss), non-scalar near / far / focal and `rays=` combined with a static camera take the elementwise torch route."""
     fusable = depths is None and torch.cuda.is_available() and _is_number(near) and _is_number(far) and _is_number(focal)
-    rays_flat = None
     if fusable and c2w is not None:
-        if patch is not None and (patch[0] + patch[2] > H or patch[1] + patch[3] > W):
-            raise RuntimeError("patch outside the image")
+        if patch is not None:
+            patch = _clip_patch(patch, H, W)
         rays_flat = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2w_staticcam,
                                        patch=patch, ndc=ndc)
-        sh = ((H, W) if patch is None else (int(patch[2]), int(patch[3]))) + (3,)
-    elif fusable and c2w is None and (c2w_staticcam is None or not use_viewdirs):
+        return rays_flat, ((H, W) if patch is None else (patch[2], patch[3])) + (3,)
+    if fusable and c2w is None and (c2w_staticcam is None or not use_viewdirs):
         rays_o, rays_d = rays
-        sh = rays_d.shape
-        rays_flat = ops.rays_pack(rays_o, rays_d, near, far, use_viewdirs=use_viewdirs, ndc=ndc, H=H, W=W, focal=focal)
-    if rays_flat is not None:
-        all_ret = batchify_rays(rays_flat, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
-        for k in all_ret:
-            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
-        k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
-        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+        return ops.rays_pack(rays_o, rays_d, near, far, use_viewdirs=use_viewdirs, ndc=ndc, H=H, W=W, focal=focal), rays_d.shape
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, focal, c2w)
         if patch is not None:
@@ -147,11 +145,22 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
         cols.append(depths.reshape(-1, 1).to(rays_d))
     if use_viewdirs:
         cols.append(viewdirs)
-    all_ret = batchify_rays(torch.cat(cols, -1), chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+    return torch.cat(cols, -1), sh
+
+
+def _split_outputs(all_ret, sh):
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
+    """(run.py:1143-1219) -> [rgb_map, disp_map, acc_map, depth_map, extras]."""
+    rays_flat, sh = _assemble_rays(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, depths, patch)
+    all_ret = batchify_rays(rays_flat, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+    return _split_outputs(all_ret, sh)
 
 
 def create_nerf(args):
@@ -407,23 +416,12 @@ def render_deferred(H, W, focal, chunk=1024 * 8, rays=None, c2w=None, ndc=True, 
     `chunk` is the number of rays whose activations exist at any one time during backward (default 8192: 16 GB)."""
     if depths is not None:
         raise NotImplementedError("render_deferred: the depths column (sigma loss) is out of scope")
-    if c2w is not None:
-        if patch is not None and (patch[0] + patch[2] > H or patch[1] + patch[3] > W):
-            raise RuntimeError("patch outside the image")
-        rays_flat = ops.rays_from_pose(H, W, focal, c2w, near, far, use_viewdirs=use_viewdirs, c2w_staticcam=c2w_staticcam,
-                                       patch=patch, ndc=ndc)
-        sh = ((H, W) if patch is None else (int(patch[2]), int(patch[3]))) + (3,)
-    else:
-        rays_o, rays_d = rays
-        sh = rays_d.shape
-        rays_flat = ops.rays_pack(rays_o, rays_d, near, far, use_viewdirs=use_viewdirs, ndc=ndc, H=H, W=W, focal=focal)
+    rays_flat, sh = _assemble_rays(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, None, patch)
     kw = dict(kwargs, need_alpha=need_alpha, detach_weights=detach_weights)
     params = [p for _, ps in _net_params(kwargs) for p in ps]
     holder = {}
     outs = _DeferredRays.apply(rays_flat, int(chunk), kw, holder, *params)
-    all_ret = {k: torch.reshape(v, list(sh[:-1]) + list(v.shape[1:])) for k, v in zip(holder["keys"], outs)}
-    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
-    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+    return _split_outputs(dict(zip(holder["keys"], outs)), sh)
 
 
 # ---------------------------------------------------------------------------------------------------

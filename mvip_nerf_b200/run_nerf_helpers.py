@@ -86,6 +86,7 @@ class _MLPFunction(torch.autograd.Function):
             raw, stash = ops.mlp_forward(packed, want_stash=True, **kw)
             ctx.stash = stash
             ctx.packed = packed
+            ctx.net, ctx.pack_gen = net, net._pack_gen
         else:
             raw = ops.mlp_forward(packed, **kw)
         ctx.need_grad = need_grad
@@ -97,6 +98,11 @@ class _MLPFunction(torch.autograd.Function):
     def backward(ctx, d_raw):
         if not ctx.need_grad or d_raw is None:
             return (None,) * (6 + ctx.n_params)
+        if ctx.net._pack_gen != ctx.pack_gen:
+            # the bf16 blob is shared and re-packed in place: dgrad would silently use the NEW weights (stock torch raises
+            # its version-counter error in the same situation)
+            raise RuntimeError("NeRF weights were re-packed (optimizer step / load_state_dict / invalidate_packed) between "
+                               "this forward and its backward; run backward before changing the parameters")
         grads = ops.mlp_backward(ctx.packed, d_raw.contiguous(), ctx.stash)
         ctx.stash = None
         return (None, None, None, None, None, None) + tuple(grads)
@@ -131,19 +137,38 @@ class NeRF(nn.Module):
         self.rgb_linear = nn.Linear(W // 2, 3)
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0          # bumped by every re-pack; _MLPFunction checks it between forward and backward
 
-    # -- packed bf16 weights, rebuilt whenever a parameter changed (optimizer step, load_state_dict) --
+    # -- packed bf16 weights ------------------------------------------------------------------------------------
+    # The kernels read a bf16 operand blob, rebuilt lazily whenever a parameter is SEEN to have changed: torch's version
+    # counters (optimizer.step, load_state_dict, p.copy_, .to()) or FusedAdam's epoch.  Writes that bypass both —
+    # `p.data.copy_(w)`, `lin.weight.data = ...` keeping the same storage, raw-pointer writers — are invisible: call
+    # invalidate_packed() after them.
     def _ordered_params(self):
         sd = dict(self.named_parameters())
         return [sd[n] for n in ops.PARAM_ORDER]
 
+    def _pack_key(self, params):
+        return (ops.param_epoch,) + tuple((p.data_ptr(), p._version) for p in params)
+
     def packed(self):
         params = self._ordered_params()
-        key = (ops.param_epoch,) + tuple((p.data_ptr(), p._version) for p in params)
+        key = self._pack_key(params)
         if self._packed is None or key != self._packed_key:
-            self._packed = ops.mlp_pack(params, out=self._packed)
-            self._packed_key = key
+            self.repack(params)
         return self._packed
+
+    def repack(self, params=None):
+        """Rebuilds the bf16 blob from the current parameter values now (one launch, in place: CUDA-graph safe)."""
+        params = self._ordered_params() if params is None else params
+        self._packed = ops.mlp_pack(params, out=self._packed)
+        self._packed_key = self._pack_key(params)
+        self._pack_gen += 1
+        return self._packed
+
+    def invalidate_packed(self):
+        """Call after writing parameters behind torch's back (`.data.copy_`, EMA / weight surgery through raw pointers)."""
+        self._packed_key = None
 
     def _need_grad(self, params):
         return torch.is_grad_enabled() and any(p.requires_grad for p in params)
@@ -180,6 +205,7 @@ class NeRF(nn.Module):
         put(self.views_linears[0], 2 * self.D + 2)
         put(self.rgb_linear, 2 * self.D + 4)
         put(self.alpha_linear, 2 * self.D + 6)
+        self.invalidate_packed()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,9 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference (MVIP-NeRF DS_NeRF) on CPU.
+"""TEST / BENCH INFRASTRUCTURE ONLY — loads the *unmodified* reference (MVIP-NeRF DS_NeRF).
 
-Only usable in the build container where /root/reference exists; used by
-oracle/make_golden.py to generate tests/golden/*.npz and by the optional
-container-only tests that pin oracle/nerf_oracle.py against the reference.
-Nothing on the product path (mvip_nerf_b200/) may import this module.
+Looks for the tree at $MVIP_REFERENCE_ROOT, /root/reference (build container) or oracle/_ref (the byte-for-byte copy
+`__graft_entry__.build()` stages with oracle/stage_ref.py so that it travels to the GPU box).  Used by
+oracle/make_golden*.py to generate tests/golden/*.npz, by bench.py's `--impl reference` arm / `cpu_baseline` leg and
+by tests/test_gpu_insitu.py.  Nothing on the product path (mvip_nerf_b200/) may import this module.
 
 The reference's run.py imports six modules that do no arithmetic on the hot path
 (matplotlib, imageio, tkinter, lpips, tinycudann, configargparse — SURVEY.md §0.4);
@@ -13,7 +13,16 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MVIP_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    cands = [os.environ.get("MVIP_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "DS_NeRF", "run.py")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 REF_DIR = os.path.join(REF_ROOT, "DS_NeRF")
 
 _STUBS = ["matplotlib", "matplotlib.pyplot", "imageio", "tkinter", "lpips",

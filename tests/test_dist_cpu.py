@@ -146,6 +146,41 @@ def _guidance_worker(rank, world, port):
     dist.destroy_process_group()
 
 
+def _gradsync_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from mvip_nerf_b200 import dist as md
+    md.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    fine, coarse, unused = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3), torch.nn.Linear(2, 2)
+    groups = [list(fine.parameters()), list(coarse.parameters()), list(unused.parameters())]
+    sync = md.GradSync(groups)
+    x = torch.arange(20, dtype=torch.float32).view(4, 5) / 10 + rank
+    for step in range(2):                       # second step: hooks re-arm, .grad accumulates in place
+        for ps in groups:
+            for p in ps:
+                p.grad = None
+        loss = (fine(x) ** 2).mean() * (step + 1) + coarse(x).sum() * 0.5
+        loss.backward()
+        assert sync.started[:2] == [True, True] and not sync.started[2]      # issued from the hooks, before finish()
+        sync.finish()
+        want = []
+        for r in range(world):
+            xr = torch.arange(20, dtype=torch.float32).view(4, 5) / 10 + r
+            want.append(torch.autograd.grad((fine(xr) ** 2).mean() * (step + 1) + coarse(xr).sum() * 0.5,
+                                            groups[0] + groups[1]))
+        for i, p in enumerate(groups[0] + groups[1]):
+            torch.testing.assert_close(p.grad, sum(w[i] for w in want), rtol=1e-6, atol=1e-6)
+        for p in groups[2]:                     # a network without gradients still takes part: zeros
+            assert p.grad is not None and float(p.grad.abs().max()) == 0.0
+    sync.remove()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_gradsync_overlapped_buckets():
+    mp.spawn(_gradsync_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 def test_world2_gloo_sharded_guidance_views_with_gradients():
     mp.spawn(_guidance_worker, args=(2, _free_port()), nprocs=2, join=True)
 

@@ -278,38 +278,3 @@ def test_mlp_backward_is_linear_and_deterministic_at_full_size(ops):
     torch.testing.assert_close(g1[21], d1[:, 3:].sum(0), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.gpu
-def test_fused_backward_matches_separate_kernels():
-    """MVIP_BWD_FUSED=1 (dgrad chain and tile-major wgrad concurrently in one launch, dZ handed over through L2 with
-    per-(tile, group) flags) must give the same gradients as the two stand-alone kernels: the chain is identical and the
-    wgrad sums only differ in how tiles are grouped into fp32 partials."""
-    import os, subprocess, sys, textwrap
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = textwrap.dedent("""
-        import sys, numpy as np, torch
-        sys.path.insert(0, %r)
-        from mvip_nerf_b200 import ops
-        from oracle import nerf_oracle as orc
-        dev = "cuda"
-        p = orc.init_params(1)
-        blob = ops.mlp_pack([torch.from_numpy(p[n]).to(dev) for n in ops.PARAM_ORDER])
-        g = torch.Generator(device=dev).manual_seed(3)
-        P = 128 * 148 * 4 + 77
-        pts = torch.rand(P, 3, device=dev, generator=g) * 4 - 2
-        dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g), dim=-1)
-        raw, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
-        d = torch.randn(P, 4, device=dev, generator=g)
-        grads = ops.mlp_backward(blob, d, stash)
-        np.save(sys.argv[1], torch.cat([x.flatten() for x in grads]).cpu().numpy())
-    """ % root)
-    import tempfile
-    with tempfile.TemporaryDirectory() as td:
-        outs = []
-        for fused in ("0", "1"):
-            env = dict(os.environ, MVIP_BWD_FUSED=fused)
-            out = os.path.join(td, "g%s.npy" % fused)
-            subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
-            outs.append(np.load(out))
-    a, b = outs
-    assert np.isfinite(b).all()
-    assert np.abs(a - b).max() <= 2e-4 * np.abs(a).max() + 1e-6
