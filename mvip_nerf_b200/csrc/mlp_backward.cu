@@ -49,8 +49,8 @@ constexpr int kDThreads = 640;
 constexpr int kDSlots = 10, kDLag = 2;                                   // groups have 2 or 4 slots: 4 + 4 <= 10
 constexpr uint32_t kDSmemHeads = 0;                                      // w_alpha[256], W_rgb[3][128] fp32 (2,560 B)
 constexpr uint32_t kDSmemW = 3072;                                       // weight ring
-constexpr uint32_t kDSmemStg = kDSmemW + kDSlots * kSlotBytes2;          // staging: [slot][buffer] x 2 chunk images
-constexpr uint32_t kDSmemBytes = kDSmemStg + 2 * 2 * 2 * kActChunk;      // 216,064
+constexpr uint32_t kDSmemStg = kDSmemW + kDSlots * kSlotBytes2;          // staging: two 4 KB pieces (32 rows of a dZ chunk image) per epilogue warp
+constexpr uint32_t kDSmemBytes = kDSmemStg + 16 * 2 * 4096;              // 216,064
 constexpr int kDGroupsPerIter = 18;
 
 // first_it / it_stride: this cluster's first tile quad and the number of clusters working on the chain
@@ -92,21 +92,12 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
     reg_inc<104>();
     const int T = warp >> 3, q = warp & 3, ch = (warp & 7) >> 2;
     const int r = q * 32 + lane;
-    const bool leader = (warp & 7) == 0 && lane == 0;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t tA = tmem_base + lane_base + T * 256;
     const uint32_t tD = tA + 128 + ch * 64;
-    const uint32_t bar_id = 1 + T;
     const uint32_t heads_a = smem_u32(smem + kDSmemHeads);
-    uint8_t* stg_slot = smem + kDSmemStg + T * 4 * kActChunk;
+    uint8_t* stg = smem + kDSmemStg + warp * 2 * 4096;      // this warp's two 4 KB staging pieces
     uint32_t acc_phase = 0, stg_buf = 0;
-    // leader only: flags of the six most recent bulk stores, not yet published (FIFO in shared memory, newest at [0]).
-    // A flag goes out once cp.async.bulk.wait_group 5 shows its store to be COMPLETE; waiting with so much slack never stalls
-    // (a store issued six stage_out calls = ~7 us earlier has long been written), unlike a wait on the previous store.
-    __shared__ uint32_t* flag_fifo_s[2][6];
-    uint32_t** flag_fifo = flag_fifo_s[T];
-    if (leader) { for (int i = 0; i < 6; ++i) flag_fifo[i] = nullptr; }
-
     auto act_arrive = [&]() {
       __syncwarp();
       if (lane == 0) {
@@ -130,31 +121,21 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
       uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
 
-      // packed bf16 rows of both column halves -> staging images (double-buffered) -> one 32 KB bulk store into the dZ stash
-      // flag_id >= 0: this store completes dZ group `flag_id` of the tile.  The flag is published two calls later, when
-      // cp.async.bulk.wait_group 1 has shown the store to be complete (written), not merely read out of shared memory.
-      auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32], int flag_id) {
-        uint8_t* buf = stg_slot + stg_buf * 2 * kActChunk;
+      // This warp's 32 packed bf16 rows (64 features of dZ chunk `chunk`) -> one of its two 4 KB staging pieces -> one bulk
+      // store into the dZ stash.  Warp-local and double-buffered: no named barrier, and the store issued two calls ago is the
+      // only one that has to have left shared memory.
+      auto stage_out = [&](int chunk, const uint32_t (&pk)[32]) {
+        uint8_t* buf = stg + stg_buf * 4096;
         stg_buf ^= 1;
-        if (leader) {
-          tma_store_wait_read1();               // the store issued two calls ago has finished reading this buffer
-          if (p.flags) {
-            tma_store_wait_all5();              // the store issued six calls ago is complete
-            if (flag_fifo[5]) { fence_proxy_async_all(); st_release_gpu(flag_fifo[5], 1u); }
-#pragma unroll
-            for (int i = 5; i > 0; --i) flag_fifo[i] = flag_fifo[i - 1];
-            flag_fifo[0] = (flag_id >= 0 && tile_valid) ? p.flags + (size_t)tile * kFlagsPerTile + flag_id : nullptr;
-          }
-        }
-        named_bar_sync(bar_id, 256);
-        uint8_t* img = buf + ch * kActChunk;
+        if (lane == 0) tma_store_wait_read1();
+        __syncwarp();
 #pragma unroll
         for (int gq = 0; gq < 8; ++gq)
-          *reinterpret_cast<uint4*>(img + chunk_off16(r, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+          *reinterpret_cast<uint4*>(buf + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 256);
-        if (leader) {
-          if (tile_valid) tma_store_1d(dz_tile + (size_t)first_chunk * kActChunk, buf, 2 * kActChunk);
+        __syncwarp();
+        if (lane == 0) {
+          if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk + q * 4096, buf, 4096);
           tma_store_commit();                   // (possibly empty) group: keeps the wait_group accounting uniform
         }
       };
@@ -162,7 +143,7 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
       uint32_t pk[32];
       const float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
       {  // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0] -> A columns [0,64) (K = 128) of step 0
-        const uint2 mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + ((size_t)8 * 128 + r) * 8 + 2 * ch)) : make_uint2(0u, 0u);
+        const uint2 mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8, r, 0, ch))) : make_uint2(0u, 0u);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int c0 = ch * 64 + 16 * b;
@@ -186,7 +167,7 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
         tmem_st_wait();
         tc_fence_before();
         act_arrive();                           // step 0 may start
-        stage_out(kDzHidden, pk, 0);
+        stage_out(kDzHidden + ch, pk);
       }
 
 #pragma unroll 1
@@ -196,7 +177,7 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint2 mw = make_uint2(~0u, ~0u);
-          if (s >= 1) mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + ((size_t)(8 - s) * 128 + r) * 8 + 2 * (2 * h + ch))) : make_uint2(0u, 0u);
+          if (s >= 1) mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8 - s, r, h, ch))) : make_uint2(0u, 0u);
           else if (!valid) mw = make_uint2(0u, 0u);
           {
             uint32_t raw[4][16];
@@ -237,18 +218,11 @@ __device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int6
             tc_fence_before();
             hi_arrive();                        // A[128,256) ready
           }
-          stage_out(first_chunk + 2 * h, pk, h == 1 ? 1 + s : -1);
+          stage_out(first_chunk + 2 * h + ch, pk);
         }
       }
     }
-    if (leader) {
-      tma_store_wait_all0();
-      if (p.flags) {
-        fence_proxy_async_all();
-        for (int i = 5; i >= 0; --i)
-          if (flag_fifo[i]) st_release_gpu(flag_fifo[i], 1u);
-      }
-    }
+    if (lane == 0) tma_store_wait_all0();
   } else {
     reg_dec<64>();
     if (warp == 16) {

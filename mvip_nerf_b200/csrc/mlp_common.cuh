@@ -52,8 +52,9 @@ struct GradPtrs {
 
 // ---- forward stash (per 128-point tile) ---------------------------------------------------------
 // chunk images, 16 KB each: 0 = PE(pts); 1+4(l-1)+j = h_l chunk j (l = 1..8); 33..36 = feature;
-// 37 = PE(viewdir); 38,39 = hidden (views layer output).  Then ReLU bit masks:
-// [9 layers][128 rows][8 x u32] (layer 8 = hidden, 4 words used).
+// 37 = PE(viewdir); 38,39 = hidden (views layer output).  Then ReLU bit masks, 4 KB per layer (layer 8 = hidden):
+// [9 layers][2 column halves ch][128 rows][2 N-halves h][2 x u32]: the two words cover the 64 columns 128 h + 64 ch + [0, 64)
+// (layer 8 has h = 0 only).  One epilogue warp owns (ch, 32 rows): a contiguous 512 B piece.
 constexpr int kStashChunks = 40;
 constexpr int kStashPE = 0, kStashH = 1, kStashFeat = 33, kStashVPE = 37, kStashHidden = 38;
 constexpr size_t kStashMaskOff = (size_t)kStashChunks * kActChunk;
@@ -69,6 +70,9 @@ constexpr size_t kDzTileBytes = (size_t)kDzChunks * kActChunk;
 // ReLU mask word layout: bit of column j (0..31) inside its 32-column mask word.  The forward epilogue derives
 // the bits from packed bf16 pairs of two 16-column blocks, hence the interleave.
 __host__ __device__ inline int mask_bit_of_column(int j) { return 16 * (j & 1) + 8 * (j >> 4) + ((j & 15) >> 1); }
+
+// u32 index of the two mask words of (layer, row r, N-half h, column half ch) inside a tile's mask block
+__host__ __device__ inline int mask_word_index(int layer, int r, int h, int ch) { return layer * 1024 + ch * 512 + r * 4 + h * 2; }
 
 inline int64_t num_tiles(int64_t n_points) { return (n_points + kTile - 1) / kTile; }
 

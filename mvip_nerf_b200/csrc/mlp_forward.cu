@@ -171,9 +171,9 @@ constexpr uint32_t kSmemPE2 = 0;                                         // pe[2
 constexpr uint32_t kSmemSmall2 = 2 * kActChunk;                          // fp32 tail of the packed blob (12,320 B)
 constexpr uint32_t kSmemXch2 = kSmemSmall2 + ((kSmallFloats * 4 + 1023) / 1024) * 1024;   // head partials, 2 x 2 KB
 constexpr uint32_t kSmemW2 = kSmemXch2 + 2 * 2048;                       // weight ring
-constexpr uint32_t kSmemStg2 = kSmemW2 + Ring2<true>::kSlots * kSlotBytes2;   // stash staging: 2 slots x 2 chunk images (train)
-constexpr uint32_t kSmemMask2 = kSmemStg2 + 4 * kActChunk;               // ReLU-mask staging: [slot][step parity] x 4 KB (train)
-constexpr uint32_t kSmemBytes2Train = kSmemMask2 + 2 * 2 * 4096;         // 230,400
+constexpr uint32_t kSmemStg2 = kSmemW2 + Ring2<true>::kSlots * kSlotBytes2;   // stash staging: one 4 KB piece (32 rows of a chunk image) per epilogue warp (train)
+constexpr uint32_t kSmemMask2 = kSmemStg2 + 16 * 4096;                   // ReLU-mask staging: 512 B per epilogue warp (train)
+constexpr uint32_t kSmemBytes2Train = kSmemMask2 + 16 * 512;             // 222,208
 constexpr uint32_t kSmemBytes2Infer = kSmemW2 + Ring2<false>::kSlots * kSlotBytes2;   // 214,016
 constexpr int kGroupsPerIter2 = 19;
 
@@ -249,8 +249,9 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
   const uint32_t tD = tA + 128 + ch * 64;                  // this thread's 64 accumulator columns
   const uint32_t bar_id = 1 + T;
   uint8_t* pe = smem + kSmemPE2 + T * kActChunk;
-  uint8_t* stg_slot = smem + kSmemStg2 + T * 2 * kActChunk;
-  uint8_t* stg = stg_slot + ch * kActChunk;
+  // training: every epilogue warp stages and bulk-stores ITS 32 rows of a chunk image (a contiguous 4 KB piece) by itself
+  uint8_t* stg = smem + kSmemStg2 + warp * 4096;
+  uint8_t* mstg = smem + kSmemMask2 + warp * 512;
   const uint32_t small_s = smem_u32(smem + kSmemSmall2);
   float4* xch = reinterpret_cast<float4*>(smem + kSmemXch2 + T * 2048) + r;
   uint32_t acc_phase = 0;
@@ -291,19 +292,22 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     const bool valid = tile_valid && g < p.pts.n_points;
     uint8_t* stash_tile = kTrain ? p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes : nullptr;
 
-    // packed bf16 rows of both column halves -> staging images -> one 32 KB bulk store into the stash
-    // mask_layer >= 0: the 4 KB of ReLU mask words of that layer (staged by all threads before the call) go out with it
-    auto stage_out = [&](int first_chunk, const uint32_t (&pk)[32], int mask_layer, const uint8_t* mask_stg) {
-      if (leader) tma_store_wait_read0();       // the previous bulk stores have finished reading the staging images
-      named_bar_sync(bar_id, 256);
+    // This warp's 32 packed bf16 rows (64 features of chunk `chunk`) -> its 4 KB staging piece -> one bulk store into the
+    // stash.  Warp-local: no named barrier and no other warp's store on the path (the CTA-wide version - 32 KB per slot
+    // behind two 256-thread barriers and a wait on the previous 36 KB store - cost ~1,700 cycles per accumulator half).
+    // mask_layer >= 0: this warp's 512 B of ReLU mask words of that layer ([row][h][2 words]) go out with it.
+    auto stage_out = [&](int chunk, const uint32_t (&pk)[32], int h, const uint32_t (&mw)[2], bool with_mask, int mask_layer) {
+      if (lane == 0) tma_store_wait_read0();    // this warp's previous bulk stores have finished reading its staging pieces
+      __syncwarp();
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq)
-        *reinterpret_cast<uint4*>(stg + chunk_off16(r, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+        *reinterpret_cast<uint4*>(stg + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+      if (with_mask) *reinterpret_cast<uint2*>(mstg + lane * 16 + h * 8) = make_uint2(mw[0], mw[1]);
       fence_proxy_async_smem();
-      named_bar_sync(bar_id, 256);
-      if (leader && tile_valid) {
-        tma_store_1d(stash_tile + (size_t)first_chunk * kActChunk, stg_slot, 2 * kActChunk);
-        if (mask_layer >= 0) tma_store_1d(stash_tile + kStashMaskOff + (size_t)mask_layer * 4096, mask_stg, 4096);
+      __syncwarp();
+      if (lane == 0 && tile_valid) {
+        tma_store_1d(stash_tile + (size_t)chunk * kActChunk + q * 4096, stg, 4096);
+        if (mask_layer >= 0) tma_store_1d(stash_tile + kStashMaskOff + (size_t)mask_layer * 4096 + ch * 2048 + q * 512, mstg, 512);
         tma_store_commit();
       }
     };
@@ -375,6 +379,10 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
         if (s < 9 && h == 1) {
           tmem_st32(tA + 64 + ch * 32, pk);
           if (s == 8) {                          // PE(viewdir) replaces PE(pts): L5 has consumed it
+            if (kTrain) {                        // ... and the bulk store of PE(pts) into the stash has read it
+              if (leader) tma_store_wait_read0();
+              named_bar_sync(bar_id, 256);
+            }
             write_pe_half<4>(pe, r, vx, vy, vz, ch);
             fence_proxy_async_smem();
           }
@@ -400,17 +408,13 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
           }
         }
         if (kTrain) {
-          // mask words: [128 rows][8 words] per layer, staged in shared memory (the 8-byte pieces of a row come from four
-          // different threads at two different times) and stored as one 4 KB bulk copy with the layer's last half
-          uint8_t* mstg = smem + kSmemMask2 + T * 8192 + (s & 1) * 4096;
-          if (s != 8) *reinterpret_cast<uint2*>(mstg + r * 32 + 8 * (2 * h + ch)) = make_uint2(mw[0], mw[1]);
           const bool last_half = (h == 1) || (s == 9);
-          stage_out(stash_chunk + 2 * h, pk, (s != 8 && last_half) ? (s == 9 ? 8 : s) : -1, mstg);
+          stage_out(stash_chunk + 2 * h + ch, pk, h, mw, s != 8, (s != 8 && last_half) ? (s == 9 ? 8 : s) : -1);
         }
       }
     }
   }
-  if (kTrain && leader) tma_store_wait_all0();
+  if (kTrain && lane == 0) tma_store_wait_all0();
   if (blockIdx.x == 0 && warp == 0 && lane == 0) { g_prof[3] = t_accw; g_prof[5] = clock64() - t_begin; }
 }
 

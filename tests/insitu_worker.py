@@ -103,7 +103,7 @@ def main():
     g = torch.Generator(device="cpu").manual_seed(3)
     poses = []
     for v in range(8):
-        p = torch.eye(4)
+        p = torch.eye(4, device="cpu")
         p[0, 3], p[1, 3] = 0.05 * v, -0.02 * v
         poses.append(p)
     poses = torch.stack(poses, 0).to(dev)
@@ -112,10 +112,11 @@ def main():
 
     def pick(n):
         ro, rd = helpers.get_rays(H, W, focal, poses[3][:3, :4])
-        idx = torch.randperm(H * W, generator=g)[:n].to(dev)
+        idx = torch.randperm(H * W, generator=g, device="cpu")[:n].to(dev)
         return torch.stack([ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx]], 0)
     data = {"hwf": [H, W, focal], "poses": poses, "masks": masks, "masked_batch_rays": pick(1024), "batch_rays_clf": pick(1024),
-            "batch_inp": pick(512), "target_clf": torch.rand(1024, 3, generator=g).to(dev), "target_inp": (torch.rand(512, generator=g) * 0.5).to(dev)}
+            "batch_inp": pick(512), "target_clf": torch.rand(1024, 3, generator=g, device="cpu").to(dev),
+            "target_inp": (torch.rand(512, generator=g, device="cpu") * 0.5).to(dev)}
 
     res = {}
     with tempfile.TemporaryDirectory() as td:
@@ -124,6 +125,12 @@ def main():
         # ---- pass 1: the stock reference on this GPU (fp32) -------------------------------------------------------------
         torch.manual_seed(0)
         kw_train_ref, kw_test_ref, _, _, opt_ref = run.create_nerf(args)
+        bds_dict = {"near": 1.2, "far": 7.7369}                         # run.py:554-559
+        kw_train_ref.update(bds_dict)
+        kw_test_ref.update(bds_dict)
+        with torch.no_grad():       # a positive density offset, as a trained scene has: every ray hits something (acc > 0, finite disp)
+            for k in ("network_fn", "network_fine"):
+                kw_train_ref[k].module.alpha_linear.bias += 0.3
         state = {k: kw_train_ref[k].state_dict() for k in ("network_fn", "network_fine")}
         state = {k: {n: t.detach().clone() for n, t in sd.items()} for k, sd in state.items()}
         torch.manual_seed(1)
@@ -135,6 +142,8 @@ def main():
         assert run.render is not stock_render and run.render.__module__ == "mvip_nerf_b200.run"
         torch.manual_seed(0)
         kw_train, kw_test, _, _, opt = run.create_nerf(args)            # ours now (same call, same Namespace)
+        kw_train.update(bds_dict)
+        kw_test.update(bds_dict)
         assert type(opt).__name__ == "FusedAdam"
         for k in ("network_fn", "network_fine"):
             kw_train[k].load_state_dict(state[k])                       # `module.`-prefixed keys of the stock nn.DataParallel
@@ -147,8 +156,11 @@ def main():
 
     def cmp(key):
         a, b = ref_out[key], our_out[key]
-        return {"max_abs": float(np.nanmax(np.abs(a - b))), "mean_abs": float(np.nanmean(np.abs(a - b))),
-                "ref_mean": float(np.nanmean(np.abs(a))), "nan_mismatch": int((np.isnan(a) != np.isnan(b)).sum())}
+        fin = np.isfinite(a) & np.isfinite(b)
+        d = np.abs(a - b)[fin]
+        return {"max_abs": float(d.max()) if d.size else None, "mean_abs": float(d.mean()) if d.size else None,
+                "ref_mean": float(np.abs(a[fin]).mean()) if d.size else None, "nan_mismatch": int((np.isnan(a) != np.isnan(b)).sum()),
+                "nan_ref": int(np.isnan(a).sum()), "nan_ours": int(np.isnan(b).sum()), "n": int(a.size)}
     for k in ("rgb", "disp", "depth1", "normal", "rgbs4", "rgb2", "disp2", "rgb0", "path_rgbs", "path_disps"):
         res[k] = cmp(k)
     res["loss_ref"], res["loss_ours"] = ref_out["loss"], our_out["loss"]

@@ -146,7 +146,8 @@ def decode_stash(stash, P):
         out["feat"].append(np.concatenate(list(dec[33:37]), -1))
         out["vpe"].append(dec[37])
         out["hidden"].append(np.concatenate(list(dec[38:40]), -1))
-        m = tb[40 * 16384:].view(np.uint32).reshape(9, 128, 8)
+        # [layer][column half ch][row][N-half h][2 words] -> [layer][row][word 2 (2 h + ch) + i]   (mlp_common.cuh)
+        m = tb[40 * 16384:].view(np.uint32).reshape(9, 2, 128, 2, 2).transpose(0, 2, 3, 1, 4).reshape(9, 128, 8)
         j = np.arange(32)
         bitpos = (16 * (j & 1) + 8 * (j >> 4) + ((j & 15) >> 1)).astype(np.uint32)     # mask_bit_of_column (mlp_common.cuh)
         bits = ((m[..., None] >> bitpos) & 1).astype(bool).reshape(9, 128, 256)
