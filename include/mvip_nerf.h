@@ -217,6 +217,8 @@ int mvip_debug_profile(unsigned long long* out16);
 int mvip_debug_trace(long long* out, int* n_out);
 /* wgrad cycle counters of CTA 0: producer empty-wait / total, issuer full-wait / total, bias warps full-wait / total, flag wait */
 int mvip_debug_wgrad_profile(unsigned long long* out8);
+/* event stamps (SM clock) of one chain-epilogue warp of the fused backward, -DMVIP_TRACE_BWD builds: out[20][12]; MVIP_E_UNSUPPORTED otherwise */
+int mvip_debug_bwd_trace(long long* out240);
 
 int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
 

@@ -335,8 +335,20 @@ constexpr uint32_t kWSmemBytes = kWStages * kWStageBytes;  // 216 KB
 constexpr int kNumItems = 11;
 constexpr size_t kPartialSlotBytes = (size_t)256 * 320 * sizeof(float);
 constexpr int kMaxCtas = 160;
+constexpr int kFusedSlots = 80;                     // partial slots [0, 80): one per CTA pair of the fused backward
+constexpr int kMaxSlots = kFusedSlots + 2 * kMaxCtas;   // then two per wgrad_kernel CTA
 
 __device__ unsigned long long g_wprof[8];
+#ifndef MVIP_FLAG_MODE
+#define MVIP_FLAG_MODE 0
+#endif
+#ifdef MVIP_TRACE_BWD
+// event stamps of epilogue warp 0 (lane 0) of cluster 0, leader CTA, for the 4th tile pair: [half-step 0..18][event]
+__device__ long long g_btrace[20][12];
+#define BTR(hs, ev) do { if (tr_on) g_btrace[hs][ev] = clock64(); } while (0)
+#else
+#define BTR(hs, ev)
+#endif
 struct WItem {
   int a_chunk;      // first dZ-stash chunk of the M side
   int m_blocks;     // 1 (128 output rows) or 2 (256)
@@ -384,22 +396,22 @@ struct WParams {
   float* partials;        // [grid][2] slots of kPartialSlotBytes
   float* bias_partials;   // [grid][2][256]
   Segment* segs;          // [grid][2]
-  // fused backward (tile-major): CTA b works on item i with item_first[i] <= b < item_first[i + 1] and owns the tiles
-  // t = b - item_first[i] (mod item_first[i + 1] - item_first[i]); it waits for the chain's flag of (tile, item).
-  const uint32_t* flags;  // null: stand-alone launch, cost-balanced contiguous (item, tile) ranges
-  int item_first[kNumItems + 1];
+  uint32_t item_mask;     // wgrad_kernel works on the items of this mask (the fused backward covers the others)
+  int slot_base;          // first partial slot of wgrad_kernel
 };
 __device__ __forceinline__ int item_flag(int item) { return item <= 4 ? item : (item == 5 ? 4 : item - 1); }
 
 // Cost-balanced static schedule: CTA b owns the cost range [b*C/G, (b+1)*C/G) of the concatenated
 // (item, tile) list; boundaries are snapped to tiles.  Returns up to 2 segments.
-__device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, Segment* out) {
+__device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, uint32_t item_mask, Segment* out) {
   int64_t total = 0;
-  for (int i = 0; i < kRealItems; ++i) total += (int64_t)kItems[i].cost * n_tiles;
+  for (int i = 0; i < kRealItems; ++i)
+    if ((item_mask >> i) & 1u) total += (int64_t)kItems[i].cost * n_tiles;
   const int64_t lo = total * b / G, hi = total * (b + 1) / G;
   int n = 0;
   int64_t base = 0;
   for (int i = 0; i < kRealItems && n < 2; ++i) {
+    if (!((item_mask >> i) & 1u)) continue;
     const int64_t c = kItems[i].cost;
     const int64_t end = base + c * n_tiles;
     // tiles of item i whose start cost lies in [lo, hi)
@@ -433,18 +445,10 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
     mbar_fence_init();
     Segment sg[2];
     sg[0].item = sg[1].item = -1; sg[0].t0 = sg[0].t1 = sg[1].t0 = sg[1].t1 = 0; sg[0].stride = sg[1].stride = 1;
-    if (p.flags) {
-      int item = 0;
-      while (item + 1 < kNumItems && cta >= p.item_first[item + 1]) ++item;
-      const int k = cta - p.item_first[item], n_i = p.item_first[item + 1] - p.item_first[item];
-      nseg_s = 0;
-      if (k < p.n_tiles) { sg[0].item = item; sg[0].t0 = k; sg[0].t1 = (int)p.n_tiles; sg[0].stride = n_i; nseg_s = 1; }
-    } else {
-      nseg_s = schedule(cta, n_ctas, p.n_tiles, sg);
-    }
+    nseg_s = schedule(cta, n_ctas, p.n_tiles, p.item_mask, sg);
     seg_s[0] = sg[0]; seg_s[1] = sg[1];
-    p.segs[cta * 2 + 0] = sg[0];
-    p.segs[cta * 2 + 1] = sg[1];
+    p.segs[p.slot_base + cta * 2 + 0] = sg[0];
+    p.segs[p.slot_base + cta * 2 + 1] = sg[1];
   }
   if (warp == 2) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
@@ -462,20 +466,9 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
       for (int sg = 0; sg < nseg; ++sg) {
         const WItem& itm = kItems[seg_s[sg].item];
         const int na = 2 * itm.m_blocks;
-        const int fl = item_flag(seg_s[sg].item);
         for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
           const uint8_t* dz_tile = p.dz + (size_t)t * kDzTileBytes;
           const uint8_t* st_tile = p.stash + (size_t)t * kStashTileBytes;
-          if (p.flags) {   // the dgrad chain (other SMs of this launch) has stored this tile's dZ group
-            const uint32_t* f = p.flags + (size_t)t * kFlagsPerTile + fl;
-            long long t0 = clock64();
-            long long tq = t0;
-            while (ld_acquire_gpu(f) == 0u) {
-              if (clock64() - t0 > 8000000000LL) { printf("mvip: wgrad flag timeout cta %d tile %d flag %d\n", cta, t, fl); __trap(); }
-            }
-            fence_proxy_async_all();
-            pf += clock64() - tq;
-          }
           for (int h = 0; h < 2; ++h) {
             uint8_t* sbase = smem + stage * kWStageBytes;
             long long tw = clock64();
@@ -585,13 +578,13 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
           if (++stage == kWStages) { stage = 0; phase ^= 1; }
         }
       }
-      float* bias_out = p.bias_partials + ((size_t)cta * 2 + sg) * 256;
+      float* bias_out = p.bias_partials + ((size_t)p.slot_base + cta * 2 + sg) * 256;
       if (do_bias) { bias_out[2 * t4] = b0; bias_out[2 * t4 + 1] = b1; }
       // drain: TMEM lane i of M block m = output row 128 m + i; columns = input features
       mbar_wait(&bar_acc, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      float* part = p.partials + ((size_t)cta * 2 + sg) * (kPartialSlotBytes / sizeof(float));
+      float* part = p.partials + ((size_t)p.slot_base + cta * 2 + sg) * (kPartialSlotBytes / sizeof(float));
       for (int m = 0; m < itm.m_blocks; ++m) {
         float* prow = part + (size_t)(128 * m + t4) * ntot;
         for (int c0 = 0; c0 < ntot; c0 += 32) {
@@ -617,6 +610,513 @@ __device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, cons
 }
 
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) { wgrad_body(p, blockIdx.x, gridDim.x); }
+
+// =================================================================================================
+// 2b. FUSED backward: the dgrad chain and the weight-gradient GEMMs of the eight 256 x 256 layers in ONE persistent launch,
+//     BOTH roles in EVERY CTA pair, dZ handed from the chain to wgrad through L2.
+//
+//     Stand-alone, wgrad re-reads the whole dZ stash (4.9 KB / point) from HBM after the chain has written it, and the
+//     chain leaves the tensor pipe idle while its epilogue warps work (it is bound by their instruction issue, not by
+//     HBM).  Here every CTA pair runs
+//       * the chain on ONE tile slot per CTA (TMEM columns [0, 256): A operand + one accumulator half, exactly the slot
+//         of dgrad_pair_kernel), tile pairs taken round-robin over the clusters, and
+//       * a cta_group::2 wgrad (M = 256 dZ features: 128 per CTA, N = 256 input features: B split 128 per CTA,
+//         K = points) whose 256 x 256 fp32 accumulator lives in TMEM columns [256, 512) of both CTAs for the whole
+//         launch; the pair is bound to ONE layer (item) and consumes that layer's dZ of every n-th tile as soon as the
+//         chain that produced it - on any SM - has published it: per-(tile, group) counters in global memory,
+//         incremented with red.release.gpu by each of the 8 epilogue warps once ITS bulk stores of the group are
+//         complete (cp.async.bulk.wait_group), polled with ld.acquire.gpu + fence.proxy.async by the wgrad producer.
+//     The dZ lines are read back while they are still in the 126 MB L2 (the chains work on a window of 148 consecutive
+//     tiles = 90 MB of dZ, every consumer follows the window), so HBM sees the forward stash once (read) and the dZ
+//     write-back; the wgrad MMAs fill the tensor pipe while the chain's epilogue runs.  The chain never waits for wgrad
+//     (dZ has its full-size buffer), wgrad only waits for counters, all CTAs are resident (grid <= #SMs): no deadlock.
+//     Shared memory per CTA: chain weight ring 8 x 8 KB, chain staging 8 warps x 2 x 4 KB, wgrad ring 3 x 32 KB.
+//     The 64-wide items (pts_linears.0, the PE part of pts_linears.5) and views_linears are left to wgrad_kernel.
+// =================================================================================================
+constexpr int kFThreads = 512;          // warps 0-7 chain epilogue (0-3 also drain the wgrad accumulator at the end), 8 chain TMA,
+                                        // 9 TMEM alloc / chain relay, 10 chain MMA, 11 wgrad TMA, 12 wgrad MMA / relay, 13-14 bias sums,
+                                        // 15 dZ bulk stores + publication  (512 threads: 128 registers per thread, no setmaxnreg needed)
+constexpr int kFSlots = 8, kFLag = 2;                                     // chain weight ring: two groups of <= 4 slots in flight (12 slots / 3 groups
+                                                                          // at the expense of the third wgrad stage measured slower: 1.27 vs 1.19 ms)
+constexpr int kFStages = 3;
+constexpr uint32_t kFStageBytes = 4 * kHalf;                              // A0 A1 B0 B1: 64 points x 64 features each
+constexpr uint32_t kFSmemW = 0;
+constexpr uint32_t kFSmemStg = kFSmemW + kFSlots * kSlotBytes2;           //  65,536
+constexpr uint32_t kFSmemWg = kFSmemStg + 2 * 2 * kActChunk;              // 131,072
+constexpr uint32_t kFSmemBytes = kFSmemWg + kFStages * kFStageBytes;      // 229,376
+constexpr int kFusedItems = 8;
+__constant__ int kFusedItemList[kFusedItems] = {1, 2, 3, 4, 6, 7, 8, 9};  // kItems indices: feature, L7, L6, L5 (h part), L4 .. L1
+constexpr uint32_t kFusedItemMask = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 6) | (1u << 7) | (1u << 8) | (1u << 9);
+
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+backward_fused_kernel(const ChainParams p, const WParams wp) {
+  constexpr int kG = kGroupBars2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_gfull[kG], bar_gempty[kG], bar_acc, bar_act, bar_hi;          // chain
+  __shared__ uint64_t bar_wfull[kFStages], bar_wempty[kFStages], bar_wacc;              // wgrad
+  __shared__ uint64_t bar_sfull[2], bar_sfree[2];                                        // dZ staging buffers: epilogue -> store warp
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int64_t n_pairs = (p.n_tiles + 1) / 2;
+  const uint8_t* wT = p.packed + kFwdBytes;
+
+  // wgrad assignment of this pair: item j = cluster % 8, k-th of n_j pairs on it, tiles k, k + n_j, ...
+  const int wj = cluster % kFusedItems, wk = cluster / kFusedItems;
+  const int wn = n_clusters / kFusedItems + (wj < n_clusters % kFusedItems ? 1 : 0);
+  const int witem = kFusedItemList[wj];
+  const bool w_active = wk < p.n_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < kG; ++i) {
+      mbar_init(&bar_gfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
+      mbar_init(&bar_gempty[i], 1);                  // multicast tcgen05.commit of the chain issuer
+    }
+    mbar_init(&bar_acc, 1); mbar_init(&bar_act, 16); mbar_init(&bar_hi, 16);
+    for (int i = 0; i < kFStages; ++i) {
+      mbar_init(&bar_wfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
+      mbar_init(&bar_wempty[i], 1 + 2);              // multicast tcgen05.commit + the two bias-sum warps
+    }
+    mbar_init(&bar_wacc, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_sfull[i], 8); mbar_init(&bar_sfree[i], 1); }
+    mbar_fence_init();
+    if (rank == 0) {
+      Segment sg;
+      sg.item = w_active ? witem : -1; sg.t0 = wk; sg.t1 = w_active ? (int)p.n_tiles : wk; sg.stride = wn;
+      wp.segs[cluster] = sg;
+    }
+  }
+  if (warp == 9) tmem_alloc_2cta(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ===================== chain epilogue: TMEM lane quarter q = warp%4, column half ch of every N-half =====================
+    const int q = warp & 3, ch = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t tA = tmem_base + lane_base;
+    const uint32_t tD = tA + 128 + ch * 64;
+    const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
+    // staging: two 32 KB buffers (the two chunk images of one accumulator half); this warp writes rows [32 q, 32 q + 32) of image ch
+    uint8_t* stg = smem + kFSmemStg + ch * kActChunk + q * 4096;
+    uint32_t acc_phase = 0, so_n = 0;
+    auto act_arrive = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&bar_act);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act), 0));
+      }
+    };
+    auto hi_arrive = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&bar_hi);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi), 0));
+      }
+    };
+
+    for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+      const int64_t tile = 2 * it + (int64_t)rank;
+      const bool tile_valid = tile < p.n_tiles;
+      const int64_t g = tile * kTile + r;
+      const bool valid = tile_valid && g < p.n_points;
+      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
+#ifdef MVIP_TRACE_BWD
+      const bool tr_on = cluster == 0 && rank == 0 && warp == 0 && lane == 0 && it == cluster + 3 * (int64_t)n_clusters;
+      int tr_hs = 0;
+#endif
+
+      // This warp's 32 packed rows -> its 4 KB piece of the current staging buffer; the store warp sends the whole 32 KB
+      // buffer (two chunk images) to the dZ stash as ONE bulk store and publishes the groups.  No global-memory operation, no
+      // bulk-group wait and no release fence on the epilogue warps (a red.release.gpu here cost 3,000 - 5,000 cycles).
+      auto stage_out = [&](const uint32_t (&pk)[32]) {
+        const uint32_t sb = so_n & 1u;
+        uint8_t* buf = stg + sb * 2 * kActChunk;
+        mbar_wait(&bar_sfree[sb], ((so_n >> 1) & 1u) ^ 1u);       // the store that used this buffer last has read it
+        ++so_n;
+        BTR(tr_hs, 7);
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq)
+          *reinterpret_cast<uint4*>(buf + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+        BTR(tr_hs, 8);
+        fence_proxy_async_smem();
+        __syncwarp();
+        BTR(tr_hs, 9);
+        if (lane == 0) mbar_arrive(&bar_sfull[sb]);
+        BTR(tr_hs, 10);
+      };
+      // ReLU mask words of (step s, half h), loaded one accumulator half ahead: they come from HBM
+      auto load_mask = [&](int s, int h) -> uint2 {
+        if (!valid) return make_uint2(0u, 0u);
+        if (s < 1) return make_uint2(~0u, ~0u);
+        return __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8 - s, r, h, ch)));
+      };
+
+      uint32_t pk[32];
+      const float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      {  // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0] -> A columns [0,64) (K = 128) of step 0
+        const uint2 mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8, r, 0, ch))) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c0 = ch * 64 + 16 * b;
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + c0 + 4 * j4));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 128 + c0 + 4 * j4));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(small + kSmWRgb + 256 + c0 + 4 * j4));
+            v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+            v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+            v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+            v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+          }
+          const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
+        }
+        tmem_st32(tA + ch * 32, pk);            // the previous tile's last MMAs are complete (its last accumulator was drained)
+        tmem_st_wait();
+        tc_fence_before();
+        act_arrive();                           // step 0 may start
+        stage_out(pk);
+      }
+
+      uint2 mw_next = load_mask(0, 0);
+#pragma unroll 1
+      for (int s = 0; s < kCSteps; ++s) {
+        // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const uint2 mw = mw_next;
+          mw_next = (h == 0) ? load_mask(s, 1) : load_mask(s + 1 < kCSteps ? s + 1 : 0, 0);
+          {
+            uint32_t raw[4][16];
+            BTR(tr_hs, 0);
+            mbar_wait(&bar_acc, acc_phase);
+            BTR(tr_hs, 1);
+            acc_phase ^= 1;
+            tc_fence_after();
+            if (h == 1 && s < kCSteps - 1) tmem_st32(tA + ch * 32, pk);      // half 0 of dZ -> next A operand, K columns [0,128)
+            load_half(tD, raw);
+            if (h == 1 && s < kCSteps - 1) tmem_st_wait();
+            BTR(tr_hs, 2);
+            tc_fence_before();
+            if (h == 0 || s < kCSteps - 1) act_arrive();   // h = 0: accumulator drained; h = 1: A[0,128) ready + accumulator drained
+            BTR(tr_hs, 3);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float v[16];
+              if (s == 1) {
+                const int c0 = h * 128 + ch * 64 + 16 * b;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(small + kSmWAlpha + c0 + 4 * j4));
+                  v[4 * j4 + 0] = __uint_as_float(raw[b][4 * j4 + 0]) + dr.w * w.x;
+                  v[4 * j4 + 1] = __uint_as_float(raw[b][4 * j4 + 1]) + dr.w * w.y;
+                  v[4 * j4 + 2] = __uint_as_float(raw[b][4 * j4 + 2]) + dr.w * w.z;
+                  v[4 * j4 + 3] = __uint_as_float(raw[b][4 * j4 + 3]) + dr.w * w.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[b][j]);
+              }
+              const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
+            }
+          }
+          BTR(tr_hs, 4);
+          if (h == 1 && s < kCSteps - 1) {
+            tmem_st32(tA + 64 + ch * 32, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            hi_arrive();                        // A[128,256) ready
+          }
+          BTR(tr_hs, 5);
+          stage_out(pk);
+          BTR(tr_hs, 6);
+#ifdef MVIP_TRACE_BWD
+          ++tr_hs;
+#endif
+        }
+      }
+    }
+    if (warp < 4 && w_active) {
+      // drain of the wgrad accumulator: TMEM lane i of CTA `rank` = output row 128 rank + i; columns = input features
+      mbar_wait(&bar_wacc, 0);
+      tc_fence_after();
+      float* prow = wp.partials + (size_t)cluster * (kPartialSlotBytes / sizeof(float)) + (size_t)(128 * rank + r) * 256;
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lane_base + 256 + c0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                                                  __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== chain TMA producer: this CTA's 64 rows of every (step, N-half, K chunk), once per tile pair =====================
+    if (lane == 0) {
+      uint32_t j = 0; int slot = 0;
+      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+        int cbase = 0;
+        for (int s = 0; s < kCSteps; ++s) {
+          const int n = chain_nchunks(s);
+          for (int h = 0; h < 2; ++h, ++j) {
+            if (j >= (uint32_t)kFLag) mbar_wait(&bar_gempty[(j - kFLag) % kG], ((j - kFLag) / kG) & 1u);
+            uint64_t* full = &bar_gfull[j % kG];
+            mbar_arrive_expect_tx(full, (uint32_t)n * kSlotBytes2);
+            for (int ci = 0; ci < n; ++ci) {
+              const uint8_t* src = wT + (size_t)(cbase + ci) * kW256 + (size_t)(2 * h + (int)rank) * kSlotBytes2;
+              tma_load_1d(smem + kFSmemW + slot * kSlotBytes2, src, kSlotBytes2, full);
+              if (++slot == kFSlots) slot = 0;
+            }
+          }
+          cbase += n;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== chain relay (peer CTA): "my part of the weight group has landed" =====================
+    if (rank == 1 && lane == 0) {
+      uint32_t j = 0;
+      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+        for (int c = 0; c < 2 * kCSteps; ++c, ++j) {
+          mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== chain MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      uint32_t act_phase = 0, hi_phase = 0, j = 0;
+      long long c_t0 = clock64(), c_act = 0, c_full = 0, c_x = 0;
+      const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
+      const uint32_t tA = tmem_base;
+      const uint32_t tDm = tA + 128;
+      const uint32_t w_lo = desc_lo2(smem_u32(smem) + kFSmemW);
+      const uint32_t w_end = w_lo + kFSlots * (kSlotBytes2 >> 4);
+      uint32_t bpos = w_lo;
+      auto next_slot = [&](uint32_t b) { b += (kSlotBytes2 >> 4); return b == w_end ? w_lo : b; };
+      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+#pragma unroll 1
+        for (int s = 0; s < kCSteps; ++s) {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h, ++j) {
+            const uint32_t b1 = bpos, b2 = next_slot(b1), b3 = next_slot(b2), b4 = next_slot(b3);
+            bpos = (s == 0) ? b3 : next_slot(b4);
+            uint64_t* gempty = &bar_gempty[j % kG];
+            c_x = clock64();
+            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
+            c_full += clock64() - c_x; c_x = clock64();
+            mbar_wait(&bar_act, act_phase);
+            c_act += clock64() - c_x;
+            act_phase ^= 1;
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + kk * 8, b1 + kk * 2, idesc, kk > 0 ? 1u : 0u);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 32 + kk * 8, b2 + kk * 2, idesc, 1u);
+              if (s == 0) {
+                umma_commit_2cta(gempty, 3);
+                umma_commit_2cta(&bar_acc, 3);
+              }
+            }
+            __syncwarp();
+            if (s > 0) {
+              if (h == 0) {
+                c_x = clock64();
+                mbar_wait(&bar_hi, hi_phase);
+                c_act += clock64() - c_x;
+                hi_phase ^= 1;
+                tc_fence_after();
+              }
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 64 + kk * 8, b3 + kk * 2, idesc, 1u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 96 + kk * 8, b4 + kk * 2, idesc, 1u);
+                umma_commit_2cta(gempty, 3);
+                umma_commit_2cta(&bar_acc, 3);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      if (cluster == 0 && lane == 0) { g_wprof[0] = clock64() - c_t0; g_wprof[1] = c_act; g_wprof[2] = c_full; }
+    }
+  } else if (warp == 11) {
+    // ===================== wgrad TMA producer (both CTAs): this CTA's 128 dZ features and 128 input features of a 64-point stage =====================
+    if (lane == 0 && w_active) {
+      const WItem& itm = kItems[witem];
+      const int fl = item_flag(witem);
+      const uint64_t pol = l2_policy_evict_first();
+      int stage = 0; uint32_t phase = 0;
+      long long p_flag = 0, p_empty = 0, p_t0 = clock64();
+      for (int t = wk; t < p.n_tiles; t += wn) {
+        const uint8_t* dz_tile = wp.dz + (size_t)t * kDzTileBytes;
+        const uint8_t* st_tile = wp.stash + (size_t)t * kStashTileBytes;
+        {  // all 8 epilogue warps of the chain that owns tile t (some SM of this launch) have stored this dZ group
+          const uint32_t* f = p.flags + (size_t)t * kFlagsPerTile + fl;
+          long long t0 = clock64();
+          while (ld_acquire_gpu(f) == 0u) {
+            if (clock64() - t0 > 8000000000LL) { printf("mvip: fused wgrad flag timeout cluster %d tile %d flag %d\n", cluster, t, fl); __trap(); }
+          }
+          fence_proxy_async_all();
+          p_flag += clock64() - t0;
+        }
+        for (int h = 0; h < 2; ++h) {
+          uint8_t* sbase = smem + kFSmemWg + stage * kFStageBytes;
+          long long te = clock64();
+          mbar_wait(&bar_wempty[stage], phase ^ 1);
+          p_empty += clock64() - te;
+          mbar_arrive_expect_tx(&bar_wfull[stage], kFStageBytes);
+          for (int j = 0; j < 2; ++j)
+            tma_load_1d_hint(sbase + j * kHalf, dz_tile + (size_t)(itm.a_chunk + 2 * (int)rank + j) * kActChunk + h * kHalf, kHalf,
+                             &bar_wfull[stage], pol);
+          for (int j = 0; j < 2; ++j)
+            tma_load_1d_hint(sbase + (2 + j) * kHalf, st_tile + (size_t)itm.b_chunk[2 * (int)rank + j] * kActChunk + h * kHalf, kHalf,
+                             &bar_wfull[stage], pol);
+          if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (cluster == 0 && rank == 0) { g_wprof[5] = p_flag; g_wprof[6] = p_empty; g_wprof[7] = clock64() - p_t0; }
+    }
+  } else if (warp == 12) {
+    // ===================== wgrad MMA issuer (leader) / relay (peer) =====================
+    if (w_active) {
+      int stage = 0; uint32_t phase = 0;
+      if (rank == 0) {
+        const uint32_t idesc = umma_idesc_bf16(256, 256, 1, 1);
+        const uint32_t d0 = tmem_base + 256;
+        bool first = true;
+        long long w_t0 = clock64(), w_full = 0;
+        for (int t = wk; t < p.n_tiles; t += wn) {
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sbase = smem_u32(smem) + kFSmemWg + stage * kFStageBytes;
+            const uint32_t a_lo = desc_lo_mn(sbase, kHalf), b_lo = desc_lo_mn(sbase + 2 * kHalf, kHalf);
+            long long tw = clock64();
+            mbar_wait(&bar_wfull[stage], phase);
+            w_full += clock64() - tw;
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t ko = (uint32_t)ks * (2048u >> 4);
+                mma2_ss(d0, a_lo + ko, b_lo + ko, idesc, (first && ks == 0) ? 0u : 1u);
+              }
+              umma_commit_2cta(&bar_wempty[stage], 3);
+            }
+            __syncwarp();
+            first = false;
+            if (++stage == kFStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one_sync()) umma_commit_2cta(&bar_wacc, 3);
+        __syncwarp();
+        if (cluster == 0 && lane == 0) { g_wprof[3] = clock64() - w_t0; g_wprof[4] = w_full; }
+      } else if (lane == 0) {
+        for (int t = wk; t < p.n_tiles; t += wn) {
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&bar_wfull[stage], phase);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_wfull[stage]), 0));
+            if (++stage == kFStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if ((warp == 13 || warp == 14) && w_active) {
+    // ===================== bias column sums of this CTA's 128 dZ features, from the staged A operand =====================
+    // thread t4 (0..63) owns features 2 t4, 2 t4 + 1: half chunk t4 / 32, 16-byte group (t4 % 32) / 4, word t4 % 4
+    const int t4 = (warp - 13) * 32 + lane;
+    const uint32_t boff = (uint32_t)(t4 >> 5) * kHalf;
+    const int bg = (t4 & 31) >> 2;
+    const uint32_t bw = (uint32_t)(t4 & 3) * 4;
+    float b0 = 0.f, b1 = 0.f;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = wk; t < p.n_tiles; t += wn) {
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&bar_wfull[stage], phase);
+        const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff + bw;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t pr;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
+            b0 += __uint_as_float(pr << 16);
+            b1 += __uint_as_float(pr & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_wempty[stage]);
+        if (++stage == kFStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    float* bias_out = wp.bias_partials + (size_t)cluster * 256 + 128 * rank;
+    bias_out[2 * t4] = b0;
+    bias_out[2 * t4 + 1] = b1;
+  } else if (warp == 15) {
+    // ===================== dZ store warp: one 32 KB bulk store per staging buffer; publication of the dZ groups =====================
+    // Three times per tile (after the outputs of chain steps 2, 5 and 8) the thread waits for ALL its bulk stores to be
+    // complete, orders them (async proxy) before its generic-proxy flag stores, issues ONE gpu-scope release fence and sets
+    // the flags of the groups that have gone out since the last time.  Only this thread ever pays for the fence.
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+        const int64_t tile = 2 * it + (int64_t)rank;
+        const bool tile_valid = tile < p.n_tiles;
+        uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
+        uint32_t* tile_flags = p.flags + (size_t)(tile_valid ? tile : 0) * kFlagsPerTile;
+        int flag_lo = 0;
+        for (int c = 0; c < 1 + 2 * kCSteps; ++c, ++n) {
+          // c == 0: d hidden_pre; c = 1 + 2 s + h: N-half h of chain step s
+          const int s = (c - 1) >> 1, h = (c - 1) & 1;
+          const int chunk = (c == 0) ? kDzHidden : ((s == 0 ? kDzFeat : kDzTrunk + 4 * (s - 1)) + 2 * h);
+          const uint32_t sb = n & 1u;
+          mbar_wait(&bar_sfull[sb], (n >> 1) & 1u);
+          if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk, smem + kFSmemStg + sb * 2 * kActChunk, 2 * kActChunk);
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&bar_sfree[sb]);
+          if (c == 6 || c == 12 || c == 18) {
+            const int flag_hi = (c == 6) ? 3 : (c == 12 ? 6 : 9);
+            tma_store_wait_all0();
+            fence_proxy_async_all();
+            __threadfence();
+            if (tile_valid)
+              for (int f = flag_lo; f <= flag_hi; ++f) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(tile_flags + f), "r"(1u) : "memory");
+            flag_lo = flag_hi + 1;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) tmem_dealloc_2cta(tmem_base, 512);
+}
 
 // =================================================================================================
 // 3. alpha / rgb head grads on CUDA cores
@@ -699,7 +1199,7 @@ struct ReduceParams {
   const float* partials;
   const float* bias_partials;
   const Segment* segs;
-  int w_grid;
+  int n_slots;            // partial slots in use: [0, kFusedSlots) fused backward, then two per wgrad_kernel CTA
   const float* head_partials;
   int head_grid;
   GradPtrs grads;
@@ -713,7 +1213,7 @@ constexpr int kReduceGridX = 80;     // 256 x 320 floats / 4 per thread / 256 th
 // first version walked ~30 slots (weights) and up to 1184 partials (heads) with a dependent add per load and took
 // 70 us per launch at 0.5 TB/s.
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
-  __shared__ int slots[2 * kMaxCtas];
+  __shared__ int slots[kMaxSlots];
   __shared__ int nslots;
   __shared__ float hred[8][32];
   const int item = blockIdx.y;
@@ -753,15 +1253,15 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   }
   // slots of this item, in slot order: the segment table is read by all threads at once (one thread walking the 296
   // entries in global memory was 15 us of latency), then compacted from shared memory
-  __shared__ unsigned char mine[2 * kMaxCtas];
-  for (int i = threadIdx.x; i < 2 * p.w_grid; i += blockDim.x) {
+  __shared__ unsigned char mine[kMaxSlots];
+  for (int i = threadIdx.x; i < p.n_slots; i += blockDim.x) {
     const Segment sg = p.segs[i];
     mine[i] = (sg.item == item && sg.t1 > sg.t0) ? 1 : 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int n = 0;
-    for (int i = 0; i < 2 * p.w_grid; ++i)
+    for (int i = 0; i < p.n_slots; ++i)
       if (mine[i]) slots[n++] = i;
     nslots = n;
   }
@@ -819,9 +1319,9 @@ Workspace carve(int64_t n_points) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
   w.dz = take((size_t)num_tiles(n_points) * kDzTileBytes);
-  w.partials = take((size_t)kMaxCtas * 2 * kPartialSlotBytes);
-  w.bias = take((size_t)kMaxCtas * 2 * 256 * sizeof(float));
-  w.segs = take((size_t)kMaxCtas * 2 * sizeof(Segment));
+  w.partials = take((size_t)kMaxSlots * kPartialSlotBytes);
+  w.bias = take((size_t)kMaxSlots * 256 * sizeof(float));
+  w.segs = take((size_t)kMaxSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
   w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
@@ -836,6 +1336,18 @@ int mvip_debug_wgrad_profile(unsigned long long* out8) {
   MVIP_CUDA_OK(cudaDeviceSynchronize());
   MVIP_CUDA_OK(cudaMemcpyFromSymbol(out8, g_wprof, sizeof(unsigned long long) * 8));
   return MVIP_OK;
+}
+
+int mvip_debug_bwd_trace(long long* out240) {
+#ifdef MVIP_TRACE_BWD
+  MVIP_CUDA_OK(cudaDeviceSynchronize());
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(out240, g_btrace, sizeof(long long) * 240));
+  return MVIP_OK;
+#else
+  (void)out240;
+  mvip_set_error("mvip_debug_bwd_trace: library built without -DMVIP_TRACE_BWD");
+  return MVIP_E_UNSUPPORTED;
+#endif
 }
 
 size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_points).total; }
@@ -872,7 +1384,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   cp.dz = wsb + ws.dz;
   cp.n_points = n_points;
   cp.n_tiles = n_tiles;
-  cp.flags = nullptr;
+  cp.flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
   WParams wp;
   wp.stash = static_cast<const uint8_t*>(stash);
   wp.dz = wsb + ws.dz;
@@ -880,21 +1392,22 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   wp.partials = reinterpret_cast<float*>(wsb + ws.partials);
   wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
   wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
-  wp.flags = nullptr;
-  for (int i = 0; i <= kNumItems; ++i) wp.item_first[i] = 0;
-  int w_grid = sms;
+  const uint32_t all_items = (1u << kNumItems) - 1u;
+  wp.item_mask = all_items & ~kFusedItemMask;
+  wp.slot_base = kFusedSlots;
+  const int n_pairs_max = sms / 2 < kFusedSlots ? sms / 2 : kFusedSlots;
 
-  // 1. dgrad chain
+  // 1 + 2. fused: dgrad chain + wgrad of the eight 256 x 256 layers (phase bit 1), then wgrad of the remaining items (phase bit 2)
   if (phase_mask & 1) {
-    const int64_t n_quads = (n_tiles + 3) / 4;
-    const int max_clusters = sms / 2;
-    const int grid2 = 2 * (int)(n_quads < max_clusters ? n_quads : max_clusters);
-    const size_t smem2 = kDSmemBytes + 1024;
-    MVIP_SMEM_OPT_IN(dgrad_pair_kernel, smem2);
-    dgrad_pair_kernel<<<grid2, kDThreads, smem2, st>>>(cp);
-    MVIP_LAUNCH_OK("dgrad_pair_kernel");
+    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t), st));
+    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0xff, (size_t)kFusedSlots * sizeof(Segment), st));      // item = -1: unused slot
+    const int clusters = n_pairs_max;     // always all pairs: each of the eight fused items needs its consumers
+    const size_t smem = kFSmemBytes + 1024;
+    MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
+    backward_fused_kernel<<<2 * clusters, kFThreads, smem, st>>>(cp, wp);
+    MVIP_LAUNCH_OK("backward_fused_kernel");
   }
-  // 2. wgrad
+  const int w_grid = sms;
   if (phase_mask & 2) {
     const size_t smem = kWSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(wgrad_kernel, smem);
@@ -915,7 +1428,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     rp.partials = reinterpret_cast<const float*>(wsb + ws.partials);
     rp.bias_partials = reinterpret_cast<const float*>(wsb + ws.bias);
     rp.segs = reinterpret_cast<const Segment*>(wsb + ws.segs);
-    rp.w_grid = w_grid;
+    rp.n_slots = kFusedSlots + 2 * w_grid;
     rp.head_partials = reinterpret_cast<const float*>(wsb + ws.heads);
     rp.head_grid = head_grid;
     rp.grads = gp;

@@ -359,8 +359,8 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-    if kernel_timer.on:   # one bracket per launch: dgrad chain, wgrad, head grads, reduce
-        for bit, label in ((1, "dgrad_pair_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
+    if kernel_timer.on:   # one bracket per launch: fused dgrad chain + wgrad of the 256 x 256 layers, wgrad of the rest, head grads, reduce
+        for bit, label in ((1, "backward_fused_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
             _call(("mvip_mlp_backward_phases", label), _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr,
                   int(bool(accumulate)), bit, _stream())
     else:

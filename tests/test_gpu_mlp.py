@@ -279,3 +279,38 @@ def test_mlp_backward_is_linear_and_deterministic_at_full_size(ops):
     torch.testing.assert_close(g1[21], d1[:, 3:].sum(0), rtol=1e-4, atol=1e-2)
 
 
+
+
+@pytest.mark.gpu
+def test_fused_backward_is_deterministic_and_never_reads_stale_dz():
+    """The fused backward hands dZ from the chain to the wgrad role through per-(tile, group) flags.  A consumer that ran ahead of
+    its producer would read whatever the workspace held before: the workspace is therefore POISONED (NaN bit patterns) before
+    each run - any premature read shows up as NaN / a different bit pattern - and three runs must agree bit for bit."""
+    import ctypes
+    from mvip_nerf_b200 import _lib, ops
+    dev = "cuda"
+    p = orc.init_params(7)
+    blob = ops.mlp_pack([torch.from_numpy(p[n]).to(dev) for n in ops.PARAM_ORDER])
+    g = torch.Generator(device=dev).manual_seed(11)
+    P = 128 * 148 * 6 + 53
+    pts = torch.rand(P, 3, device=dev, generator=g) * 4 - 2
+    dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g), dim=-1)
+    raw, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
+    d = torch.randn(P, 4, device=dev, generator=g)
+    lib = _lib.load()
+    ws = ops._aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
+    outs = []
+    for rep in range(3):
+        ws.fill_(0xFF)                                  # bf16 0xFFFF = NaN, flags != 0 are reset by the library itself
+        flat = torch.full((595844,), float("nan"), device=dev)
+        grads, off = [], 0
+        for shp in ops.PARAM_SHAPES:
+            n = int(torch.Size(shp).numel())
+            grads.append(flat[off:off + n].view(shp)); off += n
+        arr = (ctypes.c_void_p * 24)(*[x.data_ptr() for x in grads])
+        rc = lib.mvip_mlp_backward(ops._ptr(blob), ops._ptr(d), P, ops._ptr(stash), ops._ptr(ws), arr, 0, ops._stream())
+        _lib.check(rc, "mvip_mlp_backward")
+        torch.cuda.synchronize()
+        outs.append(flat.clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
