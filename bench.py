@@ -290,11 +290,9 @@ def hbm_stage_times(ops, dev, hbm_peak):
 # kernel label (ops.kernel_timer) -> (FLOP per point, algorithmic HBM bytes per point, direction)
 def kernel_table():
     return {"mvip_mlp_forward": (FLOP_FWD, HBM_FWD_TRAIN, "write"),
-            # fused backward: the dgrad chain + wgrad of the eight 256 x 256 layers (8 x 131,072 FLOP / point); dZ is written
-            # once (and re-read out of L2 by the wgrad role), 32 of the 40 forward-stash images are read once
-            "backward_fused_kernel": (FLOP_DGRAD + 8 * 131072, HBM_DGRAD + 32 * 128, "read+write"),
-            # the rest: views_linears (128 x 283), pts_linears.0 (256 x 63), PE part of pts_linears.5 (256 x 63)
-            "wgrad_kernel": (FLOP_WGRAD - 8 * 131072, (2 + 5 + 4 + 1 + 4 + 1) * 128, "read"),
+            # fused backward (dgrad chain + all weight gradients): dZ is written once (and re-read out of L2 by the wgrad role),
+            # the forward stash is read once
+            "backward_fused_kernel": (FLOP_DGRAD + FLOP_WGRAD, HBM_DGRAD + 40 * 128, "read+write"),
             "head_grads_kernel": (0, HBM_HEADS, "read")}
 
 

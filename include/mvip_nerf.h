@@ -118,6 +118,24 @@ int mvip_composite_backward(const float* raw, const float* z_vals, const float* 
                             const float* g_disp, const float* g_acc, const float* g_depth,
                             const float* g_weights, const float* g_alpha, float* d_raw, void* stream);
 
+/* The same with the photometric losses fused in (img2mse of run_nerf_helpers.py:15 as train() applies it to rgb / rgb0 /
+ * disp, run.py:1000-1027).  n_samples must be 64 or 128.
+ *   forward : also returns sq_out[0] = sum_rays sum_c (rgb_map - target_rgb)^2 and sq_out[1] = sum_rays (disp_map - target_disp)^2
+ *             (either target may be NULL -> 0); bitwise reproducible.  `workspace`: mvip_composite_mse_workspace_bytes()
+ *             bytes, zero-filled before its FIRST use (the kernel leaves it ready for the next call).
+ *   backward: g_sq[2] = d loss / d sq_out, read from DEVICE memory; 2 g_sq (map - target) is added to g_rgb / g_disp
+ *             (which may be NULL) inside the kernel, from the recomputed forward. */
+size_t mvip_composite_mse_workspace_bytes(void);
+int mvip_composite_forward_mse(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                               const float* noise, int64_t n_rays, int n_samples, int white_bkgd, const float* target_rgb,
+                               const float* target_disp, float* rgb, float* disp, float* acc, float* weights, float* depth,
+                               float* alpha, float* sq_out, void* workspace, void* stream);
+int mvip_composite_backward_mse(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                                const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
+                                const float* target_rgb, const float* target_disp, const float* g_sq, const float* g_rgb,
+                                const float* g_disp, const float* g_acc, const float* g_depth, const float* g_weights,
+                                const float* g_alpha, float* d_raw, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Depth -> least-squares plane normal.       replaces DS_NeRF/run.py:1909-1940
  *   (depth2xyz_torch + depth2normal_geo, zero-padded k x k window, normal NOT normalised)

@@ -40,6 +40,12 @@ _SIGNATURES = {
     "mvip_composite_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
+    "mvip_composite_mse_workspace_bytes": (c_size_t, []),
+    "mvip_composite_forward_mse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mvip_composite_backward_mse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
     "mvip_normal_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mvip_normal_forward": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_int, c_void_p,
                                     c_void_p, c_void_p]),

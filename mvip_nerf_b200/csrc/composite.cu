@@ -281,12 +281,26 @@ __device__ __forceinline__ void eval_ray4(Fast4& f, const float4* __restrict__ r
   f.Bc = group_sum<G>(sB);
 }
 
+// Photometric losses fused into the compositing kernels (img2mse of DS_NeRF/run_nerf_helpers.py:15 as train() applies it to
+// rgb / rgb0 / disp, run.py:1000-1027): the forward also returns  sq[0] = sum_rays sum_c (rgb_c - target_rgb_c)^2  and
+// sq[1] = sum_rays (disp - target_disp)^2  (deterministic: per-block partials summed in block order by the last block), the
+// backward takes d loss / d sq[0..1] from DEVICE memory and adds 2 g (x - target) to the upstream gradients in-kernel.
+struct MseArgs {
+  const float* target_rgb;    // [N,3] or null
+  const float* target_disp;   // [N]   or null
+  float* partials;            // forward: [grid][2] scratch
+  unsigned int* counter;      // forward: zero-initialised ticket counter (reset by the kernel)
+  float* sq_out;              // forward: [2]
+  const float* g_sq;          // backward: [2] (device)
+};
+
 template <int G>
 __global__ void __launch_bounds__(kWarps * 32, 5)
 composite_fwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                       int d_stride, const float* __restrict__ noise, int64_t n_rays, int white,
                       float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
-                      float* __restrict__ weights, float* __restrict__ depth, float* __restrict__ alpha) {
+                      float* __restrict__ weights, float* __restrict__ depth, float* __restrict__ alpha, const MseArgs mse) {
+  float sq_rgb = 0.f, sq_disp = 0.f;
   constexpr int S = 4 * G, RPW = 32 / G;   // samples per ray, rays per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % G;
   const int64_t stride = (int64_t)gridDim.x * kWarps * RPW;
@@ -310,7 +324,38 @@ composite_fwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
         disp[ray] = 1.f / m;
         acc[ray] = f.A;
         depth[ray] = f.D;
+        if (mse.target_rgb) {
+          const float e0 = (f.R + bg) - __ldg(mse.target_rgb + ray * 3), e1 = (f.G + bg) - __ldg(mse.target_rgb + ray * 3 + 1),
+                      e2 = (f.Bc + bg) - __ldg(mse.target_rgb + ray * 3 + 2);
+          sq_rgb += e0 * e0 + e1 * e1 + e2 * e2;
+        }
+        if (mse.target_disp) { const float e = 1.f / m - __ldg(mse.target_disp + ray); sq_disp += e * e; }
       }
+    }
+  }
+  if (mse.sq_out) {   // warp -> block -> grid, every level in a fixed order
+    __shared__ float part_s[kWarps][2];
+    __shared__ bool last_s;
+    sq_rgb = warp_sum(sq_rgb);
+    sq_disp = warp_sum(sq_disp);
+    if (lane == 0) { part_s[warp][0] = sq_rgb; part_s[warp][1] = sq_disp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < kWarps; ++w) { a += part_s[w][0]; b += part_s[w][1]; }
+      mse.partials[2 * blockIdx.x] = a;
+      mse.partials[2 * blockIdx.x + 1] = b;
+      __threadfence();
+      last_s = atomicAdd(mse.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_s && warp == 0) {
+      __threadfence();
+      float a = 0.f, b = 0.f;
+      for (int i = lane; i < (int)gridDim.x; i += 32) { a += __ldcg(mse.partials + 2 * i); b += __ldcg(mse.partials + 2 * i + 1); }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) { mse.sq_out[0] = a; mse.sq_out[1] = b; *mse.counter = 0u; }
     }
   }
 }
@@ -321,8 +366,10 @@ composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
                       int d_stride, const float* __restrict__ noise, int64_t n_rays, int white, int detach_w,
                       const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
                       const float* __restrict__ g_depth, const float* __restrict__ g_weights,
-                      const float* __restrict__ g_alpha, float4* __restrict__ d_raw) {
+                      const float* __restrict__ g_alpha, float4* __restrict__ d_raw, const MseArgs mse) {
   constexpr int S = 4 * G, RPW = 32 / G;
+  const float gs_rgb = (mse.g_sq && mse.target_rgb) ? 2.f * __ldg(mse.g_sq) : 0.f;
+  const float gs_disp = (mse.g_sq && mse.target_disp) ? 2.f * __ldg(mse.g_sq + 1) : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % G;
   const int64_t stride = (int64_t)gridDim.x * kWarps * RPW;
   for (int64_t ray0 = ((int64_t)blockIdx.x * kWarps + warp) * RPW; ray0 < n_rays; ray0 += stride) {
@@ -333,7 +380,10 @@ composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
     // upstream gradients first: their latency overlaps the forward recomputation
     float gR = 0.f, gG = 0.f, gB = 0.f;
     if (g_rgb) { gR = __ldg(g_rgb + ray * 3); gG = __ldg(g_rgb + ray * 3 + 1); gB = __ldg(g_rgb + ray * 3 + 2); }
-    const float gdisp = g_disp ? __ldg(g_disp + ray) : 0.f;
+    float gdisp = g_disp ? __ldg(g_disp + ray) : 0.f;
+    float tR = 0.f, tG = 0.f, tB = 0.f, tdisp = 0.f;
+    if (mse.target_rgb) { tR = __ldg(mse.target_rgb + ray * 3); tG = __ldg(mse.target_rgb + ray * 3 + 1); tB = __ldg(mse.target_rgb + ray * 3 + 2); }
+    if (mse.target_disp) tdisp = __ldg(mse.target_disp + ray);
     float gD = g_depth ? __ldg(g_depth + ray) : 0.f;
     float gA = g_acc ? __ldg(g_acc + ray) : 0.f;
     float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f), ga4 = gw4;
@@ -342,7 +392,17 @@ composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
     Fast4 f;
     eval_ray4<G>(f, raw + off, z + off, noise ? noise + off : nullptr, rays_d + ray * d_stride, sub);
     const float r = f.D / f.A;
-    if (!(r <= 1e-10f) && g_disp) {   // NaN keeps the path, as torch.max's backward does
+    if (mse.target_rgb) {             // d (sum of squares) / d rgb_map, from the recomputed forward
+      const float bg = white ? (1.f - f.A) : 0.f;
+      gR = fmaf(gs_rgb, (f.R + bg) - tR, gR);
+      gG = fmaf(gs_rgb, (f.G + bg) - tG, gG);
+      gB = fmaf(gs_rgb, (f.Bc + bg) - tB, gB);
+    }
+    if (mse.target_disp) {
+      const float m = (r != r) ? r : fmaxf(1e-10f, r);
+      gdisp = fmaf(gs_disp, 1.f / m - tdisp, gdisp);
+    }
+    if (!(r <= 1e-10f) && (g_disp || mse.target_disp)) {   // NaN keeps the path, as torch.max's backward does
       gD += -gdisp * f.A / (f.D * f.D);
       gA += gdisp / f.D;
     }
@@ -407,28 +467,32 @@ int grid_for_rays(int64_t n) {
 
 extern "C" {
 
-int mvip_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
-                           const float* noise, int64_t n_rays, int n_samples, int white_bkgd, float* rgb, float* disp,
-                           float* acc, float* weights, float* depth, float* alpha, void* stream) {
+static int composite_forward_impl(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                                  const float* noise, int64_t n_rays, int n_samples, int white_bkgd, float* rgb, float* disp,
+                                  float* acc, float* weights, float* depth, float* alpha, const MseArgs& mse, void* stream) {
   MVIP_REQUIRE(n_rays == 0 || (raw && z_vals && rays_d && rgb && disp && acc && weights && depth), MVIP_E_INVALID,
                "mvip_composite_forward: null pointer");
   MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_forward: bad shape");
   MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_forward: n_samples %d > 512", n_samples);
   MVIP_REQUIRE(mvip_aligned(raw, 16) && mvip_aligned(weights, 16) && (!alpha || mvip_aligned(alpha, 16)),
                MVIP_E_INVALID, "mvip_composite_forward: raw/weights/alpha must be 16-byte aligned");
-  if (n_rays == 0) return MVIP_OK;
+  if (n_rays == 0) {
+    if (mse.sq_out) MVIP_CUDA_OK(cudaMemsetAsync(mse.sq_out, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    return MVIP_OK;
+  }
   const bool vec_ok = mvip_aligned(z_vals, 16) && (!noise || mvip_aligned(noise, 16));
   if (vec_ok && (n_samples == 64 || n_samples == 128)) {
     auto* r4 = reinterpret_cast<const float4*>(raw);
     if (n_samples == 128)
       composite_fwd4_kernel<32><<<grid_for_rays4(n_rays, 1), kWarps * 32, 0, (cudaStream_t)stream>>>(
-          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha);
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha, mse);
     else
       composite_fwd4_kernel<16><<<grid_for_rays4(n_rays, 2), kWarps * 32, 0, (cudaStream_t)stream>>>(
-          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha);
+          r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, rgb, disp, acc, weights, depth, alpha, mse);
     MVIP_LAUNCH_OK("composite_fwd4_kernel");
     return MVIP_OK;
   }
+  MVIP_REQUIRE(!mse.sq_out, MVIP_E_UNSUPPORTED, "mvip_composite_forward_mse: the fused losses need n_samples = 64 or 128 and 16-byte aligned rows");
   DISPATCH_C(n_samples, (composite_fwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
                             reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
                             n_samples, white_bkgd, rgb, disp, acc, weights, depth, alpha)));
@@ -436,10 +500,10 @@ int mvip_composite_forward(const float* raw, const float* z_vals, const float* r
   return MVIP_OK;
 }
 
-int mvip_composite_backward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
-                            const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
-                            const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
-                            const float* g_weights, const float* g_alpha, float* d_raw, void* stream) {
+static int composite_backward_impl(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                                   const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
+                                   const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
+                                   const float* g_weights, const float* g_alpha, float* d_raw, const MseArgs& mse, void* stream) {
   MVIP_REQUIRE(n_rays == 0 || (raw && z_vals && rays_d && d_raw), MVIP_E_INVALID, "mvip_composite_backward: null pointer");
   MVIP_REQUIRE(n_rays >= 0 && n_samples >= 1 && rays_d_stride >= 3, MVIP_E_INVALID, "mvip_composite_backward: bad shape");
   MVIP_REQUIRE(n_samples <= 512, MVIP_E_UNSUPPORTED, "mvip_composite_backward: n_samples %d > 512", n_samples);
@@ -454,20 +518,64 @@ int mvip_composite_backward(const float* raw, const float* z_vals, const float* 
     if (n_samples == 128)
       composite_bwd4_kernel<32><<<grid_for_rays4(n_rays, 1), kWarps * 32, 0, (cudaStream_t)stream>>>(
           r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
-          g_weights, g_alpha, o4);
+          g_weights, g_alpha, o4, mse);
     else
       composite_bwd4_kernel<16><<<grid_for_rays4(n_rays, 2), kWarps * 32, 0, (cudaStream_t)stream>>>(
           r4, z_vals, rays_d, rays_d_stride, noise, n_rays, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
-          g_weights, g_alpha, o4);
+          g_weights, g_alpha, o4, mse);
     MVIP_LAUNCH_OK("composite_bwd4_kernel");
     return MVIP_OK;
   }
+  MVIP_REQUIRE(!mse.g_sq, MVIP_E_UNSUPPORTED, "mvip_composite_backward_mse: the fused losses need n_samples = 64 or 128 and 16-byte aligned rows");
   DISPATCH_C(n_samples, (composite_bwd_kernel<C><<<grid_for_rays(n_rays), kWarps * 32, 0, (cudaStream_t)stream>>>(
                             reinterpret_cast<const float4*>(raw), z_vals, rays_d, rays_d_stride, noise, n_rays,
                             n_samples, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha,
                             reinterpret_cast<float4*>(d_raw))));
   MVIP_LAUNCH_OK("composite_bwd_kernel");
   return MVIP_OK;
+}
+
+int mvip_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                           const float* noise, int64_t n_rays, int n_samples, int white_bkgd, float* rgb, float* disp,
+                           float* acc, float* weights, float* depth, float* alpha, void* stream) {
+  const MseArgs none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return composite_forward_impl(raw, z_vals, rays_d, rays_d_stride, noise, n_rays, n_samples, white_bkgd, rgb, disp, acc, weights,
+                                depth, alpha, none, stream);
+}
+
+int mvip_composite_backward(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                            const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
+                            const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
+                            const float* g_weights, const float* g_alpha, float* d_raw, void* stream) {
+  const MseArgs none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return composite_backward_impl(raw, z_vals, rays_d, rays_d_stride, noise, n_rays, n_samples, white_bkgd, detach_weights, g_rgb,
+                                 g_disp, g_acc, g_depth, g_weights, g_alpha, d_raw, none, stream);
+}
+
+size_t mvip_composite_mse_workspace_bytes(void) { return (size_t)(2 * 1184 + 4) * sizeof(float); }
+
+int mvip_composite_forward_mse(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                               const float* noise, int64_t n_rays, int n_samples, int white_bkgd, const float* target_rgb,
+                               const float* target_disp, float* rgb, float* disp, float* acc, float* weights, float* depth,
+                               float* alpha, float* sq_out, void* workspace, void* stream) {
+  MVIP_REQUIRE(sq_out && workspace && (target_rgb || target_disp), MVIP_E_INVALID, "mvip_composite_forward_mse: null pointer");
+  MVIP_REQUIRE(mvip_num_sms() * 8 <= 1184, MVIP_E_UNSUPPORTED, "mvip_composite_forward_mse: more than 148 SMs");
+  float* ws = static_cast<float*>(workspace);
+  // workspace: [0] ticket counter (must be zero on the first call: the kernel resets it), [4 ...] per-block partials
+  const MseArgs mse = {target_rgb, target_disp, ws + 4, reinterpret_cast<unsigned int*>(ws), sq_out, nullptr};
+  return composite_forward_impl(raw, z_vals, rays_d, rays_d_stride, noise, n_rays, n_samples, white_bkgd, rgb, disp, acc, weights,
+                                depth, alpha, mse, stream);
+}
+
+int mvip_composite_backward_mse(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                                const float* noise, int64_t n_rays, int n_samples, int white_bkgd, int detach_weights,
+                                const float* target_rgb, const float* target_disp, const float* g_sq, const float* g_rgb,
+                                const float* g_disp, const float* g_acc, const float* g_depth, const float* g_weights,
+                                const float* g_alpha, float* d_raw, void* stream) {
+  MVIP_REQUIRE(g_sq && (target_rgb || target_disp), MVIP_E_INVALID, "mvip_composite_backward_mse: null pointer");
+  const MseArgs mse = {target_rgb, target_disp, nullptr, nullptr, nullptr, g_sq};
+  return composite_backward_impl(raw, z_vals, rays_d, rays_d_stride, noise, n_rays, n_samples, white_bkgd, detach_weights, g_rgb,
+                                 g_disp, g_acc, g_depth, g_weights, g_alpha, d_raw, mse, stream);
 }
 
 }  // extern "C"

@@ -1,18 +1,18 @@
 // mlp_backward.cu — backward of the fused NeRF MLP (what autograd computes for NeRF.forward,
 // DS_NeRF/run_nerf_helpers.py:104-127), from the activation stash written by mlp_forward.cu.
 //
-// Four launches per call:
-//   1. dgrad_chain_kernel  tcgen05, tile-major like the forward: d_raw -> d hidden_pre -> d feature ->
-//                          dZ_7 .. dZ_0 (grad w.r.t. each layer's pre-activation), transposed weights
-//                          streamed by TMA, ReLU masks from the stash; every dZ tile image is bulk-stored.
-//   2. wgrad_kernel        tcgen05 with MN-major operands: dW_l = dZ_l^T X_l, K = points.  The stash
-//                          images are used as-is (the bytes of a K-major [points x features] tile are an
-//                          MN-major operand when points are the contraction).  Persistent CTAs own a
-//                          contiguous, cost-balanced range of (layer, tile) work; accumulators stay in
-//                          TMEM over the whole range and are flushed once as fp32 partials.  Four spare
-//                          warps sum the dZ columns (bias grads) from the staged operand.
-//   3. head_grads_kernel   CUDA cores: alpha_linear / rgb_linear weight + bias grads (N = 1 and 3).
-//   4. reduce_kernel       deterministic (fixed-order) sum of the partials into the caller's grad tensors.
+// Three launches per call:
+//   1. backward_fused_kernel  ONE persistent tcgen05 kernel, both roles in every CTA pair:
+//        chain  d_raw -> d hidden_pre -> d feature -> dZ_7 .. dZ_0 (grad w.r.t. each layer's pre-activation), tile-major like
+//               the forward: gradient tiles resident in tensor memory, transposed weights streamed by TMA, ReLU masks from the
+//               stash; every dZ tile image is bulk-stored to the dZ stash;
+//        wgrad  dW_l = dZ_l^T X_l (K = points) with MN-major operands: the stash images are used as-is (the bytes of a K-major
+//               [points x features] tile are an MN-major operand when points are the contraction); the pair is bound to one
+//               layer, its 256 x 256 fp32 accumulator stays in TMEM for the whole launch and is flushed once; the dZ tiles are
+//               picked up out of L2 right after the chain (on any SM) has published them; two warps sum the dZ columns
+//               (bias grads) from the staged operand.
+//   2. head_grads_kernel      CUDA cores: alpha_linear / rgb_linear weight + bias grads (N = 1 and 3).
+//   3. reduce_kernel          deterministic (fixed-order) sum of the partials into the caller's grad tensors.
 // No gradient flows to pts / viewdirs (none is required by the reference: z_samples is detached, run.py:1812).
 #include "mlp_pair.cuh"
 #include <stdlib.h>
@@ -20,10 +20,7 @@
 namespace {
 using namespace mlp;
 
-// =================================================================================================
-// 1. dgrad chain
-// =================================================================================================
-constexpr int kCSteps = 9;
+constexpr int kCSteps = 9;          // chain steps: 0 = d feature, s >= 1: dZ_{8-s}
 
 struct ChainParams {
   const uint8_t* packed;
@@ -32,316 +29,20 @@ struct ChainParams {
   uint8_t* dz;
   int64_t n_points;
   int64_t n_tiles;
-  uint32_t* flags;      // fused backward: [n_tiles][kFlagsPerTile] "dZ group stored" flags for the concurrent wgrad CTAs, or null
+  uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ group is in the stash" flags, set by the chain's store warp
 };
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
 
 __device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
 
-// =================================================================================================
-// 1b. dgrad chain, CTA pairs (cta_group::2) with the gradient tiles resident in tensor memory - same skeleton as
-//     mlp_forward_pair_kernel (mlp_forward.cu): two tile slots per CTA, one N-half (128 columns) of a layer per block of
-//     MMAs, A operand (the previous dZ, bf16) in TMEM columns [0,128) of the slot, accumulator half in [128,256);
-//     two independent issuer warps; weights (transposed chunks) in a ring of 8 KB slots shared by the two slots.
-//     Every dZ tile image is also staged in shared memory (double-buffered, 2 x 32 KB per slot) and bulk-stored.
-// =================================================================================================
-constexpr int kDThreads = 640;
-constexpr int kDSlots = 10, kDLag = 2;                                   // groups have 2 or 4 slots: 4 + 4 <= 10
-constexpr uint32_t kDSmemHeads = 0;                                      // w_alpha[256], W_rgb[3][128] fp32 (2,560 B)
-constexpr uint32_t kDSmemW = 3072;                                       // weight ring
-constexpr uint32_t kDSmemStg = kDSmemW + kDSlots * kSlotBytes2;          // staging: two 4 KB pieces (32 rows of a dZ chunk image) per epilogue warp
-constexpr uint32_t kDSmemBytes = kDSmemStg + 16 * 2 * 4096;              // 216,064
-constexpr int kDGroupsPerIter = 18;
-
-// first_it / it_stride: this cluster's first tile quad and the number of clusters working on the chain
-__device__ __forceinline__ void dgrad_pair_body(const ChainParams& p, const int64_t first_it, const int64_t it_stride) {
-  constexpr int kG = kGroupBars2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_gfull[kG], bar_gempty[kG], bar_acc[2], bar_act[2], bar_hi[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int64_t n_quads = (p.n_tiles + 3) / 4;
-  const uint8_t* wT = p.packed + kFwdBytes;
-
-  if (tid == 0) {
-    for (int i = 0; i < kG; ++i) {
-      mbar_init(&bar_gfull[i], rank == 0 ? 2 : 1);   // leader: own producer + peer relay
-      mbar_init(&bar_gempty[i], 2);                  // multicast tcgen05.commit of the two issuer warps
-    }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 16); mbar_init(&bar_hi[i], 16); }
-    mbar_fence_init();
-  }
-  if (warp == 17) tmem_alloc_2cta(&tmem_base_s, 512);
-  {
-    const float* sm = reinterpret_cast<const float*>(p.packed + kSmallOff);
-    float* heads_s = reinterpret_cast<float*>(smem + kDSmemHeads);
-    for (int i = tid; i < 256; i += kDThreads) heads_s[i] = __ldg(sm + kSmWAlpha + i);
-    for (int i = tid; i < 384; i += kDThreads) heads_s[256 + i] = __ldg(sm + kSmWRgb + i);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp < 16) {
-    // ===================== epilogue warps: slot T = warp/8, TMEM lane quarter q = warp%4, column half ch of every N-half =====================
-    reg_inc<104>();
-    const int T = warp >> 3, q = warp & 3, ch = (warp & 7) >> 2;
-    const int r = q * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t tA = tmem_base + lane_base + T * 256;
-    const uint32_t tD = tA + 128 + ch * 64;
-    const uint32_t heads_a = smem_u32(smem + kDSmemHeads);
-    uint8_t* stg = smem + kDSmemStg + warp * 2 * 4096;      // this warp's two 4 KB staging pieces
-    uint32_t acc_phase = 0, stg_buf = 0;
-    auto act_arrive = [&]() {
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(&bar_act[T]);
-        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_act[T]), 0));
-      }
-    };
-    auto hi_arrive = [&]() {
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(&bar_hi[T]);
-        else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_hi[T]), 0));
-      }
-    };
-
-    for (int64_t it = first_it; it < n_quads; it += it_stride) {
-      const int64_t tile = 4 * it + 2 * T + (int64_t)rank;
-      const bool tile_valid = tile < p.n_tiles;
-      const int64_t g = tile * kTile + r;
-      const bool valid = tile_valid && g < p.n_points;
-      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
-      const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
-
-      // This warp's 32 packed bf16 rows (64 features of dZ chunk `chunk`) -> one of its two 4 KB staging pieces -> one bulk
-      // store into the dZ stash.  Warp-local and double-buffered: no named barrier, and the store issued two calls ago is the
-      // only one that has to have left shared memory.
-      auto stage_out = [&](int chunk, const uint32_t (&pk)[32]) {
-        uint8_t* buf = stg + stg_buf * 4096;
-        stg_buf ^= 1;
-        if (lane == 0) tma_store_wait_read1();
-        __syncwarp();
-#pragma unroll
-        for (int gq = 0; gq < 8; ++gq)
-          *reinterpret_cast<uint4*>(buf + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk + q * 4096, buf, 4096);
-          tma_store_commit();                   // (possibly empty) group: keeps the wait_group accounting uniform
-        }
-      };
-
-      uint32_t pk[32];
-      const float4 dr = valid ? __ldg(p.d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-      {  // ---- input stage: d hidden_pre = (W_rgb^T d_rgb) * [hidden > 0] -> A columns [0,64) (K = 128) of step 0
-        const uint2 mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8, r, 0, ch))) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c0 = ch * 64 + 16 * b;
-          float v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            float4 w0, w1, w2;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0.x), "=f"(w0.y), "=f"(w0.z), "=f"(w0.w) : "r"(heads_a + (256 + c0 + 4 * j4) * 4));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w1.x), "=f"(w1.y), "=f"(w1.z), "=f"(w1.w) : "r"(heads_a + (384 + c0 + 4 * j4) * 4));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w) : "r"(heads_a + (512 + c0 + 4 * j4) * 4));
-            v[4 * j4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
-            v[4 * j4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
-            v[4 * j4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
-            v[4 * j4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
-          }
-          const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
-        }
-        tmem_st32(tA + ch * 32, pk);            // the previous tile's last MMAs are complete (its last accumulator was drained)
-        tmem_st_wait();
-        tc_fence_before();
-        act_arrive();                           // step 0 may start
-        stage_out(kDzHidden + ch, pk);
-      }
-
-#pragma unroll 1
-      for (int s = 0; s < kCSteps; ++s) {
-        // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
-        const int first_chunk = (s == 0) ? kDzFeat : kDzTrunk + 4 * (s - 1);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint2 mw = make_uint2(~0u, ~0u);
-          if (s >= 1) mw = valid ? __ldg(reinterpret_cast<const uint2*>(masks + mask_word_index(8 - s, r, h, ch))) : make_uint2(0u, 0u);
-          else if (!valid) mw = make_uint2(0u, 0u);
-          {
-            uint32_t raw[4][16];
-            mbar_wait(&bar_acc[T], acc_phase);
-            acc_phase ^= 1;
-            tc_fence_after();
-            if (h == 1 && s < kCSteps - 1) tmem_st32(tA + ch * 32, pk);      // half 0 of dZ -> next A operand, K columns [0,128)
-            load_half(tD, raw);
-            if (h == 1 && s < kCSteps - 1) tmem_st_wait();
-            tc_fence_before();
-            if (h == 0 || s < kCSteps - 1) act_arrive();   // h = 0: accumulator drained; h = 1: A[0,128) ready + accumulator drained
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              float v[16];
-              if (s == 1) {
-                const int c0 = h * 128 + ch * 64 + 16 * b;
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  float4 w;
-                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(heads_a + (c0 + 4 * j4) * 4));
-                  v[4 * j4 + 0] = __uint_as_float(raw[b][4 * j4 + 0]) + dr.w * w.x;
-                  v[4 * j4 + 1] = __uint_as_float(raw[b][4 * j4 + 1]) + dr.w * w.y;
-                  v[4 * j4 + 2] = __uint_as_float(raw[b][4 * j4 + 2]) + dr.w * w.z;
-                  v[4 * j4 + 3] = __uint_as_float(raw[b][4 * j4 + 3]) + dr.w * w.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[b][j]);
-              }
-              const uint32_t m = (b < 2 ? mw.x : mw.y) >> (8 * (b & 1));
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[8 * b + i] = mask_bf16x2(pack_bf16x2(v[2 * i], v[2 * i + 1]), (m >> i) & 0x00010001u);
-            }
-          }
-          if (h == 1 && s < kCSteps - 1) {
-            tmem_st32(tA + 64 + ch * 32, pk);
-            tmem_st_wait();
-            tc_fence_before();
-            hi_arrive();                        // A[128,256) ready
-          }
-          stage_out(first_chunk + 2 * h + ch, pk);
-        }
-      }
-    }
-    if (lane == 0) tma_store_wait_all0();
-  } else {
-    reg_dec<64>();
-    if (warp == 16) {
-      // ===================== TMA producer: this CTA's 64 rows of every (step, N-half, K chunk), once per quad =====================
-      if (lane == 0) {
-        uint32_t j = 0; int slot = 0;
-        for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          int cbase = 0;
-          for (int s = 0; s < kCSteps; ++s) {
-            const int n = chain_nchunks(s);
-            for (int h = 0; h < 2; ++h, ++j) {
-              if (j >= (uint32_t)kDLag) mbar_wait(&bar_gempty[(j - kDLag) % kG], ((j - kDLag) / kG) & 1u);
-              uint64_t* full = &bar_gfull[j % kG];
-              mbar_arrive_expect_tx(full, (uint32_t)n * kSlotBytes2);
-              for (int ci = 0; ci < n; ++ci) {
-                const uint8_t* src = wT + (size_t)(cbase + ci) * kW256 + (size_t)(2 * h + (int)rank) * kSlotBytes2;
-                tma_load_1d(smem + kDSmemW + slot * kSlotBytes2, src, kSlotBytes2, full);
-                if (++slot == kDSlots) slot = 0;
-              }
-            }
-            cbase += n;
-          }
-        }
-      }
-    } else if (warp == 19 && rank == 1) {
-      if (lane == 0) {
-        uint32_t j = 0;
-        for (int64_t it = first_it; it < n_quads; it += it_stride) {
-          for (int c = 0; c < kDGroupsPerIter; ++c, ++j) {
-            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
-            mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
-          }
-        }
-      }
-    } else if (warp >= 18 && rank == 0) {
-      // ===================== MMA issuers (leader CTA): warp 18 -> slot X, warp 19 -> slot Y =====================
-      const int T = warp - 18;
-      uint32_t act_phase = 0, hi_phase = 0, j = 0;
-      const uint32_t idesc = umma_idesc_bf16(256, 128, 0, 0);
-      const uint32_t tA = tmem_base + T * 256;
-      const uint32_t tDm = tA + 128;
-      const uint32_t w_lo = desc_lo2(smem_u32(smem) + kDSmemW);
-      const uint32_t w_end = w_lo + kDSlots * (kSlotBytes2 >> 4);
-      uint32_t bpos = w_lo;
-      auto next_slot = [&](uint32_t b) { b += (kSlotBytes2 >> 4); return b == w_end ? w_lo : b; };
-      for (int64_t it = first_it; it < n_quads; it += it_stride) {
-#pragma unroll 1
-        for (int s = 0; s < kCSteps; ++s) {
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h, ++j) {
-            const uint32_t b1 = bpos, b2 = next_slot(b1), b3 = next_slot(b2), b4 = next_slot(b3);
-            bpos = (s == 0) ? b3 : next_slot(b4);
-            uint64_t* gempty = &bar_gempty[j % kG];
-            mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
-            mbar_wait(&bar_act[T], act_phase);
-            act_phase ^= 1;
-            tc_fence_after();
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + kk * 8, b1 + kk * 2, idesc, kk > 0 ? 1u : 0u);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 32 + kk * 8, b2 + kk * 2, idesc, 1u);
-              if (s == 0) {
-                umma_commit_2cta(gempty, 3);
-                umma_commit_2cta(&bar_acc[T], 3);
-              }
-            }
-            __syncwarp();
-            if (s > 0) {
-              if (h == 0) {
-                mbar_wait(&bar_hi[T], hi_phase);
-                hi_phase ^= 1;
-                tc_fence_after();
-              }
-              if (elect_one_sync()) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 64 + kk * 8, b3 + kk * 2, idesc, 1u);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) mma2_ts(tDm, tA + 96 + kk * 8, b4 + kk * 2, idesc, 1u);
-                umma_commit_2cta(gempty, 3);
-                umma_commit_2cta(&bar_acc[T], 3);
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1) dgrad_pair_kernel(const ChainParams p) {
-  dgrad_pair_body(p, blockIdx.x >> 1, gridDim.x >> 1);
-}
-
-// =================================================================================================
-// 2. wgrad
-// =================================================================================================
-constexpr int kWThreads = 256;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 bias sums + drain
-constexpr int kWStages = 3;
 constexpr uint32_t kHalf = kActChunk / 2;                // 64 points of a chunk image
-constexpr uint32_t kWStageA = 0, kWStageB = 4 * kHalf;   // A: <=4 half chunks, B: <=5 half chunks
-constexpr uint32_t kWStageBytes = 9 * kHalf;             // 72 KB
-constexpr uint32_t kWSmemBytes = kWStages * kWStageBytes;  // 216 KB
 constexpr int kNumItems = 11;
 constexpr size_t kPartialSlotBytes = (size_t)256 * 320 * sizeof(float);
-constexpr int kMaxCtas = 160;
-constexpr int kFusedSlots = 80;                     // partial slots [0, 80): one per CTA pair of the fused backward
-constexpr int kMaxSlots = kFusedSlots + 2 * kMaxCtas;   // then two per wgrad_kernel CTA
+constexpr int kFusedSlots = 80;                          // partial slots: one per CTA pair (74 on a B200)
 
+// cycle counters of cluster 0 (debug aid, mvip_debug_wgrad_profile): [0] chain issuer total, [1] waiting for the epilogue,
+// [2] waiting for weights, [3] wgrad issuer total, [4] waiting for operands, [5] wgrad producer: flag wait, [6] stage wait, [7] total
 __device__ unsigned long long g_wprof[8];
-#ifndef MVIP_FLAG_MODE
-#define MVIP_FLAG_MODE 0
-#endif
 #ifdef MVIP_TRACE_BWD
 // event stamps of epilogue warp 0 (lane 0) of cluster 0, leader CTA, for the 4th tile pair: [half-step 0..18][event]
 __device__ long long g_btrace[20][12];
@@ -349,17 +50,19 @@ __device__ long long g_btrace[20][12];
 #else
 #define BTR(hs, ev)
 #endif
+
+// ---- geometry of the weight-gradient partial slots, one entry per (parameter, column block): used by the reduce ----
 struct WItem {
   int a_chunk;      // first dZ-stash chunk of the M side
   int m_blocks;     // 1 (128 output rows) or 2 (256)
-  int nb;           // number of 64-wide B chunks
+  int nb;           // number of 64-wide B chunks: a slot row has 64 nb floats
   int b_chunk[5];   // forward-stash chunk index of each
   int dst;          // parameter index of the weight
   int ld;           // its leading dimension
   int col[5];       // destination column of each B chunk
   int valid[5];     // valid columns of each B chunk
   int bias;         // parameter index of the bias grad computed with this item, or -1
-  int cost;         // 8 KB units per 64-point stage
+  int cost;         // (unused by the fused backward)
 };
 
 __constant__ WItem kItems[kNumItems] = {
@@ -384,7 +87,7 @@ __constant__ WItem kItems[kNumItems] = {
 constexpr int kRealItems = kNumItems;
 
 struct Segment {
-  int item;       // -1 = empty
+  int item;       // kItems index of the slot, -1 = empty
   int t0, t1;     // tiles t0, t0 + stride, ... < t1
   int stride;
 };
@@ -393,245 +96,32 @@ struct WParams {
   const uint8_t* stash;
   const uint8_t* dz;
   int64_t n_tiles;
-  float* partials;        // [grid][2] slots of kPartialSlotBytes
-  float* bias_partials;   // [grid][2][256]
-  Segment* segs;          // [grid][2]
-  uint32_t item_mask;     // wgrad_kernel works on the items of this mask (the fused backward covers the others)
-  int slot_base;          // first partial slot of wgrad_kernel
+  float* partials;        // [kFusedSlots] slots of kPartialSlotBytes
+  float* bias_partials;   // [kFusedSlots][256]
+  Segment* segs;          // [kFusedSlots]
 };
-__device__ __forceinline__ int item_flag(int item) { return item <= 4 ? item : (item == 5 ? 4 : item - 1); }
-
-// Cost-balanced static schedule: CTA b owns the cost range [b*C/G, (b+1)*C/G) of the concatenated
-// (item, tile) list; boundaries are snapped to tiles.  Returns up to 2 segments.
-__device__ __forceinline__ int schedule(int b, int G, int64_t n_tiles, uint32_t item_mask, Segment* out) {
-  int64_t total = 0;
-  for (int i = 0; i < kRealItems; ++i)
-    if ((item_mask >> i) & 1u) total += (int64_t)kItems[i].cost * n_tiles;
-  const int64_t lo = total * b / G, hi = total * (b + 1) / G;
-  int n = 0;
-  int64_t base = 0;
-  for (int i = 0; i < kRealItems && n < 2; ++i) {
-    if (!((item_mask >> i) & 1u)) continue;
-    const int64_t c = kItems[i].cost;
-    const int64_t end = base + c * n_tiles;
-    // tiles of item i whose start cost lies in [lo, hi)
-    int64_t t0 = lo <= base ? 0 : (lo - base + c - 1) / c;
-    int64_t t1 = hi >= end ? n_tiles : (hi - base + c - 1) / c;
-    if (t0 < 0) t0 = 0;
-    if (t1 > n_tiles) t1 = n_tiles;
-    if (t1 > t0 && hi > base && lo < end) {
-      out[n].item = i; out[n].t0 = (int)t0; out[n].t1 = (int)t1; out[n].stride = 1;
-      ++n;
-    }
-    base = end;
-  }
-  return n;
-}
-
-// cta / n_ctas: index of this CTA among the wgrad CTAs.  Uses warps 0..7 of the block (more are allowed and idle).
-__device__ __forceinline__ void wgrad_body(const WParams& p, const int cta, const int n_ctas) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[kWStages], bar_empty[kWStages], bar_acc, bar_drained;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ Segment seg_s[2];
-  __shared__ int nseg_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int i = 0; i < kWStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1 + 4); }
-    mbar_init(&bar_acc, 1);
-    mbar_init(&bar_drained, 4);
-    mbar_fence_init();
-    Segment sg[2];
-    sg[0].item = sg[1].item = -1; sg[0].t0 = sg[0].t1 = sg[1].t0 = sg[1].t1 = 0; sg[0].stride = sg[1].stride = 1;
-    nseg_s = schedule(cta, n_ctas, p.n_tiles, p.item_mask, sg);
-    seg_s[0] = sg[0]; seg_s[1] = sg[1];
-    p.segs[p.slot_base + cta * 2 + 0] = sg[0];
-    p.segs[p.slot_base + cta * 2 + 1] = sg[1];
-  }
-  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const int nseg = nseg_s;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      long long pw = 0, pf = 0, pt0 = clock64();
-      const uint64_t pol = l2_policy_evict_first();      // both operand streams are read exactly once
-      for (int sg = 0; sg < nseg; ++sg) {
-        const WItem& itm = kItems[seg_s[sg].item];
-        const int na = 2 * itm.m_blocks;
-        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
-          const uint8_t* dz_tile = p.dz + (size_t)t * kDzTileBytes;
-          const uint8_t* st_tile = p.stash + (size_t)t * kStashTileBytes;
-          for (int h = 0; h < 2; ++h) {
-            uint8_t* sbase = smem + stage * kWStageBytes;
-            long long tw = clock64();
-            mbar_wait(&bar_empty[stage], phase ^ 1);
-            pw += clock64() - tw;
-            mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(na + itm.nb) * kHalf);
-            for (int j = 0; j < na; ++j)
-              tma_load_1d_hint(sbase + kWStageA + j * kHalf, dz_tile + (size_t)(itm.a_chunk + j) * kActChunk + h * kHalf, kHalf,
-                               &bar_full[stage], pol);
-            for (int j = 0; j < itm.nb; ++j)
-              tma_load_1d_hint(sbase + kWStageB + j * kHalf, st_tile + (size_t)itm.b_chunk[j] * kActChunk + h * kHalf, kHalf,
-                               &bar_full[stage], pol);
-            if (++stage == kWStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-      if (cta == 0) { g_wprof[0] = pw; g_wprof[1] = clock64() - pt0; g_wprof[6] = pf; }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (all lanes run the loop, one elected lane issues) =====================
-    {
-      int stage = 0; uint32_t phase = 0; uint32_t drained_phase = 0;
-      long long mw = 0, mt0 = clock64();
-      for (int sg = 0; sg < nseg; ++sg) {
-        const WItem& itm = kItems[seg_s[sg].item];
-        const int ntot = 64 * itm.nb;                        // accumulator columns per M block
-        const int n_main = itm.nb > 4 ? 256 : ntot;
-        const uint32_t idesc_main = umma_idesc_bf16(128, n_main, 1, 1);
-        const uint32_t idesc_tail = umma_idesc_bf16(128, 64, 1, 1);
-        if (sg > 0) {  // previous segment's accumulators must have been drained
-          mbar_wait(&bar_drained, drained_phase);
-          drained_phase ^= 1;
-          tc_fence_after();
-        }
-        bool first = true;
-        const bool two_m = itm.m_blocks == 2, tail = itm.nb > 4;
-        const uint32_t d0 = tmem_base, d1 = tmem_base + ntot;
-        for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
-          for (int h = 0; h < 2; ++h) {
-            // descriptor low words of this stage: A = dZ half chunks (M side), B = forward-stash half chunks; 16 points per MMA
-            const uint32_t sbase = smem_u32(smem) + stage * kWStageBytes;
-            const uint32_t a_lo = desc_lo_mn(sbase + kWStageA, kHalf), b_lo = desc_lo_mn(sbase + kWStageB, kHalf);
-            long long tw = clock64();
-            mbar_wait(&bar_full[stage], phase);
-            mw += clock64() - tw;
-            tc_fence_after();
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t accum = (first && ks == 0) ? 0u : 1u;
-                const uint32_t ko = (uint32_t)ks * (2048u >> 4);
-                mma1_ss(d0, a_lo + ko, b_lo + ko, idesc_main, accum);
-                if (tail) mma1_ss(d0 + 256, a_lo + ko, b_lo + ko + (4 * kHalf >> 4), idesc_tail, accum);
-                if (two_m) mma1_ss(d1, a_lo + ko + (2 * kHalf >> 4), b_lo + ko, idesc_main, accum);
-              }
-              umma_commit(&bar_empty[stage]);
-            }
-            __syncwarp();
-            first = false;
-            if (++stage == kWStages) { stage = 0; phase ^= 1; }
-          }
-        }
-        if (elect_one_sync()) umma_commit(&bar_acc);
-        __syncwarp();
-      }
-      if (cta == 0 && lane == 0) { g_wprof[2] = mw; g_wprof[3] = clock64() - mt0; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== bias column sums + accumulator drain =====================
-    const int t4 = tid - 128;                 // 0..127
-    const int w4 = warp - 4;
-    const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
-    int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
-    long long bw_ = 0, bt0 = clock64();
-    for (int sg = 0; sg < nseg; ++sg) {
-      const WItem& itm = kItems[seg_s[sg].item];
-      const int ntot = 64 * itm.nb;
-      const bool do_bias = itm.bias >= 0 && (t4 < 64 * itm.m_blocks);
-      // thread t4 owns dZ features 2*t4, 2*t4+1: chunk t4/32, 16-byte group (t4%32)/4, word (t4%4)
-      const uint32_t boff = (uint32_t)(t4 >> 5) * kHalf;
-      const int bg = (t4 & 31) >> 2;
-      const uint32_t bw = (uint32_t)(t4 & 3) * 4;
-      float b0 = 0.f, b1 = 0.f;
-      for (int t = seg_s[sg].t0; t < seg_s[sg].t1; t += seg_s[sg].stride) {
-        for (int h = 0; h < 2; ++h) {
-          long long tw = clock64();
-          mbar_wait(&bar_full[stage], phase);
-          bw_ += clock64() - tw;
-          if (do_bias) {
-            // explicit shared-space loads with per-thread row-phase offsets (row = 8 i + k): generic loads with 64-bit
-            // address arithmetic made this loop the slowest stage of the pipeline (1,900 cycles vs 1,400 for the MMAs)
-            const uint32_t a32 = smem_u32(smem) + stage * kWStageBytes + kWStageA + boff + bw;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                uint32_t pr;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
-                b0 += __uint_as_float(pr << 16);
-                b1 += __uint_as_float(pr & 0xffff0000u);
-              }
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_empty[stage]);
-          if (++stage == kWStages) { stage = 0; phase ^= 1; }
-        }
-      }
-      float* bias_out = p.bias_partials + ((size_t)p.slot_base + cta * 2 + sg) * 256;
-      if (do_bias) { bias_out[2 * t4] = b0; bias_out[2 * t4 + 1] = b1; }
-      // drain: TMEM lane i of M block m = output row 128 m + i; columns = input features
-      mbar_wait(&bar_acc, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      float* part = p.partials + ((size_t)p.slot_base + cta * 2 + sg) * (kPartialSlotBytes / sizeof(float));
-      for (int m = 0; m < itm.m_blocks; ++m) {
-        float* prow = part + (size_t)(128 * m + t4) * ntot;
-        for (int c0 = 0; c0 < ntot; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + lane_base + m * ntot + c0, acc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                                                                    __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_drained);
-    }
-    if (cta == 0 && tid == 128) { g_wprof[4] = bw_; g_wprof[5] = clock64() - bt0; }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const WParams p) { wgrad_body(p, blockIdx.x, gridDim.x); }
 
 // =================================================================================================
-// 2b. FUSED backward: the dgrad chain and the weight-gradient GEMMs of the eight 256 x 256 layers in ONE persistent launch,
-//     BOTH roles in EVERY CTA pair, dZ handed from the chain to wgrad through L2.
+// 1. FUSED backward: the dgrad chain and ALL weight-gradient GEMMs in ONE persistent launch, BOTH roles in EVERY CTA pair,
+//    dZ handed from the chain to wgrad through L2.
 //
-//     Stand-alone, wgrad re-reads the whole dZ stash (4.9 KB / point) from HBM after the chain has written it, and the
-//     chain leaves the tensor pipe idle while its epilogue warps work (it is bound by their instruction issue, not by
-//     HBM).  Here every CTA pair runs
-//       * the chain on ONE tile slot per CTA (TMEM columns [0, 256): A operand + one accumulator half, exactly the slot
-//         of dgrad_pair_kernel), tile pairs taken round-robin over the clusters, and
-//       * a cta_group::2 wgrad (M = 256 dZ features: 128 per CTA, N = 256 input features: B split 128 per CTA,
-//         K = points) whose 256 x 256 fp32 accumulator lives in TMEM columns [256, 512) of both CTAs for the whole
-//         launch; the pair is bound to ONE layer (item) and consumes that layer's dZ of every n-th tile as soon as the
-//         chain that produced it - on any SM - has published it: per-(tile, group) counters in global memory,
-//         incremented with red.release.gpu by each of the 8 epilogue warps once ITS bulk stores of the group are
-//         complete (cp.async.bulk.wait_group), polled with ld.acquire.gpu + fence.proxy.async by the wgrad producer.
-//     The dZ lines are read back while they are still in the 126 MB L2 (the chains work on a window of 148 consecutive
-//     tiles = 90 MB of dZ, every consumer follows the window), so HBM sees the forward stash once (read) and the dZ
-//     write-back; the wgrad MMAs fill the tensor pipe while the chain's epilogue runs.  The chain never waits for wgrad
-//     (dZ has its full-size buffer), wgrad only waits for counters, all CTAs are resident (grid <= #SMs): no deadlock.
-//     Shared memory per CTA: chain weight ring 8 x 8 KB, chain staging 8 warps x 2 x 4 KB, wgrad ring 3 x 32 KB.
-//     The 64-wide items (pts_linears.0, the PE part of pts_linears.5) and views_linears are left to wgrad_kernel.
+//     With separate kernels wgrad re-reads the whole dZ stash (4.9 KB / point) from HBM after the chain has written it, and
+//     the chain leaves the tensor pipe idle while its epilogue warps work (it is bound by their latency, not by HBM).
+//     Here every CTA pair runs
+//       * the chain on ONE tile slot per CTA (TMEM columns [0, 256): A operand + one accumulator half), tile pairs taken
+//         round-robin over the clusters.  The epilogue warps write packed bf16 rows into two 32 KB staging buffers; a
+//         dedicated store warp sends each buffer to the dZ stash as one bulk store and, three times per tile, waits for
+//         its stores to be complete, issues ONE gpu-scope release fence and sets the flags of the groups that went out
+//         (a red.release.gpu per group on the epilogue warps cost them 3,000 - 5,000 cycles each time);
+//       * a cta_group::2 wgrad (M = 256: 128 rows per CTA, N <= 256: B split over the CTAs, K = points) whose fp32
+//         accumulator lives in TMEM columns [256, 512) of both CTAs for the whole launch; the pair is bound to ONE work
+//         item (kFItems) and consumes its operands of every n-th tile as soon as the chain that produced the dZ group - on
+//         any SM - has published it: ld.acquire.gpu + fence.proxy.async, then TMA loads that hit L2.
+//     The chains work on a window of 148 consecutive tiles (90 MB of dZ) and every consumer follows the window, so HBM
+//     sees the forward stash once (read) and the dZ write-back; the wgrad MMAs fill the tensor pipe while the chain's
+//     epilogue runs (cluster 0: pipe busy ~82 % of the time).  The chain never waits for wgrad (dZ has its full-size
+//     buffer), wgrad only waits for flags, all CTAs are resident (grid <= #SMs): no deadlock.
+//     Shared memory per CTA: chain weight ring 8 x 8 KB, dZ staging 2 x 32 KB, wgrad ring 3 x 32 KB.
 // =================================================================================================
 constexpr int kFThreads = 512;          // warps 0-7 chain epilogue (0-3 also drain the wgrad accumulator at the end), 8 chain TMA,
                                         // 9 TMEM alloc / chain relay, 10 chain MMA, 11 wgrad TMA, 12 wgrad MMA / relay, 13-14 bias sums,
@@ -644,17 +134,53 @@ constexpr uint32_t kFSmemW = 0;
 constexpr uint32_t kFSmemStg = kFSmemW + kFSlots * kSlotBytes2;           //  65,536
 constexpr uint32_t kFSmemWg = kFSmemStg + 2 * 2 * kActChunk;              // 131,072
 constexpr uint32_t kFSmemBytes = kFSmemWg + kFStages * kFStageBytes;      // 229,376
-constexpr int kFusedItems = 8;
-__constant__ int kFusedItemList[kFusedItems] = {1, 2, 3, 4, 6, 7, 8, 9};  // kItems indices: feature, L7, L6, L5 (h part), L4 .. L1
-constexpr uint32_t kFusedItemMask = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 6) | (1u << 7) | (1u << 8) | (1u << 9);
+// ---- work items of the wgrad role: every one is a cta_group::2 MMA  D[256 x N] += A^T[256 x 64 points] B[64 points x N]
+//      with A = 2 half chunk images per CTA (its 128 M rows) and B = n_b half chunk images per CTA (its N / 2 columns).
+//   full   (8 x): A = dZ_l (256 features), B = X_l (256 features), N = 256.
+//   L0 / L5 PE part: A = dZ_0 / dZ_5, B = PE(pts) given by BOTH CTAs (N = 128: columns [64, 128) duplicate [0, 64)).
+//   views, feature part: TRANSPOSED - A = feature (256), B = d hidden_pre (128 = 64 per CTA), D[m = feature][n = hidden].
+//   views, PE(viewdir) part: A = d hidden_pre given by BOTH CTAs (rows [128, 256) duplicate), B = PE(viewdir) by both, N = 128.
+struct FItem {
+  int slot_item;         // kItems index the partial slot belongs to (geometry of the reduce)
+  int flag;              // dZ group the item waits for
+  int a_src, b_src;      // 0: dZ stash, 1: forward stash
+  int a_chunk[2][2];     // [rank][j]
+  int b_chunk[2][2];     // [rank][j], j < n_b
+  int n_b, n_mma;        // B half chunks per CTA; MMA N
+  int transposed;        // drain: D[m][n] -> part[n * ld + 128 rank + m]  (else part[(128 rank + m) * ld + col0 + n])
+  int ld, col0, n_cols;  // slot geometry
+  int drain_ranks;       // bit r: CTA r writes its D rows
+  int bias_ranks;        // bit r: CTA r writes its 128 bias sums (column sums of ITS A operand); other CTAs write zeros
+  int zero_lo, zero_hi;  // columns [zero_lo, zero_hi) of the 128 rows of the slot are zero-filled (the other views item owns them)
+  int cost;              // relative cost (pairs are dealt out in proportion)
+};
+constexpr int kFusedItems = 12;
+#define MVIP_FULL_ITEM(it, fl, a0, b0) {it, fl, 0, 1, {{a0, a0 + 1}, {a0 + 2, a0 + 3}}, {{b0, b0 + 1}, {b0 + 2, b0 + 3}}, 2, 256, 0, 256, 0, 256, 3, 3, 0, 0, 10}
+__constant__ FItem kFItems[kFusedItems] = {
+    MVIP_FULL_ITEM(1, 1, kDzFeat, 29),             // feature_linear   : d feature^T h8
+    MVIP_FULL_ITEM(2, 2, kDzTrunk + 0, 25),        // pts_linears.7
+    MVIP_FULL_ITEM(3, 3, kDzTrunk + 4, 21),        // pts_linears.6
+    MVIP_FULL_ITEM(4, 4, kDzTrunk + 8, 17),        // pts_linears.5, h part
+    MVIP_FULL_ITEM(6, 5, kDzTrunk + 12, 13),       // pts_linears.4
+    MVIP_FULL_ITEM(7, 6, kDzTrunk + 16, 9),        // pts_linears.3
+    MVIP_FULL_ITEM(8, 7, kDzTrunk + 20, 5),        // pts_linears.2
+    MVIP_FULL_ITEM(9, 8, kDzTrunk + 24, 1),        // pts_linears.1
+    // pts_linears.5, PE part (no bias: it comes with the h part)
+    {5, 4, 0, 1, {{kDzTrunk + 8, kDzTrunk + 9}, {kDzTrunk + 10, kDzTrunk + 11}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 0, 0, 0, 7},
+    // pts_linears.0
+    {10, 9, 0, 1, {{kDzTrunk + 28, kDzTrunk + 29}, {kDzTrunk + 30, kDzTrunk + 31}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 3, 0, 0, 7},
+    // views_linears.0, feature part (transposed)
+    {0, 0, 1, 0, {{33, 34}, {35, 36}}, {{kDzHidden, 0}, {kDzHidden + 1, 0}}, 1, 128, 1, 320, 0, 128, 3, 0, 256, 320, 7},
+    // views_linears.0, PE(viewdir) part + bias
+    {0, 0, 0, 1, {{kDzHidden, kDzHidden + 1}, {kDzHidden, kDzHidden + 1}}, {{37, 0}, {37, 0}}, 1, 128, 0, 320, 256, 64, 1, 1, 0, 256, 7},
+};
+struct FusedPlan {          // host-computed: which item each CTA pair works on, as the k-th of n pairs on that item
+  unsigned char item[kFusedSlots], k[kFusedSlots], n[kFusedSlots];
+};
 
-__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
-backward_fused_kernel(const ChainParams p, const WParams wp) {
+backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan plan) {
   constexpr int kG = kGroupBars2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -669,10 +195,9 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
   const int64_t n_pairs = (p.n_tiles + 1) / 2;
   const uint8_t* wT = p.packed + kFwdBytes;
 
-  // wgrad assignment of this pair: item j = cluster % 8, k-th of n_j pairs on it, tiles k, k + n_j, ...
-  const int wj = cluster % kFusedItems, wk = cluster / kFusedItems;
-  const int wn = n_clusters / kFusedItems + (wj < n_clusters % kFusedItems ? 1 : 0);
-  const int witem = kFusedItemList[wj];
+  // wgrad assignment of this pair: the wk-th of wn pairs on fused item wj: tiles wk, wk + wn, ...
+  const int wj = plan.item[cluster], wk = plan.k[cluster], wn = plan.n[cluster];
+  const FItem& fit = kFItems[wj];
   const bool w_active = wk < p.n_tiles;
 
   if (tid == 0) {
@@ -690,7 +215,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
     mbar_fence_init();
     if (rank == 0) {
       Segment sg;
-      sg.item = w_active ? witem : -1; sg.t0 = wk; sg.t1 = w_active ? (int)p.n_tiles : wk; sg.stride = wn;
+      sg.item = w_active ? fit.slot_item : -1; sg.t0 = wk; sg.t1 = w_active ? (int)p.n_tiles : wk; sg.stride = wn;
       wp.segs[cluster] = sg;
     }
   }
@@ -732,7 +257,6 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
       const bool tile_valid = tile < p.n_tiles;
       const int64_t g = tile * kTile + r;
       const bool valid = tile_valid && g < p.n_points;
-      uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
 #ifdef MVIP_TRACE_BWD
       const bool tr_on = cluster == 0 && rank == 0 && warp == 0 && lane == 0 && it == cluster + 3 * (int64_t)n_clusters;
@@ -855,18 +379,31 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
       }
     }
     if (warp < 4 && w_active) {
-      // drain of the wgrad accumulator: TMEM lane i of CTA `rank` = output row 128 rank + i; columns = input features
+      // drain of the wgrad accumulator: TMEM lane i of CTA `rank` = M row 128 rank + i, columns = N
       mbar_wait(&bar_wacc, 0);
       tc_fence_after();
-      float* prow = wp.partials + (size_t)cluster * (kPartialSlotBytes / sizeof(float)) + (size_t)(128 * rank + r) * 256;
-      for (int c0 = 0; c0 < 256; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lane_base + 256 + c0, acc);
-        tmem_ld_wait();
+      float* part = wp.partials + (size_t)cluster * (kPartialSlotBytes / sizeof(float));
+      if ((fit.drain_ranks >> rank) & 1) {
+        for (int c0 = 0; c0 < fit.n_cols; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_base + 256 + c0, acc);
+          tmem_ld_wait();
+          if (fit.transposed) {       // D[m][n] -> part[n][128 rank + m]: consecutive lanes write consecutive floats
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                                                                  __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            for (int j = 0; j < 32; ++j) part[(size_t)(c0 + j) * fit.ld + 128 * rank + r] = __uint_as_float(acc[j]);
+          } else {
+            float* prow = part + (size_t)(128 * rank + r) * fit.ld + fit.col0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                                                 __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+          }
+        }
+      }
+      if (fit.zero_hi > fit.zero_lo) {   // the two views items share kItems[0]'s slot geometry: each zero-fills the other's columns
+        const int row = 64 * (int)rank + (r & 63), half = r >> 6, w = (fit.zero_hi - fit.zero_lo) / 2;
+        float* z = part + (size_t)row * fit.ld + fit.zero_lo + half * w;
+        for (int j = 0; j < w; j += 4) *reinterpret_cast<float4*>(z + j) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   } else if (warp == 8) {
@@ -966,9 +503,9 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
   } else if (warp == 11) {
     // ===================== wgrad TMA producer (both CTAs): this CTA's 128 dZ features and 128 input features of a 64-point stage =====================
     if (lane == 0 && w_active) {
-      const WItem& itm = kItems[witem];
-      const int fl = item_flag(witem);
+      const int fl = fit.flag;
       const uint64_t pol = l2_policy_evict_first();
+      const uint32_t stage_tx = (uint32_t)(2 + fit.n_b) * kHalf;
       int stage = 0; uint32_t phase = 0;
       long long p_flag = 0, p_empty = 0, p_t0 = clock64();
       for (int t = wk; t < p.n_tiles; t += wn) {
@@ -988,13 +525,13 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
           long long te = clock64();
           mbar_wait(&bar_wempty[stage], phase ^ 1);
           p_empty += clock64() - te;
-          mbar_arrive_expect_tx(&bar_wfull[stage], kFStageBytes);
+          mbar_arrive_expect_tx(&bar_wfull[stage], stage_tx);
+          const uint8_t* a_tile = fit.a_src ? st_tile : dz_tile;
+          const uint8_t* b_tile = fit.b_src ? st_tile : dz_tile;
           for (int j = 0; j < 2; ++j)
-            tma_load_1d_hint(sbase + j * kHalf, dz_tile + (size_t)(itm.a_chunk + 2 * (int)rank + j) * kActChunk + h * kHalf, kHalf,
-                             &bar_wfull[stage], pol);
-          for (int j = 0; j < 2; ++j)
-            tma_load_1d_hint(sbase + (2 + j) * kHalf, st_tile + (size_t)itm.b_chunk[2 * (int)rank + j] * kActChunk + h * kHalf, kHalf,
-                             &bar_wfull[stage], pol);
+            tma_load_1d_hint(sbase + j * kHalf, a_tile + (size_t)fit.a_chunk[rank][j] * kActChunk + h * kHalf, kHalf, &bar_wfull[stage], pol);
+          for (int j = 0; j < fit.n_b; ++j)
+            tma_load_1d_hint(sbase + (2 + j) * kHalf, b_tile + (size_t)fit.b_chunk[rank][j] * kActChunk + h * kHalf, kHalf, &bar_wfull[stage], pol);
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -1005,7 +542,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
     if (w_active) {
       int stage = 0; uint32_t phase = 0;
       if (rank == 0) {
-        const uint32_t idesc = umma_idesc_bf16(256, 256, 1, 1);
+        const uint32_t idesc = umma_idesc_bf16(256, fit.n_mma, 1, 1);
         const uint32_t d0 = tmem_base + 256;
         bool first = true;
         long long w_t0 = clock64(), w_full = 0;
@@ -1051,20 +588,23 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
     const int bg = (t4 & 31) >> 2;
     const uint32_t bw = (uint32_t)(t4 & 3) * 4;
     float b0 = 0.f, b1 = 0.f;
+    const bool do_bias = (fit.bias_ranks >> rank) & 1;
     int stage = 0; uint32_t phase = 0;
     for (int t = wk; t < p.n_tiles; t += wn) {
       for (int h = 0; h < 2; ++h) {
         mbar_wait(&bar_wfull[stage], phase);
-        const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff + bw;
+        if (do_bias) {
+          const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff + bw;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t pr;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
-            b0 += __uint_as_float(pr << 16);
-            b1 += __uint_as_float(pr & 0xffff0000u);
+            for (int i = 0; i < 8; ++i) {
+              uint32_t pr;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
+              b0 += __uint_as_float(pr << 16);
+              b1 += __uint_as_float(pr & 0xffff0000u);
+            }
           }
         }
         __syncwarp();
@@ -1072,7 +612,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp) {
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
     }
-    float* bias_out = wp.bias_partials + (size_t)cluster * 256 + 128 * rank;
+    float* bias_out = wp.bias_partials + (size_t)cluster * 256 + 128 * rank;      // zeros where this CTA contributes nothing
     bias_out[2 * t4] = b0;
     bias_out[2 * t4 + 1] = b1;
   } else if (warp == 15) {
@@ -1199,7 +739,7 @@ struct ReduceParams {
   const float* partials;
   const float* bias_partials;
   const Segment* segs;
-  int n_slots;            // partial slots in use: [0, kFusedSlots) fused backward, then two per wgrad_kernel CTA
+  int n_slots;            // partial slots in use (one per CTA pair of the fused backward)
   const float* head_partials;
   int head_grid;
   GradPtrs grads;
@@ -1213,7 +753,7 @@ constexpr int kReduceGridX = 80;     // 256 x 320 floats / 4 per thread / 256 th
 // first version walked ~30 slots (weights) and up to 1184 partials (heads) with a dependent add per load and took
 // 70 us per launch at 0.5 TB/s.
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
-  __shared__ int slots[kMaxSlots];
+  __shared__ int slots[kFusedSlots];
   __shared__ int nslots;
   __shared__ float hred[8][32];
   const int item = blockIdx.y;
@@ -1253,7 +793,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   }
   // slots of this item, in slot order: the segment table is read by all threads at once (one thread walking the 296
   // entries in global memory was 15 us of latency), then compacted from shared memory
-  __shared__ unsigned char mine[kMaxSlots];
+  __shared__ unsigned char mine[kFusedSlots];
   for (int i = threadIdx.x; i < p.n_slots; i += blockDim.x) {
     const Segment sg = p.segs[i];
     mine[i] = (sg.item == item && sg.t1 > sg.t0) ? 1 : 0;
@@ -1319,9 +859,9 @@ Workspace carve(int64_t n_points) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
   w.dz = take((size_t)num_tiles(n_points) * kDzTileBytes);
-  w.partials = take((size_t)kMaxSlots * kPartialSlotBytes);
-  w.bias = take((size_t)kMaxSlots * 256 * sizeof(float));
-  w.segs = take((size_t)kMaxSlots * sizeof(Segment));
+  w.partials = take((size_t)kFusedSlots * kPartialSlotBytes);
+  w.bias = take((size_t)kFusedSlots * 256 * sizeof(float));
+  w.segs = take((size_t)kFusedSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
   w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
@@ -1375,7 +915,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   const Workspace ws = carve(n_points);
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   const int64_t n_tiles = num_tiles(n_points);
-  const int sms = mvip_num_sms() < kMaxCtas ? mvip_num_sms() : kMaxCtas;
+  const int sms = mvip_num_sms();
 
   ChainParams cp;
   cp.packed = static_cast<const uint8_t*>(packed);
@@ -1392,27 +932,47 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   wp.partials = reinterpret_cast<float*>(wsb + ws.partials);
   wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
   wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
-  const uint32_t all_items = (1u << kNumItems) - 1u;
-  wp.item_mask = all_items & ~kFusedItemMask;
-  wp.slot_base = kFusedSlots;
-  const int n_pairs_max = sms / 2 < kFusedSlots ? sms / 2 : kFusedSlots;
+  const int clusters = sms / 2 < kFusedSlots ? sms / 2 : kFusedSlots;
+  MVIP_REQUIRE(clusters >= kFusedItems, MVIP_E_UNSUPPORTED, "mvip_mlp_backward: needs at least %d SM pairs", kFusedItems);
 
-  // 1 + 2. fused: dgrad chain + wgrad of the eight 256 x 256 layers (phase bit 1), then wgrad of the remaining items (phase bit 2)
+  // 1. fused dgrad chain + weight gradients (phase bit 1; bit 2 is kept for ABI compatibility and launches nothing)
   if (phase_mask & 1) {
+    // CTA pairs dealt out to the work items in proportion to their cost (largest remainder); always ALL pairs, whatever the
+    // number of tiles: every item needs its consumers
+    static FusedPlan plan;
+    static int plan_clusters = 0;
+    if (plan_clusters != clusters) {
+      FItem items_h[kFusedItems];
+      MVIP_CUDA_OK(cudaMemcpyFromSymbol(items_h, kFItems, sizeof(items_h)));
+      int total = 0, n_i[kFusedItems], assigned = 0;
+      for (int i = 0; i < kFusedItems; ++i) total += items_h[i].cost;
+      for (int i = 0; i < kFusedItems; ++i) { n_i[i] = clusters * items_h[i].cost / total; if (n_i[i] < 1) n_i[i] = 1; assigned += n_i[i]; }
+      while (assigned < clusters) {   // next pair to the item with the largest cost per pair
+        int best = 0;
+        for (int i = 1; i < kFusedItems; ++i)
+          if ((long long)items_h[i].cost * n_i[best] > (long long)items_h[best].cost * n_i[i]) best = i;
+        ++n_i[best]; ++assigned;
+      }
+      while (assigned > clusters) {   // (only if the floor of 1 pair per item overshot)
+        int worst = -1;
+        for (int i = 0; i < kFusedItems; ++i)
+          if (n_i[i] > 1 && (worst < 0 || (long long)items_h[i].cost * n_i[worst] < (long long)items_h[worst].cost * n_i[i])) worst = i;
+        --n_i[worst]; --assigned;
+      }
+      // interleave the items over the cluster index, so that neighbouring SM pairs work on different layers
+      int given[kFusedItems] = {0};
+      int c = 0;
+      while (c < clusters)
+        for (int i = 0; i < kFusedItems && c < clusters; ++i)
+          if (given[i] < n_i[i]) { plan.item[c] = (unsigned char)i; plan.k[c] = (unsigned char)given[i]; plan.n[c] = (unsigned char)n_i[i]; ++given[i]; ++c; }
+      plan_clusters = clusters;
+    }
     MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t), st));
     MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0xff, (size_t)kFusedSlots * sizeof(Segment), st));      // item = -1: unused slot
-    const int clusters = n_pairs_max;     // always all pairs: each of the eight fused items needs its consumers
     const size_t smem = kFSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
-    backward_fused_kernel<<<2 * clusters, kFThreads, smem, st>>>(cp, wp);
+    backward_fused_kernel<<<2 * clusters, kFThreads, smem, st>>>(cp, wp, plan);
     MVIP_LAUNCH_OK("backward_fused_kernel");
-  }
-  const int w_grid = sms;
-  if (phase_mask & 2) {
-    const size_t smem = kWSmemBytes + 1024;
-    MVIP_SMEM_OPT_IN(wgrad_kernel, smem);
-    wgrad_kernel<<<w_grid, kWThreads, smem, st>>>(wp);
-    MVIP_LAUNCH_OK("wgrad_kernel");
   }
   // 3. heads
   const int head_cap = sms * 8 < kHeadMaxBlocks ? sms * 8 : kHeadMaxBlocks;
@@ -1428,7 +988,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
     rp.partials = reinterpret_cast<const float*>(wsb + ws.partials);
     rp.bias_partials = reinterpret_cast<const float*>(wsb + ws.bias);
     rp.segs = reinterpret_cast<const Segment*>(wsb + ws.segs);
-    rp.n_slots = kFusedSlots + 2 * w_grid;
+    rp.n_slots = kFusedSlots;
     rp.head_partials = reinterpret_cast<const float*>(wsb + ws.heads);
     rp.head_grid = head_grid;
     rp.grads = gp;

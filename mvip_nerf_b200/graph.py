@@ -25,7 +25,15 @@ from .run_nerf_helpers import img2mse
 
 
 def default_loss(rgb, disp, acc, depth, extras, target, scale):
-    """img2mse(rgb, target) + img2mse(rgb0, target)   (run.py:1000, 1024-1026), scaled for data-parallel averaging"""
+    """img2mse(rgb, target) + img2mse(rgb0, target)   (run.py:1000, 1024-1026), scaled for data-parallel averaging.
+    When the render was given `_mse=(target, None)` the squared-error sums come out of the compositing kernels (`sqerr`,
+    `sqerr0`) and their gradient goes back into the compositing backward: the ~20 elementwise / reduction / autograd kernels
+    of the two img2mse calls become three scalar ops."""
+    if "sqerr" in extras:
+        sq = extras["sqerr"][0]
+        if "sqerr0" in extras:
+            sq = sq + extras["sqerr0"][0]
+        return sq * (scale / rgb.numel())
     loss = img2mse(rgb, target)
     if "rgb0" in extras:
         loss = loss + img2mse(extras["rgb0"], target)
@@ -49,6 +57,9 @@ class GraphedTrainStep:
         self.args = (H, W, focal)
         self.chunk, self.near, self.far = chunk, near, far
         self.loss_fn = loss_fn
+        # the default photometric loss is fused into the compositing kernels (64 / 128 samples per ray: what those kernels cover)
+        self.fused_loss = (loss_fn is default_loss and self.kw.get("N_samples") == 64 and self.kw.get("N_importance") in (0, 64)
+                           and target_shape is None)
         self.scale = 1.0 / mdist.world()
         self.rays = torch.zeros((2, n_rays, 3), device=self.dev)
         self.target = torch.zeros(tuple(target_shape or (n_rays, 3)), device=self.dev)
@@ -64,8 +75,9 @@ class GraphedTrainStep:
     def _forward_backward(self):
         self.opt.zero_grad(set_to_none=True)
         H, W, focal = self.args
+        mse = {"_mse": (self.target, None)} if self.fused_loss else {}
         rgb, disp, acc, depth, extras = run.render(H, W, focal, chunk=self.chunk, rays=self.rays, near=self.near, far=self.far,
-                                                   **self.kw)
+                                                   **mse, **self.kw)
         loss = self.loss_fn(rgb, disp, acc, depth, extras, self.target, self.scale)
         loss.backward()                 # GradSync hooks (if any) start each network's allreduce as its gradients complete
         if self.sync is not None:

@@ -21,8 +21,8 @@ launch_count = 0
 # bumped by optim.FusedAdam.step(): parameters changed in place without torch's version counters noticing
 param_epoch = 0
 _LAUNCHES = {"mvip_rays_from_pose": 1, "mvip_rays_from_pose_ndc": 1, "mvip_rays_pack": 1, "mvip_sample_coarse": 1, "mvip_sample_pdf": 1, "mvip_sample_fine": 1, "mvip_composite_forward": 1,
-             "mvip_composite_backward": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
-             "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 4, "mvip_selftest_umma": 1}
+             "mvip_composite_backward": 1, "mvip_composite_forward_mse": 1, "mvip_composite_backward_mse": 1, "mvip_normal_forward": 2, "mvip_normal_backward": 4, "mvip_normal_forward_xyz": 2, "mvip_normal_backward_xyz": 4, "mvip_embed": 1,
+             "mvip_mlp_pack_weights": 1, "mvip_mlp_forward": 1, "mvip_mlp_backward": 3, "mvip_selftest_umma": 1}
 
 
 class _KernelTimer:
@@ -181,7 +181,20 @@ def sample_fine(z_vals, weights, u, want_samples=True, want_inds=False, want_std
 
 
 # ---------------------------------------------------------------------------------------------- compositing
-def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_alpha=False):
+_mse_ws = {}
+
+
+def _mse_workspace(dev):
+    """ticket counter + per-block partials of the fused-loss forward: zero-filled once per device, reused by every call"""
+    ws = _mse_ws.get(dev)
+    if ws is None:
+        ws = _mse_ws[dev] = torch.zeros(_lib.load().mvip_composite_mse_workspace_bytes() // 4, device=dev, dtype=torch.float32)
+    return ws
+
+
+def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_alpha=False, target_rgb=None, target_disp=None):
+    """-> (rgb, disp, acc, weights, depth, alpha | None) [+ sq [2] = (sum (rgb - target_rgb)^2, sum (disp - target_disp)^2) when a
+    target is given: img2mse fused into the kernel, DS_NeRF/run.py:1000-1027]"""
     raw = _f32(raw, "raw")
     z_vals = _f32(z_vals, "z_vals")
     rays_d, d_stride = _rows3(rays_d, "rays_d")
@@ -194,19 +207,33 @@ def composite_forward(raw, z_vals, rays_d, noise=None, white_bkgd=False, need_al
     depth = torch.empty((N,), device=dev, dtype=torch.float32)
     weights = torch.empty((N, S), device=dev, dtype=torch.float32)
     alpha = torch.empty((N, S), device=dev, dtype=torch.float32) if need_alpha else None
+    if target_rgb is not None or target_disp is not None:
+        target_rgb, target_disp = _f32(target_rgb, "target_rgb"), _f32(target_disp, "target_disp")
+        if (target_rgb is not None and target_rgb.numel() != 3 * N) or (target_disp is not None and target_disp.numel() != N):
+            raise RuntimeError("fused-loss targets must have one row per ray")
+        sq = torch.empty((2,), device=dev, dtype=torch.float32)
+        _call("mvip_composite_forward_mse", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(noise), N, S, int(bool(white_bkgd)),
+              _ptr(target_rgb), _ptr(target_disp), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(weights), _ptr(depth), _ptr(alpha), _ptr(sq),
+              _ptr(_mse_workspace(dev)), _stream())
+        return rgb, disp, acc, weights, depth, alpha, sq
     _call("mvip_composite_forward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(noise), N, S,
           int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(weights), _ptr(depth), _ptr(alpha), _stream())
     return rgb, disp, acc, weights, depth, alpha
 
 
 def composite_backward(raw, z_vals, rays_d, noise, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth,
-                       g_weights=None, g_alpha=None):
+                       g_weights=None, g_alpha=None, target_rgb=None, target_disp=None, g_sq=None):
     raw = _f32(raw, "raw")
     z_vals = _f32(z_vals, "z_vals")
     rays_d, d_stride = _rows3(rays_d, "rays_d")
     N, S = z_vals.shape
     d_raw = torch.empty((N, S, 4), device=raw.device, dtype=torch.float32)
     args = [_f32(t, "grad") for t in (g_rgb, g_disp, g_acc, g_depth, g_weights, g_alpha)]
+    if g_sq is not None and (target_rgb is not None or target_disp is not None):
+        _call("mvip_composite_backward_mse", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(_f32(noise, "noise")), N, S,
+              int(bool(white_bkgd)), int(bool(detach_weights)), _ptr(_f32(target_rgb, "target_rgb")), _ptr(_f32(target_disp, "target_disp")),
+              _ptr(_f32(g_sq, "g_sq")), *[_ptr(a) for a in args], _ptr(d_raw), _stream())
+        return d_raw
     _call("mvip_composite_backward", _ptr(raw), _ptr(z_vals), _ptr(rays_d), d_stride, _ptr(_f32(noise, "noise")),
           N, S, int(bool(white_bkgd)), int(bool(detach_weights)), *[_ptr(a) for a in args], _ptr(d_raw), _stream())
     return d_raw
@@ -359,8 +386,8 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         accumulate = False
     ws = _aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
     arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-    if kernel_timer.on:   # one bracket per launch: fused dgrad chain + wgrad of the 256 x 256 layers, wgrad of the rest, head grads, reduce
-        for bit, label in ((1, "backward_fused_kernel"), (2, "wgrad_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
+    if kernel_timer.on:   # one bracket per launch: fused dgrad chain + weight gradients, head grads, reduce
+        for bit, label in ((1, "backward_fused_kernel"), (4, "head_grads_kernel"), (8, "reduce_kernel")):
             _call(("mvip_mlp_backward_phases", label), _ptr(packed), _ptr(d_raw), P, _ptr(stash), _ptr(ws), arr,
                   int(bool(accumulate)), bit, _stream())
     else:

@@ -82,14 +82,22 @@ class _FusedQuery:
                            netchunk=self.netchunk)
 
 
-def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=False, **kwargs):
-    """(run.py:1127-1140) render in chunks, concatenate per key."""
+def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=False, _mse=None, **kwargs):
+    """(run.py:1127-1140) render in chunks, concatenate per key.  `_mse=(target_rgb | None, target_disp | None)` (ours): per-ray
+    targets of the fused photometric losses, chunked with the rays; the squared-error sums `sqerr` / `sqerr0` are added up."""
     pieces = {}
     for i in range(0, rays_flat.shape[0], chunk):
-        ret = render_rays(rays_flat[i:i + chunk], need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+        mse = None if _mse is None else tuple(None if t is None else t.reshape(rays_flat.shape[0], -1)[i:i + chunk] for t in _mse)
+        ret = render_rays(rays_flat[i:i + chunk], need_alpha=need_alpha, detach_weights=detach_weights, _mse=mse, **kwargs)
         for k, v in ret.items():
             pieces.setdefault(k, []).append(v)
-    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
+    out = {}
+    for k, v in pieces.items():
+        if k in ("sqerr", "sqerr0"):
+            out[k] = v[0] if len(v) == 1 else torch.stack(v, 0).sum(0)
+        else:
+            out[k] = v[0] if len(v) == 1 else torch.cat(v, 0)
+    return out
 
 
 def _is_number(x):
@@ -150,7 +158,8 @@ def _assemble_rays(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_sta
 
 def _split_outputs(all_ret, sh):
     for k in all_ret:
-        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+        if k not in ("sqerr", "sqerr0"):           # per-batch sums of the fused losses: not one row per ray
+            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
@@ -231,7 +240,7 @@ def _pytest_uniform(shape, dev):
 
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., pytest=False, sigma_loss=None,
-                verbose=False, need_alpha=False, detach_weights=False, _randoms=None):
+                verbose=False, need_alpha=False, detach_weights=False, _randoms=None, _mse=None):
     """(run.py:1703-1847) volumetric rendering of one chunk of rays -> dict with the reference's keys.
 
     Random numbers are drawn on the host side in the reference's order (t_rand, coarse noise, u, fine noise)
@@ -276,13 +285,13 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         return None
 
     raw = query(network_fn, z_vals)
-    rgb_map, disp_map, acc_map, weights, depth_map, alpha = raw2outputs(
+    rgb_map, disp_map, acc_map, weights, depth_map, alpha, *sq = raw2outputs(
         raw, z_vals, rays_d, raw_noise_std, white_bkgd, need_alpha=need_alpha, detach_weights=detach_weights,
-        _noise=noise_for((N_rays, N_samples), "noise0"))
+        _noise=noise_for((N_rays, N_samples), "noise0"), _mse=_mse)
 
     z_std = None
     if N_importance > 0:
-        rgb_map_0, disp_map_0, acc_map_0, alpha0 = rgb_map, disp_map, acc_map, alpha
+        rgb_map_0, disp_map_0, acc_map_0, alpha0, sq0 = rgb_map, disp_map, acc_map, alpha, sq
         # ---- hierarchical samples: z_mid, sample_pdf, detach, sort-merge (run.py:1809-1816) ------------
         u = rnd.get("u")
         if u is None:
@@ -296,9 +305,9 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         z_vals, z_std = fs["z_merged"], fs["z_std"]
         run_fn = network_fn if network_fine is None else network_fine
         raw = query(run_fn, z_vals)
-        rgb_map, disp_map, acc_map, weights, depth_map, alpha = raw2outputs(
+        rgb_map, disp_map, acc_map, weights, depth_map, alpha, *sq = raw2outputs(
             raw, z_vals, rays_d, raw_noise_std, white_bkgd, need_alpha=need_alpha, detach_weights=detach_weights,
-            _noise=noise_for((N_rays, N_samples + N_importance), "noise1"))
+            _noise=noise_for((N_rays, N_samples + N_importance), "noise1"), _mse=_mse)
 
     ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map, 'depth_map': depth_map,
            'weights': weights, 'z_vals': z_vals}
@@ -312,6 +321,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         ret['disp0'] = disp_map_0
         ret['acc0'] = acc_map_0
         ret['z_std'] = z_std
+    if _mse is not None:             # fused img2mse: [sum (rgb - target)^2, sum (disp - target)^2] of the fine / coarse maps
+        ret['sqerr'] = sq[0]
+        if N_importance > 0:
+            ret['sqerr0'] = sq0[0]
     if DEBUG:
         for k in ret:
             if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():

@@ -279,39 +279,53 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, return_inds=Fa
 # Alpha compositing (run_nerf_helpers.py:350-404)
 # ------------------------------------------------------------------------------------------------
 class _CompositeFunction(torch.autograd.Function):
+    """raw2outputs as one forward and one backward kernel.  With `target_rgb` / `target_disp` the photometric losses are fused in
+    (img2mse of rgb / rgb0 / disp as train() uses it, run.py:1000-1027): a seventh output sq [2] = (sum (rgb_map - target_rgb)^2,
+    sum (disp_map - target_disp)^2), whose gradient is applied inside the backward kernel from the recomputed maps."""
+
     @staticmethod
-    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, need_alpha, detach_weights):
-        rgb, disp, acc, weights, depth, alpha = ops.composite_forward(raw, z_vals, rays_d, noise, white_bkgd, need_alpha)
+    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, need_alpha, detach_weights, target_rgb=None, target_disp=None):
+        fused = target_rgb is not None or target_disp is not None
+        outs = ops.composite_forward(raw, z_vals, rays_d, noise, white_bkgd, need_alpha, target_rgb, target_disp)
+        rgb, disp, acc, weights, depth, alpha = outs[:6]
         ctx.set_materialize_grads(False)   # unused outputs arrive as None (the kernel takes NULL = zeros): no fill kernels
-        ctx.save_for_backward(raw, z_vals, rays_d, noise)
+        ctx.save_for_backward(raw, z_vals, rays_d, noise, target_rgb, target_disp)
         ctx.flags = (bool(white_bkgd), bool(detach_weights), bool(need_alpha))
         if not need_alpha:
             alpha = raw.new_empty(0)
             ctx.mark_non_differentiable(alpha)
-        return rgb, disp, acc, weights, depth, alpha
+        sq = outs[6] if fused else raw.new_empty(0)
+        if not fused:
+            ctx.mark_non_differentiable(sq)
+        return rgb, disp, acc, weights, depth, alpha, sq
 
     @staticmethod
-    def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha):
-        raw, z_vals, rays_d, noise = ctx.saved_tensors
+    def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha, g_sq):
+        raw, z_vals, rays_d, noise, target_rgb, target_disp = ctx.saved_tensors
         white, detach_w, need_alpha = ctx.flags
-        if all(g is None for g in (g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha)):
-            return None, None, None, None, None, None, None
+        if all(g is None for g in (g_rgb, g_disp, g_acc, g_weights, g_depth, g_alpha, g_sq)):
+            return (None,) * 9
         d_raw = ops.composite_backward(raw, z_vals, rays_d, noise, white, detach_w, g_rgb, g_disp, g_acc, g_depth,
-                                       g_weights, g_alpha if need_alpha else None)
-        return d_raw, None, None, None, None, None, None
+                                       g_weights, g_alpha if need_alpha else None, target_rgb, target_disp, g_sq)
+        return (d_raw,) + (None,) * 8
 
 
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, need_alpha=False,
-                detach_weights=False, _noise=None):
-    """-> (rgb_map, disp_map, acc_map, weights, depth_map, alpha|None), differentiable w.r.t. raw."""
+                detach_weights=False, _noise=None, _mse=None):
+    """-> (rgb_map, disp_map, acc_map, weights, depth_map, alpha|None), differentiable w.r.t. raw.
+    `_mse=(target_rgb | None, target_disp | None)` (ours): the squared-error sums of img2mse come out of the same kernels as a
+    seventh element sq [2]."""
     noise = _noise
     if noise is None and raw_noise_std > 0.:
         noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
         if pytest:   # the reference overwrites with UNIFORM numpy randoms here (helpers:377-381)
             np.random.seed(0)
             noise = torch.Tensor(np.random.rand(*list(raw[..., 3].shape)) * raw_noise_std).to(raw.device)
-    rgb, disp, acc, weights, depth, alpha = _CompositeFunction.apply(raw, z_vals, rays_d, noise, white_bkgd,
-                                                                     need_alpha, detach_weights)
+    t_rgb, t_disp = _mse if _mse is not None else (None, None)
+    rgb, disp, acc, weights, depth, alpha, sq = _CompositeFunction.apply(raw, z_vals, rays_d, noise, white_bkgd, need_alpha,
+                                                                         detach_weights, t_rgb, t_disp)
+    if _mse is not None:
+        return rgb, disp, acc, weights, depth, (alpha if need_alpha else None), sq
     return rgb, disp, acc, weights, depth, (alpha if need_alpha else None)
 
 

@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvip_nerf_b200 import _lib, ops  # noqa: E402
 from oracle import nerf_oracle as orc  # noqa: E402
 
+if os.environ.get("MVIP_LIB"):          # experiment builds (scripts/build_variant.sh)
+    _lib.LIB_PATH = os.path.abspath(os.environ["MVIP_LIB"])
+
 dev = "cuda"
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 524288
 p = orc.init_params(1)
@@ -48,7 +51,7 @@ if os.environ.get("TRACE"):
                      r[10] - r[9], r[6] - r[10], (a[hs + 1, 0] - r[0]) if hs < 18 else 0))
     sys.exit(0)
 
-for mask, name in ((1, "backward_fused_kernel"), (2, "wgrad_kernel (small items)"), (4, "head_grads"), (8, "reduce"), (15, "all")):
+for mask, name in ((1, "backward_fused_kernel"), (4, "head_grads"), (8, "reduce"), (15, "all")):
     for _ in range(2):
         run(mask)
     torch.cuda.synchronize()

@@ -367,3 +367,45 @@ def test_render_ndc_and_rays_entry_use_fused_batch(ops, golden):
         assert np.array_equal(npy(seen["rays"]), g["ndc_rays_batch"])
     finally:
         run.batchify_rays = orig
+
+
+@pytest.mark.parametrize("S,white,noise", [(64, True, True), (128, True, False), (128, False, True)])
+def test_fused_mse_losses_match_img2mse_autograd(ops, S, white, noise):
+    """img2mse on rgb and on disp fused into the compositing kernels (DS_NeRF/run.py:1000-1027,
+    run_nerf_helpers.py:15): loss value vs the fp64 oracle maps, gradient w.r.t. raw vs torch autograd of the unfused maps
+    (the unfused backward itself is held against the reference's autograd above)."""
+    from mvip_nerf_b200 import run_nerf_helpers as h
+    rng = np.random.RandomState(S + white)
+    N = 3001                                               # ragged: not a multiple of the rays per block
+    raw_np = rng.randn(N, S, 4).astype(np.float32)
+    raw_np[..., 3] += 0.5                                   # some density on every ray: finite disp
+    z_np = np.sort(1.2 + 6.5 * rng.rand(N, S).astype(np.float32), -1)
+    rd_np = rng.randn(N, 3).astype(np.float32)
+    nz_np = rng.rand(N, S).astype(np.float32) if noise else None
+    t_rgb, t_disp = rng.rand(N, 3).astype(np.float32), (0.2 + 0.3 * rng.rand(N)).astype(np.float32)
+    w_rgb, w_disp = 1.0, 0.1                                # loss = img2mse(rgb, t) + depth_lambda * img2mse(disp, t_disp)
+    z, rd, nz = cu(z_np), cu(rd_np), (cu(nz_np) if noise else None)
+
+    raw_a = cu(raw_np).requires_grad_(True)
+    rgb, disp, acc, wts, depth, _ = h.raw2outputs(raw_a, z, rd, 1.0 if noise else 0.0, white, _noise=nz)
+    loss_a = w_rgb * h.img2mse(rgb, cu(t_rgb)) + w_disp * h.img2mse(disp, cu(t_disp)) + 0.01 * depth.mean()
+    loss_a.backward()
+
+    raw_b = cu(raw_np).requires_grad_(True)
+    rgb_b, disp_b, acc_b, wts_b, depth_b, _, sq = h.raw2outputs(raw_b, z, rd, 1.0 if noise else 0.0, white, _noise=nz,
+                                                                _mse=(cu(t_rgb), cu(t_disp)))
+    loss_b = w_rgb * sq[0] / (3 * N) + w_disp * sq[1] / N + 0.01 * depth_b.mean()      # an ordinary upstream gradient rides along
+    loss_b.backward()
+    assert torch.equal(rgb, rgb_b) and torch.equal(disp, disp_b)
+    want = orc.raw2outputs(raw_np, z_np, rd_np, nz_np, white)
+    sq_ref = [float(((want["rgb_map"].astype(np.float64) - t_rgb) ** 2).sum()), float(((want["disp_map"].astype(np.float64) - t_disp) ** 2).sum())]
+    assert abs(float(sq[0]) - sq_ref[0]) <= 2e-5 * sq_ref[0] and abs(float(sq[1]) - sq_ref[1]) <= 2e-5 * sq_ref[1]
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_a))
+    ga, gb = npy(raw_a.grad), npy(raw_b.grad)
+    assert np.abs(ga - gb).max() <= 2e-5 * np.abs(ga).max()
+    # bitwise reproducible (fixed-order reduction) and the workspace is left ready for the next call
+    sq2 = h.raw2outputs(cu(raw_np), z, rd, 1.0 if noise else 0.0, white, _noise=nz, _mse=(cu(t_rgb), cu(t_disp)))[6]
+    assert torch.equal(sq, sq2)
+    # one target only
+    sq3 = h.raw2outputs(cu(raw_np), z, rd, 1.0 if noise else 0.0, white, _noise=nz, _mse=(cu(t_rgb), None))[6]
+    assert float(sq3[0]) == float(sq[0]) and float(sq3[1]) == 0.0
