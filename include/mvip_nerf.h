@@ -237,6 +237,11 @@ int mvip_debug_trace(long long* out, int* n_out);
 int mvip_debug_wgrad_profile(unsigned long long* out8);
 /* event stamps (SM clock) of one chain-epilogue warp of the fused backward, -DMVIP_TRACE_BWD builds: out[20][12]; MVIP_E_UNSUPPORTED otherwise */
 int mvip_debug_bwd_trace(long long* out240);
+/* hand-over lag of the dZ units in the last fused backward: out[80 CTA pairs][4] = sum / max of (pick-up - publication) in ns, units
+ * consumed, units already published when asked for; synchronises the device */
+int mvip_debug_bwd_lag(unsigned long long* out320);
+/* tuning aid of the fused backward: SM cycles between the chain starts of consecutive CTA pairs (< 0: default) */
+int mvip_debug_set_bwd_stagger(int cycles);
 
 int mvip_selftest_umma(int which, const float* a, const float* b, int N, int K, float* out, void* stream);
 

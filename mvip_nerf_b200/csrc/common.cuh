@@ -139,8 +139,14 @@ __device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gme
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// pull `bytes` (multiple of 16) at a 16-byte aligned global address into L2; no completion tracking
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // ordering between async-proxy (TMA) and generic-proxy accesses of this thread, all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same restricted to the global state space: does not have to wait for this thread's bulk copies into / out of shared memory
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // inter-CTA flags in global memory (producer/consumer kernels or roles running concurrently on different SMs)
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -163,6 +169,7 @@ __device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.b
 // all but the most recent committed bulk store have finished reading their smem source (double-buffered staging)
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 // all but the 5 most recent committed bulk stores are complete (their global writes performed)
 __device__ __forceinline__ void tma_store_wait_all5() { asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); }
 

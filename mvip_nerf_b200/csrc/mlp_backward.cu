@@ -29,7 +29,8 @@ struct ChainParams {
   uint8_t* dz;
   int64_t n_points;
   int64_t n_tiles;
-  uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ group is in the stash" flags, set by the chain's store warp
+  uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ unit is in the stash" flags, set by the chain's store warp
+  int stagger;          // cycles by which the chain of cluster c starts after that of cluster c - 1 (0: all at once)
 };
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
 
@@ -43,6 +44,14 @@ constexpr int kFusedSlots = 80;                          // partial slots: one p
 // cycle counters of cluster 0 (debug aid, mvip_debug_wgrad_profile): [0] chain issuer total, [1] waiting for the epilogue,
 // [2] waiting for weights, [3] wgrad issuer total, [4] waiting for operands, [5] wgrad producer: flag wait, [6] stage wait, [7] total
 __device__ unsigned long long g_wprof[8];
+// hand-over lag of the dZ units (debug aid, mvip_debug_bwd_lag): per CTA pair [0] sum, [1] max of (consumer picks the unit up) -
+// (chain published it) in ns of %globaltimer, [2] units consumed, [3] units that were already published when the consumer asked
+__device__ unsigned long long g_lag[80][4];
+__device__ __forceinline__ uint32_t globaltimer_lo() {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t));
+  return t;
+}
 #ifdef MVIP_TRACE_BWD
 // event stamps of epilogue warp 0 (lane 0) of cluster 0, leader CTA, for the 4th tile pair: [half-step 0..18][event]
 __device__ long long g_btrace[20][12];
@@ -188,6 +197,8 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
   __shared__ uint64_t bar_wfull[kFStages], bar_wempty[kFStages], bar_wacc;              // wgrad
   __shared__ uint64_t bar_sfull[2], bar_sfree[2];                                        // dZ staging buffers: epilogue -> store warp
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t w_ready_s;                                                         // wgrad: leading tiles of this pair's sequence whose dZ unit is published
+  volatile uint32_t* w_ready = &w_ready_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -199,6 +210,36 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
   const int wj = plan.item[cluster], wk = plan.k[cluster], wn = plan.n[cluster];
   const FItem& fit = kFItems[wj];
   const bool w_active = wk < p.n_tiles;
+  // ===================== wgrad flag watcher (one otherwise idle warp per CTA) =====================
+  // Lane l polls the flag of the (ready + l)-th tile of this pair's sequence: one acquire round trip (~1,500 cycles) covers 32
+  // tiles and stays off the TMA producer's path.  The count of leading published tiles goes to shared memory.
+  auto watch_flags = [&]() {
+    if (!w_active) return;
+    const int n_my = ((int)p.n_tiles - wk + wn - 1) / wn;
+    unsigned long long l_sum = 0, l_max = 0;
+    int ready = 0;
+    while (ready < n_my) {
+      const int idx = ready + lane;
+      uint32_t stamp = 0;
+      if (idx < n_my) stamp = ld_acquire_gpu(p.flags + (size_t)(wk + idx * wn) * kFlagsPerTile + fit.flag);
+      const uint32_t got = __ballot_sync(0xffffffffu, stamp != 0u);
+      const int prefix = (got == 0xffffffffu) ? 32 : __ffs(~got) - 1;
+      if (prefix > 0) {
+        if (lane < prefix) { const uint32_t lag = globaltimer_lo() - (stamp & ~1u); l_sum += lag; l_max = lag > l_max ? lag : l_max; }
+        ready += prefix;
+        __threadfence_block();
+        if (lane == 0) *w_ready = (uint32_t)ready;
+      } else {
+        __nanosleep(100);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      l_sum += __shfl_xor_sync(0xffffffffu, l_sum, o);
+      const unsigned long long m = __shfl_xor_sync(0xffffffffu, l_max, o);
+      l_max = m > l_max ? m : l_max;
+    }
+    if (rank == 0 && lane == 0) { g_lag[cluster][0] = l_sum; g_lag[cluster][1] = l_max; }
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kG; ++i) {
@@ -211,6 +252,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       mbar_init(&bar_wempty[i], 1 + 2);              // multicast tcgen05.commit + the two bias-sum warps
     }
     mbar_init(&bar_wacc, 1);
+    w_ready_s = 0;
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_sfull[i], 8); mbar_init(&bar_sfree[i], 1); }
     mbar_fence_init();
     if (rank == 0) {
@@ -252,6 +294,13 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       }
     };
 
+    // Staggered start: cluster c begins c * stagger cycles late, so that at any time the chains are spread evenly over the
+    // nine steps and every wgrad item sees a steady stream of units in tile order (the order its pairs consume them in),
+    // instead of a whole wave of units of the same layer at once.
+    if (p.stagger > 0) {
+      const long long t0 = clock64(), delay = (long long)cluster * p.stagger;
+      while (clock64() - t0 < delay) __nanosleep(200);
+    }
     for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
       const int64_t tile = 2 * it + (int64_t)rank;
       const bool tile_valid = tile < p.n_tiles;
@@ -438,6 +487,8 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
         }
       }
+    } else if (rank == 0) {
+      watch_flags();
     }
   } else if (warp == 10) {
     // ===================== chain MMA issuer (leader CTA) =====================
@@ -499,25 +550,42 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
         }
       }
       if (cluster == 0 && lane == 0) { g_wprof[0] = clock64() - c_t0; g_wprof[1] = c_act; g_wprof[2] = c_full; }
+    } else {
+      watch_flags();
     }
   } else if (warp == 11) {
     // ===================== wgrad TMA producer (both CTAs): this CTA's 128 dZ features and 128 input features of a 64-point stage =====================
-    if (lane == 0 && w_active) {
-      const int fl = fit.flag;
+    // The whole warp runs converged: lane l < 2 + n_b issues the l-th 8 KB load of a stage, so a stage costs ONE issue slot
+    // instead of four to six (a single thread needs ~150 cycles per bulk-copy instruction; with the flag poll on the same
+    // thread the producer took 3,900 cycles per tile against 1,400 for the MMAs and the pairs fell ever further behind the
+    // chains, every dZ byte coming back from HBM).  The flags are watched by another warp (below): this one polls a counter
+    // in shared memory.
+    if (w_active) {
       const uint64_t pol = l2_policy_evict_first();
-      const uint32_t stage_tx = (uint32_t)(2 + fit.n_b) * kHalf;
+      const int n_loads = 2 + fit.n_b;
+      const uint32_t stage_tx = (uint32_t)n_loads * kHalf;
+      const bool loader = lane < n_loads;
+      const int lj = lane < 2 ? lane : lane - 2;
+      const bool from_stash = loader && (lane < 2 ? fit.a_src : fit.b_src);
+      const int my_chunk = loader ? (lane < 2 ? fit.a_chunk[rank][lj] : fit.b_chunk[rank][lj]) : 0;
+      const int n_my = ((int)p.n_tiles - wk + wn - 1) / wn;
       int stage = 0; uint32_t phase = 0;
       long long p_flag = 0, p_empty = 0, p_t0 = clock64();
-      for (int t = wk; t < p.n_tiles; t += wn) {
-        const uint8_t* dz_tile = wp.dz + (size_t)t * kDzTileBytes;
-        const uint8_t* st_tile = wp.stash + (size_t)t * kStashTileBytes;
-        {  // all 8 epilogue warps of the chain that owns tile t (some SM of this launch) have stored this dZ group
-          const uint32_t* f = p.flags + (size_t)t * kFlagsPerTile + fl;
+      unsigned long long l_ready = 0;
+      // the forward-stash operands of a tile do not depend on the chain: they are pulled into L2 one tile ahead
+      if (from_stash) tma_prefetch_l2(wp.stash + (size_t)wk * kStashTileBytes + (size_t)my_chunk * kActChunk, kActChunk);
+      for (int i = 0; i < n_my; ++i) {
+        const int t = wk + i * wn;
+        const uint8_t* src = (from_stash ? wp.stash + (size_t)t * kStashTileBytes : wp.dz + (size_t)t * kDzTileBytes) + (size_t)my_chunk * kActChunk;
+        if (from_stash && i + 1 < n_my) tma_prefetch_l2(src + (size_t)wn * kStashTileBytes, kActChunk);
+        {  // the chain that owns tile t (some SM of this launch) has published this item's dZ unit
           long long t0 = clock64();
-          while (ld_acquire_gpu(f) == 0u) {
-            if (clock64() - t0 > 8000000000LL) { printf("mvip: fused wgrad flag timeout cluster %d tile %d flag %d\n", cluster, t, fl); __trap(); }
+          if (*w_ready > (uint32_t)i) ++l_ready;
+          while (*w_ready <= (uint32_t)i) {
+            if (clock64() - t0 > 8000000000LL) { if (lane == 0) printf("mvip: fused wgrad flag timeout cluster %d tile %d flag %d\n", cluster, t, fit.flag); __trap(); }
           }
-          fence_proxy_async_all();
+          __threadfence_block();
+          fence_proxy_async_global();
           p_flag += clock64() - t0;
         }
         for (int h = 0; h < 2; ++h) {
@@ -525,17 +593,14 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           long long te = clock64();
           mbar_wait(&bar_wempty[stage], phase ^ 1);
           p_empty += clock64() - te;
-          mbar_arrive_expect_tx(&bar_wfull[stage], stage_tx);
-          const uint8_t* a_tile = fit.a_src ? st_tile : dz_tile;
-          const uint8_t* b_tile = fit.b_src ? st_tile : dz_tile;
-          for (int j = 0; j < 2; ++j)
-            tma_load_1d_hint(sbase + j * kHalf, a_tile + (size_t)fit.a_chunk[rank][j] * kActChunk + h * kHalf, kHalf, &bar_wfull[stage], pol);
-          for (int j = 0; j < fit.n_b; ++j)
-            tma_load_1d_hint(sbase + (2 + j) * kHalf, b_tile + (size_t)fit.b_chunk[rank][j] * kActChunk + h * kHalf, kHalf, &bar_wfull[stage], pol);
+          if (lane == 0) mbar_arrive_expect_tx(&bar_wfull[stage], stage_tx);
+          __syncwarp();
+          if (loader) tma_load_1d_hint(sbase + lane * kHalf, src + h * kHalf, kHalf, &bar_wfull[stage], pol);
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (cluster == 0 && rank == 0) { g_wprof[5] = p_flag; g_wprof[6] = p_empty; g_wprof[7] = clock64() - p_t0; }
+      if (cluster == 0 && rank == 0 && lane == 0) { g_wprof[5] = p_flag; g_wprof[6] = p_empty; g_wprof[7] = clock64() - p_t0; }
+      if (rank == 0 && lane == 0) { g_lag[cluster][2] = n_my; g_lag[cluster][3] = l_ready; }
     }
   } else if (warp == 12) {
     // ===================== wgrad MMA issuer (leader) / relay (peer) =====================
@@ -616,18 +681,26 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     bias_out[2 * t4] = b0;
     bias_out[2 * t4 + 1] = b1;
   } else if (warp == 15) {
-    // ===================== dZ store warp: one 32 KB bulk store per staging buffer; publication of the dZ groups =====================
-    // Three times per tile (after the outputs of chain steps 2, 5 and 8) the thread waits for ALL its bulk stores to be
-    // complete, orders them (async proxy) before its generic-proxy flag stores, issues ONE gpu-scope release fence and sets
-    // the flags of the groups that have gone out since the last time.  Only this thread ever pays for the fence.
+    // ===================== dZ store warp: one 32 KB bulk store per staging buffer; publication of every dZ unit =====================
+    // A unit (the output of one chain step of one tile: flag 0 = d hidden_pre, 1 + s = step s) is published as soon as its
+    // stores are complete: the wgrad pair that consumes it picks it up out of L2 a few microseconds later, long before the
+    // line would be evicted (measured with scripts/ubench/l2_handoff.cu: bulk-stored data is read back from L2 as long as
+    // less than ~70 MB are written between the store and the load; publishing three times per tile, with all chains in
+    // lock step, put a whole wave of tiles = 92 MB in between and every dZ byte was re-read from HBM).
+    // The store of buffer c is given until buffer c + 2 has been issued to complete (cp.async.bulk.wait_group 2), then the
+    // thread orders it (async proxy) before its generic-proxy flag store and releases the flag at gpu scope.
+    // Only this thread ever pays for the fences.
     if (lane == 0) {
       uint32_t n = 0;
+      uint32_t* pend[2] = {nullptr, nullptr};       // flags of the units whose last store is the bulk group n - 1 / n - 2
+      auto publish = [&](uint32_t*& f) {
+        if (f) { fence_proxy_async_global(); st_release_gpu(f, globaltimer_lo() | 1u); f = nullptr; }   // non-zero; the value is a time stamp (debug)
+      };
       for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
         const int64_t tile = 2 * it + (int64_t)rank;
         const bool tile_valid = tile < p.n_tiles;
         uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
         uint32_t* tile_flags = p.flags + (size_t)(tile_valid ? tile : 0) * kFlagsPerTile;
-        int flag_lo = 0;
         for (int c = 0; c < 1 + 2 * kCSteps; ++c, ++n) {
           // c == 0: d hidden_pre; c = 1 + 2 s + h: N-half h of chain step s
           const int s = (c - 1) >> 1, h = (c - 1) & 1;
@@ -638,17 +711,15 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           tma_store_commit();
           tma_store_wait_read0();
           mbar_arrive(&bar_sfree[sb]);
-          if (c == 6 || c == 12 || c == 18) {
-            const int flag_hi = (c == 6) ? 3 : (c == 12 ? 6 : 9);
-            tma_store_wait_all0();
-            fence_proxy_async_all();
-            __threadfence();
-            if (tile_valid)
-              for (int f = flag_lo; f <= flag_hi; ++f) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(tile_flags + f), "r"(1u) : "memory");
-            flag_lo = flag_hi + 1;
-          }
+          tma_store_wait_all2();                    // every store but the last two is complete
+          publish(pend[1]);
+          pend[1] = pend[0];
+          pend[0] = (tile_valid && (c == 0 || h == 1)) ? tile_flags + (c == 0 ? 0 : 1 + s) : nullptr;
         }
       }
+      tma_store_wait_all0();
+      publish(pend[1]);
+      publish(pend[0]);
     }
   }
 
@@ -878,6 +949,12 @@ int mvip_debug_wgrad_profile(unsigned long long* out8) {
   return MVIP_OK;
 }
 
+int mvip_debug_bwd_lag(unsigned long long* out320) {
+  MVIP_CUDA_OK(cudaDeviceSynchronize());
+  MVIP_CUDA_OK(cudaMemcpyFromSymbol(out320, g_lag, sizeof(unsigned long long) * 320));
+  return MVIP_OK;
+}
+
 int mvip_debug_bwd_trace(long long* out240) {
 #ifdef MVIP_TRACE_BWD
   MVIP_CUDA_OK(cudaDeviceSynchronize());
@@ -889,6 +966,10 @@ int mvip_debug_bwd_trace(long long* out240) {
   return MVIP_E_UNSUPPORTED;
 #endif
 }
+
+// cycles between the chain starts of consecutive CTA pairs (tuning aid; < 0 restores the default)
+static int g_stagger = -1;
+int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
 size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_points).total; }
 
@@ -933,6 +1014,9 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   wp.bias_partials = reinterpret_cast<float*>(wsb + ws.bias);
   wp.segs = reinterpret_cast<Segment*>(wsb + ws.segs);
   const int clusters = sms / 2 < kFusedSlots ? sms / 2 : kFusedSlots;
+  // one tile pair takes a chain ~53,000 cycles (profiles/r02_bwd_trace.md): spread the chain starts over one such period;
+  // pointless when there is a single wave of tile pairs
+  cp.stagger = ((n_tiles + 1) / 2 > clusters) ? (g_stagger >= 0 ? g_stagger : 53000 / clusters) : 0;
   MVIP_REQUIRE(clusters >= kFusedItems, MVIP_E_UNSUPPORTED, "mvip_mlp_backward: needs at least %d SM pairs", kFusedItems);
 
   // 1. fused dgrad chain + weight gradients (phase bit 1; bit 2 is kept for ABI compatibility and launches nothing)

@@ -22,6 +22,8 @@ dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g),
 raw, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
 d_raw = torch.randn(P, 4, device=dev, generator=g)
 lib = _lib.load()
+if os.environ.get("STAGGER"):
+    lib.mvip_debug_set_bwd_stagger(int(os.environ["STAGGER"]))
 ws = ops._aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
 flat = torch.zeros(595844, device=dev)
 grads, off = [], 0
@@ -67,4 +69,9 @@ for mask, name in ((1, "backward_fused_kernel"), (4, "head_grads"), (8, "reduce"
         v = list(out)
         print("  cluster 0: chain issuer total %d  wait act/hi %d (%.0f%%)  wait weights %d (%.0f%%)" % (v[0], v[1], 100. * v[1] / max(v[0], 1), v[2], 100. * v[2] / max(v[0], 1)))
         print("             wgrad issuer total %d  wait full %d (%.0f%%)" % (v[3], v[4], 100. * v[4] / max(v[3], 1)))
+        lag = (ctypes.c_ulonglong * 320)()
+        lib.mvip_debug_bwd_lag(lag)
+        L = [list(lag)[4 * i:4 * i + 4] for i in range(80)]
+        print("  dZ hand-over per CTA pair (mean us / max us / %% already published): " + "  ".join(
+            "%d:%.0f/%.0f/%d%%" % (i, l[0] / max(l[2], 1) / 1e3, l[1] / 1e3, 100 * l[3] / max(l[2], 1)) for i, l in enumerate(L) if l[2]))
         print("             wgrad producer total %d  flag wait %d (%.0f%%)  empty wait %d (%.0f%%)" % (v[7], v[5], 100. * v[5] / max(v[7], 1), v[6], 100. * v[6] / max(v[7], 1)))

@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_under_ncu.log 2>&1
-KERNELS='mlp_forward_pair_kernel|dgrad_pair_kernel|wgrad_kernel|composite_fwd4_kernel|composite_bwd4_kernel|head_grads_kernel|reduce_kernel|adam_kernel|sample_fine64_kernel|sample_coarse_warp_kernel|rays_pack_kernel|pack_kernel'
+KERNELS='mlp_forward_pair_kernel|backward_fused_kernel|composite_fwd4_kernel|composite_bwd4_kernel|head_grads_kernel|reduce_kernel|adam_kernel|sample_fine64_kernel|sample_coarse_warp_kernel|rays_pack_kernel|pack_kernel'
 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" \
     -s 40 -c 20 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/prof.log 2>&1
 ncu --set full --clock-control none -k regex:'mlp_forward_pair_kernel|composite_fwd4_kernel|composite_bwd4_kernel|sample_fine64_kernel|sample_coarse_warp_kernel|rays_kernel' \
