@@ -240,6 +240,8 @@ int mvip_debug_bwd_trace(long long* out240);
 /* hand-over lag of the dZ units in the last fused backward: out[80 CTA pairs][4] = sum / max of (pick-up - publication) in ns, units
  * consumed, units already published when asked for; synchronises the device */
 int mvip_debug_bwd_lag(unsigned long long* out320);
+/* byte offsets, inside the backward workspace, of the per-(tile, dZ unit) publication and pick-up time stamps (u32 %globaltimer_lo) */
+int mvip_debug_bwd_stamp_offsets(int64_t n_points, size_t* pub, size_t* pick);
 /* tuning aid of the fused backward: SM cycles between the chain starts of consecutive CTA pairs (< 0: default) */
 int mvip_debug_set_bwd_stagger(int cycles);
 

@@ -30,6 +30,7 @@ struct ChainParams {
   int64_t n_points;
   int64_t n_tiles;
   uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ unit is in the stash" flags, set by the chain's store warp
+  uint32_t* cons_stamp; // [n_tiles][kFlagsPerTile] %globaltimer_lo when the consuming pair started on the unit (debug aid)
   int stagger;          // cycles by which the chain of cluster c starts after that of cluster c - 1 (0: all at once)
 };
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
@@ -572,21 +573,32 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       int stage = 0; uint32_t phase = 0;
       long long p_flag = 0, p_empty = 0, p_t0 = clock64();
       unsigned long long l_ready = 0;
-      // the forward-stash operands of a tile do not depend on the chain: they are pulled into L2 one tile ahead
-      if (from_stash) tma_prefetch_l2(wp.stash + (size_t)wk * kStashTileBytes + (size_t)my_chunk * kActChunk, kActChunk);
+      uint32_t fenced = 0;
+      // the forward-stash operands of a tile do not depend on the chain: they are pulled into L2 two tiles ahead
+      if (from_stash) {
+        tma_prefetch_l2(wp.stash + (size_t)wk * kStashTileBytes + (size_t)my_chunk * kActChunk, kActChunk);
+        if (n_my > 1) tma_prefetch_l2(wp.stash + (size_t)(wk + wn) * kStashTileBytes + (size_t)my_chunk * kActChunk, kActChunk);
+      }
       for (int i = 0; i < n_my; ++i) {
         const int t = wk + i * wn;
         const uint8_t* src = (from_stash ? wp.stash + (size_t)t * kStashTileBytes : wp.dz + (size_t)t * kDzTileBytes) + (size_t)my_chunk * kActChunk;
-        if (from_stash && i + 1 < n_my) tma_prefetch_l2(src + (size_t)wn * kStashTileBytes, kActChunk);
+        if (from_stash && i + 2 < n_my) tma_prefetch_l2(src + (size_t)2 * wn * kStashTileBytes, kActChunk);
         {  // the chain that owns tile t (some SM of this launch) has published this item's dZ unit
           long long t0 = clock64();
-          if (*w_ready > (uint32_t)i) ++l_ready;
-          while (*w_ready <= (uint32_t)i) {
-            if (clock64() - t0 > 8000000000LL) { if (lane == 0) printf("mvip: fused wgrad flag timeout cluster %d tile %d flag %d\n", cluster, t, fit.flag); __trap(); }
+          if ((uint32_t)i >= fenced) {                 // one proxy fence covers every tile the watcher had reported before it
+            uint32_t r = *w_ready;
+            if (r > (uint32_t)i) ++l_ready;
+            while (r <= (uint32_t)i) {
+              if (clock64() - t0 > 8000000000LL) { if (lane == 0) printf("mvip: fused wgrad flag timeout cluster %d tile %d flag %d\n", cluster, t, fit.flag); __trap(); }
+              r = *w_ready;
+            }
+            fence_proxy_async_global();
+            fenced = r;
+          } else {
+            ++l_ready;
           }
-          __threadfence_block();
-          fence_proxy_async_global();
           p_flag += clock64() - t0;
+          if (rank == 0 && lane == 0) p.cons_stamp[(size_t)t * kFlagsPerTile + fit.flag] = globaltimer_lo();
         }
         for (int h = 0; h < 2; ++h) {
           uint8_t* sbase = smem + kFSmemWg + stage * kFStageBytes;
@@ -923,7 +935,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
 
 // workspace carve-up (all offsets 1024-aligned)
 struct Workspace {
-  size_t dz, partials, bias, segs, heads, flags, total;
+  size_t dz, partials, bias, segs, heads, flags, stamps, total;
 };
 Workspace carve(int64_t n_points) {
   Workspace w;
@@ -935,6 +947,7 @@ Workspace carve(int64_t n_points) {
   w.segs = take((size_t)kFusedSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
   w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
+  w.stamps = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
   return w;
 }
@@ -971,6 +984,13 @@ int mvip_debug_bwd_trace(long long* out240) {
 static int g_stagger = -1;
 int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
+// byte offsets of the publication stamps ([n_tiles][10] u32) and the pick-up stamps inside the workspace (debug aid)
+int mvip_debug_bwd_stamp_offsets(int64_t n_points, size_t* pub, size_t* pick) {
+  const Workspace w = carve(n_points);
+  *pub = w.flags; *pick = w.stamps;
+  return MVIP_OK;
+}
+
 size_t mvip_mlp_backward_workspace_bytes(int64_t n_points) { return carve(n_points).total; }
 
 int mvip_mlp_backward(const void* packed, const float* d_raw, int64_t n_points, const void* stash, void* workspace,
@@ -1006,6 +1026,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   cp.n_points = n_points;
   cp.n_tiles = n_tiles;
   cp.flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
+  cp.cons_stamp = reinterpret_cast<uint32_t*>(wsb + ws.stamps);
   WParams wp;
   wp.stash = static_cast<const uint8_t*>(stash);
   wp.dz = wsb + ws.dz;
