@@ -31,6 +31,9 @@ struct ChainParams {
   int64_t n_tiles;
   uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ unit is in the stash" flags, set by the chain's store warp
   uint32_t* cons_stamp; // [n_tiles][kFlagsPerTile] %globaltimer_lo when the consuming pair started on the unit (debug aid)
+  uint32_t* credit;     // [0] 2 x dZ units published, [1] 2 x dZ units picked up (a unit read by two work items counts 1 per item)
+  int throttle_units;   // a chain does not start a tile while more than this many units are published but not picked up ...
+  int throttle_cycles;  // ... for at most this many cycles (a soft limit: it can delay, never block)
   int stagger;          // cycles by which the chain of cluster c starts after that of cluster c - 1 (0: all at once)
 };
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
@@ -138,11 +141,11 @@ constexpr int kFThreads = 512;          // warps 0-7 chain epilogue (0-3 also dr
                                         // 15 dZ bulk stores + publication  (512 threads: 128 registers per thread, no setmaxnreg needed)
 constexpr int kFSlots = 8, kFLag = 2;                                     // chain weight ring: two groups of <= 4 slots in flight (12 slots / 3 groups
                                                                           // at the expense of the third wgrad stage measured slower: 1.27 vs 1.19 ms)
-constexpr int kFStages = 3;
+constexpr int kFStages = 4;
 constexpr uint32_t kFStageBytes = 4 * kHalf;                              // A0 A1 B0 B1: 64 points x 64 features each
 constexpr uint32_t kFSmemW = 0;
 constexpr uint32_t kFSmemStg = kFSmemW + kFSlots * kSlotBytes2;           //  65,536
-constexpr uint32_t kFSmemWg = kFSmemStg + 2 * 2 * kActChunk;              // 131,072
+constexpr uint32_t kFSmemWg = kFSmemStg + 2 * kActChunk;                  //  98,304
 constexpr uint32_t kFSmemBytes = kFSmemWg + kFStages * kFStageBytes;      // 229,376
 // ---- work items of the wgrad role: every one is a cta_group::2 MMA  D[256 x N] += A^T[256 x 64 points] B[64 points x N]
 //      with A = 2 half chunk images per CTA (its 128 M rows) and B = n_b half chunk images per CTA (its N / 2 columns).
@@ -318,8 +321,10 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       // bulk-group wait and no release fence on the epilogue warps (a red.release.gpu here cost 3,000 - 5,000 cycles).
       auto stage_out = [&](const uint32_t (&pk)[32]) {
         const uint32_t sb = so_n & 1u;
-        uint8_t* buf = stg + sb * 2 * kActChunk;
-        mbar_wait(&bar_sfree[sb], ((so_n >> 1) & 1u) ^ 1u);       // the store that used this buffer last has read it
+        uint8_t* buf = stg;
+        // ONE 32 KB staging buffer: the previous half-step's bulk store (issued ~2,900 cycles ago, ~1,300 cycles to read its
+        // source) has finished with it.  The 32 KB a second buffer took are a fourth stage of the wgrad ring.
+        if (so_n > 0) mbar_wait(&bar_sfree[sb ^ 1u], ((so_n - 1) >> 1) & 1u);
         ++so_n;
         BTR(tr_hs, 7);
 #pragma unroll
@@ -598,7 +603,10 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
             ++l_ready;
           }
           p_flag += clock64() - t0;
-          if (rank == 0 && lane == 0) p.cons_stamp[(size_t)t * kFlagsPerTile + fit.flag] = globaltimer_lo();
+          if (rank == 0 && lane == 0) {
+            p.cons_stamp[(size_t)t * kFlagsPerTile + fit.flag] = globaltimer_lo();
+            red_add_relaxed_gpu(p.credit + 1, (fit.flag == 0 || fit.flag == 4) ? 1u : 2u);
+          }
         }
         for (int h = 0; h < 2; ++h) {
           uint8_t* sbase = smem + kFSmemWg + stage * kFStageBytes;
@@ -706,7 +714,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       uint32_t n = 0;
       uint32_t* pend[2] = {nullptr, nullptr};       // flags of the units whose last store is the bulk group n - 1 / n - 2
       auto publish = [&](uint32_t*& f) {
-        if (f) { fence_proxy_async_global(); st_release_gpu(f, globaltimer_lo() | 1u); f = nullptr; }   // non-zero; the value is a time stamp (debug)
+        if (f) { fence_proxy_async_global(); st_release_gpu(f, globaltimer_lo() | 1u); red_add_relaxed_gpu(p.credit, 2u); f = nullptr; }   // non-zero; the value is a time stamp (debug)
       };
       for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
         const int64_t tile = 2 * it + (int64_t)rank;
@@ -718,8 +726,14 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           const int s = (c - 1) >> 1, h = (c - 1) & 1;
           const int chunk = (c == 0) ? kDzHidden : ((s == 0 ? kDzFeat : kDzTrunk + 4 * (s - 1)) + 2 * h);
           const uint32_t sb = n & 1u;
+          if (c == 0 && p.throttle_cycles > 0) {
+            // soft back-pressure: hold the tile back (for a bounded time) while the wgrad pairs are more than ~50 MB behind,
+            // so that they read dZ out of L2 and stay fast enough to keep up
+            const long long t0 = clock64();
+            while ((int)(ld_relaxed_gpu(p.credit) - ld_relaxed_gpu(p.credit + 1)) > 2 * p.throttle_units && clock64() - t0 < p.throttle_cycles) __nanosleep(500);
+          }
           mbar_wait(&bar_sfull[sb], (n >> 1) & 1u);
-          if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk, smem + kFSmemStg + sb * 2 * kActChunk, 2 * kActChunk);
+          if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk, smem + kFSmemStg, 2 * kActChunk);
           tma_store_commit();
           tma_store_wait_read0();
           mbar_arrive(&bar_sfree[sb]);
@@ -946,7 +960,7 @@ Workspace carve(int64_t n_points) {
   w.bias = take((size_t)kFusedSlots * 256 * sizeof(float));
   w.segs = take((size_t)kFusedSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
-  w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
+  w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t) + 64);      // + the two credit counters
   w.stamps = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
   return w;
@@ -982,6 +996,8 @@ int mvip_debug_bwd_trace(long long* out240) {
 
 // cycles between the chain starts of consecutive CTA pairs (tuning aid; < 0 restores the default)
 static int g_stagger = -1;
+static int g_throttle_units = 800, g_throttle_cycles = 30000;
+int mvip_debug_set_bwd_throttle(int units, int cycles) { g_throttle_units = units; g_throttle_cycles = cycles; return MVIP_OK; }
 int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
 // byte offsets of the publication stamps ([n_tiles][10] u32) and the pick-up stamps inside the workspace (debug aid)
@@ -1027,6 +1043,9 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   cp.n_tiles = n_tiles;
   cp.flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
   cp.cons_stamp = reinterpret_cast<uint32_t*>(wsb + ws.stamps);
+  cp.credit = cp.flags + (size_t)n_tiles * kFlagsPerTile;
+  cp.throttle_units = g_throttle_units;
+  cp.throttle_cycles = g_throttle_cycles;
   WParams wp;
   wp.stash = static_cast<const uint8_t*>(stash);
   wp.dz = wsb + ws.dz;
@@ -1072,7 +1091,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
           if (given[i] < n_i[i]) { plan.item[c] = (unsigned char)i; plan.k[c] = (unsigned char)given[i]; plan.n[c] = (unsigned char)n_i[i]; ++given[i]; ++c; }
       plan_clusters = clusters;
     }
-    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t), st));
+    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t) + 64, st));
     MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0xff, (size_t)kFusedSlots * sizeof(Segment), st));      // item = -1: unused slot
     const size_t smem = kFSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);

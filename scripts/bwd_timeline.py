@@ -17,6 +17,8 @@ dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g),
 raw, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
 d_raw = torch.randn(P, 4, device=dev, generator=g)
 lib = _lib.load()
+if os.environ.get("THROTTLE"):
+    lib.mvip_debug_set_bwd_throttle(*[int(x) for x in os.environ["THROTTLE"].split(",")])
 if os.environ.get("STAGGER"):
     lib.mvip_debug_set_bwd_stagger(int(os.environ["STAGGER"]))
 ws = ops._aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
