@@ -40,7 +40,9 @@ constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: out
 
 __device__ __forceinline__ int chain_nchunks(int s) { return s == 0 ? 2 : 4; }
 
-constexpr uint32_t kHalf = kActChunk / 2;                // 64 points of a chunk image
+constexpr int kStagePts = 64;                            // points per stage of the wgrad ring (whole-tile stages, 2 x 64 KB, measured slower: 1.41 vs 1.36 ms)
+constexpr int kSubStages = kTile / kStagePts;            // stages per tile
+constexpr uint32_t kHalf = kStagePts * 128;              // bytes of one operand piece: kStagePts points of a chunk image
 constexpr int kNumItems = 11;
 constexpr size_t kPartialSlotBytes = (size_t)256 * 320 * sizeof(float);
 constexpr int kFusedSlots = 80;                          // partial slots: one per CTA pair (74 on a B200)
@@ -141,8 +143,8 @@ constexpr int kFThreads = 512;          // warps 0-7 chain epilogue (0-3 also dr
                                         // 15 dZ bulk stores + publication  (512 threads: 128 registers per thread, no setmaxnreg needed)
 constexpr int kFSlots = 8, kFLag = 2;                                     // chain weight ring: two groups of <= 4 slots in flight (12 slots / 3 groups
                                                                           // at the expense of the third wgrad stage measured slower: 1.27 vs 1.19 ms)
-constexpr int kFStages = 4;
-constexpr uint32_t kFStageBytes = 4 * kHalf;                              // A0 A1 B0 B1: 64 points x 64 features each
+constexpr int kFStages = (4 * 64) / kStagePts;        // 128 KB of ring
+constexpr uint32_t kFStageBytes = 4 * kHalf;                              // A0 A1 B0 B1: kStagePts points x 64 features each
 constexpr uint32_t kFSmemW = 0;
 constexpr uint32_t kFSmemStg = kFSmemW + kFSlots * kSlotBytes2;           //  65,536
 constexpr uint32_t kFSmemWg = kFSmemStg + 2 * kActChunk;                  //  98,304
@@ -608,7 +610,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
             red_add_relaxed_gpu(p.credit + 1, (fit.flag == 0 || fit.flag == 4) ? 1u : 2u);
           }
         }
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kSubStages; ++h) {
           uint8_t* sbase = smem + kFSmemWg + stage * kFStageBytes;
           long long te = clock64();
           mbar_wait(&bar_wempty[stage], phase ^ 1);
@@ -632,7 +634,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
         bool first = true;
         long long w_t0 = clock64(), w_full = 0;
         for (int t = wk; t < p.n_tiles; t += wn) {
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < kSubStages; ++h) {
             const uint32_t sbase = smem_u32(smem) + kFSmemWg + stage * kFStageBytes;
             const uint32_t a_lo = desc_lo_mn(sbase, kHalf), b_lo = desc_lo_mn(sbase + 2 * kHalf, kHalf);
             long long tw = clock64();
@@ -641,7 +643,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
             tc_fence_after();
             if (elect_one_sync()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
+              for (int ks = 0; ks < kStagePts / 16; ++ks) {
                 const uint32_t ko = (uint32_t)ks * (2048u >> 4);
                 mma2_ss(d0, a_lo + ko, b_lo + ko, idesc, (first && ks == 0) ? 0u : 1u);
               }
@@ -657,7 +659,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
         if (cluster == 0 && lane == 0) { g_wprof[3] = clock64() - w_t0; g_wprof[4] = w_full; }
       } else if (lane == 0) {
         for (int t = wk; t < p.n_tiles; t += wn) {
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < kSubStages; ++h) {
             mbar_wait(&bar_wfull[stage], phase);
             mbar_arrive_cluster(mapa_u32(smem_u32(&bar_wfull[stage]), 0));
             if (++stage == kFStages) { stage = 0; phase ^= 1; }
@@ -676,7 +678,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     const bool do_bias = (fit.bias_ranks >> rank) & 1;
     int stage = 0; uint32_t phase = 0;
     for (int t = wk; t < p.n_tiles; t += wn) {
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < kSubStages; ++h) {
         mbar_wait(&bar_wfull[stage], phase);
         if (do_bias) {
           const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff + bw;
@@ -684,7 +686,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           for (int k = 0; k < 8; ++k) {
             const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kStagePts / 8; ++i) {
               uint32_t pr;
               asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
               b0 += __uint_as_float(pr << 16);
@@ -996,7 +998,7 @@ int mvip_debug_bwd_trace(long long* out240) {
 
 // cycles between the chain starts of consecutive CTA pairs (tuning aid; < 0 restores the default)
 static int g_stagger = -1;
-static int g_throttle_units = 800, g_throttle_cycles = 30000;
+static int g_throttle_units = 500, g_throttle_cycles = 60000;
 int mvip_debug_set_bwd_throttle(int units, int cycles) { g_throttle_units = units; g_throttle_cycles = cycles; return MVIP_OK; }
 int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
