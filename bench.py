@@ -316,7 +316,7 @@ def run_ours(a):
     coarse, fine = kw_train["network_fn"], kw_train["network_fine"]
     groups = [list(fine.parameters()), list(coarse.parameters())]
     inv_world = 1.0 / world
-    sync = md.GradSync(groups)         # per-network allreduce issued from autograd hooks: overlaps the rest of the backward
+    sync = md.GradSync(groups, overlap=a.overlap_allreduce)
 
     def step(rays, tgt):
         optimizer.zero_grad(set_to_none=True)
@@ -357,12 +357,12 @@ def run_ours(a):
         if a.no_graph:
             return None, "eager launches"
         from mvip_nerf_b200.graph import GraphedTrainStep
-        for in_graph, note in ((True, "one CUDA graph per step: render + loss + backward + per-network NCCL allreduce (overlapped) + Adam + bf16 re-pack"),
+        for in_graph, note in ((True, "one CUDA graph per step: render + loss + backward + per-network NCCL allreduce + Adam + bf16 re-pack"),
                                (False, "two CUDA graphs per step: (render + loss + backward) | eager NCCL allreduce | (Adam + bf16 re-pack)")):
             if not in_graph and world == 1:
                 break
             try:
-                g = GraphedTrainStep(kw_train, optimizer, H, W, FOCAL, n_rand, NEAR, FAR, nccl_in_graph=in_graph)
+                g = GraphedTrainStep(kw_train, optimizer, H, W, FOCAL, n_rand, NEAR, FAR, nccl_in_graph=in_graph, overlap_allreduce=a.overlap_allreduce)
                 g.rays.copy_(d_rays)
                 g.target.copy_(d_target)
                 g.capture()
@@ -381,7 +381,7 @@ def run_ours(a):
 
     # ---- device-resident arm ---------------------------------------------------------------------
     if gstep is None:
-        sync = md.GradSync(groups)
+        sync = md.GradSync(groups, overlap=a.overlap_allreduce)
     for _ in range(a.warmup):
         resident_step()
     clocks = ClockSampler(local)
@@ -425,7 +425,7 @@ def run_ours(a):
         gstep.sync.remove()
 
     # ---- the same K steps launched eagerly with a CUDA-event bracket around every library call: per-kernel times --------
-    sync = md.GradSync(groups)
+    sync = md.GradSync(groups, overlap=a.overlap_allreduce)
     for _ in range(3):
         step(d_rays, d_target)
     ops.kernel_timer.enable(True)
@@ -482,8 +482,7 @@ def run_ours(a):
     gtrain_value = world * GH * GW / (ms_gtrain * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_process(world)
         return
 
     # ---- HBM-bound stages at image-sized batches (rank 0, CUDA events per launch, L2 flushed between launches) ---------
@@ -575,8 +574,18 @@ def run_ours(a):
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
+    finish_process(world)
+
+
+def finish_process(world):
+    """End of a rank under torchrun.  destroy_process_group() can block for minutes while captured CUDA graphs still hold NCCL
+    work (seen on 2 B200: the JSON line was out, the launcher only returned when its timeout fired); every result has been
+    printed and flushed at this point, so the rank leaves without running NCCL's teardown."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -591,6 +600,8 @@ def main():
                          "--gpus 8 = cfg 4 (65,536 rays per step; also measured as a secondary entry of every 8-GPU run)")
     ap.add_argument("--sample", type=int, default=1024,
                     help="reference arm: rays per timed step (a bounded sample of the N_rand batch; 1024 = the reference's own N_rand)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="start each network's gradient allreduce from autograd hooks while the backward still runs (default: after it)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     if a.impl == "reference":

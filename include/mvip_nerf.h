@@ -243,8 +243,8 @@ int mvip_debug_bwd_lag(unsigned long long* out320);
 /* byte offsets, inside the backward workspace, of the per-(tile, dZ unit) publication and pick-up time stamps (u32 %globaltimer_lo) */
 int mvip_debug_bwd_stamp_offsets(int64_t n_points, size_t* pub, size_t* pick);
 /* tuning aid of the fused backward: a chain holds a tile back for at most `cycles` while more than `units` dZ units (64 KB) are
- * published but not picked up (cycles = 0: never) */
-int mvip_debug_set_bwd_throttle(int units, int cycles);
+ * published but not picked up (cycles = 0: never); gain > 0: the delay is (excess units) x gain cycles instead */
+int mvip_debug_set_bwd_throttle(int units, int cycles, int gain);
 /* tuning aid of the fused backward: SM cycles between the chain starts of consecutive CTA pairs (< 0: default) */
 int mvip_debug_set_bwd_stagger(int cycles);
 

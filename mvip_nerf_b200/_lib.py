@@ -73,7 +73,7 @@ _SIGNATURES = {
     "mvip_debug_bwd_trace": (c_int, [c_void_p]),
     "mvip_debug_set_bwd_stagger": (c_int, [c_int]),
     "mvip_debug_bwd_lag": (c_int, [c_void_p]),
-    "mvip_debug_set_bwd_throttle": (c_int, [c_int, c_int]),
+    "mvip_debug_set_bwd_throttle": (c_int, [c_int, c_int, c_int]),
     "mvip_debug_bwd_stamp_offsets": (c_int, [c_int64, c_void_p, c_void_p]),
     "mvip_selftest_umma": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }

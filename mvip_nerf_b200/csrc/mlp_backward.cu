@@ -34,6 +34,7 @@ struct ChainParams {
   uint32_t* credit;     // [0] 2 x dZ units published, [1] 2 x dZ units picked up (a unit read by two work items counts 1 per item)
   int throttle_units;   // a chain does not start a tile while more than this many units are published but not picked up ...
   int throttle_cycles;  // ... for at most this many cycles (a soft limit: it can delay, never block)
+  int throttle_gain;    // > 0: the delay is (excess units) x gain cycles, decided once per tile; 0: wait until the excess is gone
   int stagger;          // cycles by which the chain of cluster c starts after that of cluster c - 1 (0: all at once)
 };
 constexpr int kFlagsPerTile = 10;   // 0: d hidden_pre (input stage), 1 + s: output of chain step s
@@ -732,7 +733,14 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
             // soft back-pressure: hold the tile back (for a bounded time) while the wgrad pairs are more than ~50 MB behind,
             // so that they read dZ out of L2 and stay fast enough to keep up
             const long long t0 = clock64();
-            while ((int)(ld_relaxed_gpu(p.credit) - ld_relaxed_gpu(p.credit + 1)) > 2 * p.throttle_units && clock64() - t0 < p.throttle_cycles) __nanosleep(500);
+            if (p.throttle_gain > 0) {        // proportional: one look, a delay that grows with the excess (no stop-and-go waves)
+              const int excess = (int)(ld_relaxed_gpu(p.credit) - ld_relaxed_gpu(p.credit + 1)) / 2 - p.throttle_units;
+              long long delay = (long long)excess * p.throttle_gain;
+              if (delay > p.throttle_cycles) delay = p.throttle_cycles;
+              while (clock64() - t0 < delay) __nanosleep(200);
+            } else {
+              while ((int)(ld_relaxed_gpu(p.credit) - ld_relaxed_gpu(p.credit + 1)) > 2 * p.throttle_units && clock64() - t0 < p.throttle_cycles) __nanosleep(500);
+            }
           }
           mbar_wait(&bar_sfull[sb], (n >> 1) & 1u);
           if (tile_valid) tma_store_1d(dz_tile + (size_t)chunk * kActChunk, smem + kFSmemStg, 2 * kActChunk);
@@ -998,8 +1006,8 @@ int mvip_debug_bwd_trace(long long* out240) {
 
 // cycles between the chain starts of consecutive CTA pairs (tuning aid; < 0 restores the default)
 static int g_stagger = -1;
-static int g_throttle_units = 500, g_throttle_cycles = 60000;
-int mvip_debug_set_bwd_throttle(int units, int cycles) { g_throttle_units = units; g_throttle_cycles = cycles; return MVIP_OK; }
+static int g_throttle_units = 500, g_throttle_cycles = 60000, g_throttle_gain = 20;   // measured: 1.42 ms (best = median) at P = 524,288; waiting for the excess to clear: best 1.34, median 1.43 - 1.6
+int mvip_debug_set_bwd_throttle(int units, int cycles, int gain) { g_throttle_units = units; g_throttle_cycles = cycles; g_throttle_gain = gain; return MVIP_OK; }
 int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
 // byte offsets of the publication stamps ([n_tiles][10] u32) and the pick-up stamps inside the workspace (debug aid)
@@ -1048,6 +1056,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   cp.credit = cp.flags + (size_t)n_tiles * kFlagsPerTile;
   cp.throttle_units = g_throttle_units;
   cp.throttle_cycles = g_throttle_cycles;
+  cp.throttle_gain = g_throttle_gain;
   WParams wp;
   wp.stash = static_cast<const uint8_t*>(stash);
   wp.dz = wsb + ws.dz;

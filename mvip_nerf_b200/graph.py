@@ -42,7 +42,7 @@ def default_loss(rgb, disp, acc, depth, extras, target, scale):
 
 class GraphedTrainStep:
     def __init__(self, render_kwargs_train, optimizer, H, W, focal, n_rays, near=None, far=None, chunk=1024 * 32, loss_fn=default_loss,
-                 target_shape=None, warmup=3, device=None, nccl_in_graph=True):
+                 target_shape=None, warmup=3, device=None, nccl_in_graph=True, overlap_allreduce=False):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a CUDA device (no CPU fallback)")
         self.kw = dict(render_kwargs_train)
@@ -69,7 +69,7 @@ class GraphedTrainStep:
         self.graph_a = self.graph_b = None
         self.loss = None
         self.one_graph = bool(nccl_in_graph) or mdist.world() == 1
-        self.sync = mdist.GradSync(self.groups) if (self.one_graph and mdist.world() > 1) else None
+        self.sync = mdist.GradSync(self.groups, overlap=overlap_allreduce) if (self.one_graph and mdist.world() > 1) else None
 
     # -- the two halves of the step, exactly as the eager loop runs them -----------------------------------------------
     def _forward_backward(self):
