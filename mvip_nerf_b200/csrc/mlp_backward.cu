@@ -171,6 +171,9 @@ struct FItem {
   int cost;              // relative cost (pairs are dealt out in proportion)
 };
 constexpr int kFusedItems = 12;
+#ifndef MVIP_SMALL_COST
+#define MVIP_SMALL_COST 10     // measured: per tile a small item takes a pair about as long as a full one (operand loads, not MMAs, set the pace)
+#endif
 #define MVIP_FULL_ITEM(it, fl, a0, b0) {it, fl, 0, 1, {{a0, a0 + 1}, {a0 + 2, a0 + 3}}, {{b0, b0 + 1}, {b0 + 2, b0 + 3}}, 2, 256, 0, 256, 0, 256, 3, 3, 0, 0, 10}
 __constant__ FItem kFItems[kFusedItems] = {
     MVIP_FULL_ITEM(1, 1, kDzFeat, 29),             // feature_linear   : d feature^T h8
@@ -182,13 +185,13 @@ __constant__ FItem kFItems[kFusedItems] = {
     MVIP_FULL_ITEM(8, 7, kDzTrunk + 20, 5),        // pts_linears.2
     MVIP_FULL_ITEM(9, 8, kDzTrunk + 24, 1),        // pts_linears.1
     // pts_linears.5, PE part (no bias: it comes with the h part)
-    {5, 4, 0, 1, {{kDzTrunk + 8, kDzTrunk + 9}, {kDzTrunk + 10, kDzTrunk + 11}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 0, 0, 0, 7},
+    {5, 4, 0, 1, {{kDzTrunk + 8, kDzTrunk + 9}, {kDzTrunk + 10, kDzTrunk + 11}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 0, 0, 0, MVIP_SMALL_COST},
     // pts_linears.0
-    {10, 9, 0, 1, {{kDzTrunk + 28, kDzTrunk + 29}, {kDzTrunk + 30, kDzTrunk + 31}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 3, 0, 0, 7},
+    {10, 9, 0, 1, {{kDzTrunk + 28, kDzTrunk + 29}, {kDzTrunk + 30, kDzTrunk + 31}}, {{0, 0}, {0, 0}}, 1, 128, 0, 64, 0, 64, 3, 3, 0, 0, MVIP_SMALL_COST},
     // views_linears.0, feature part (transposed)
-    {0, 0, 1, 0, {{33, 34}, {35, 36}}, {{kDzHidden, 0}, {kDzHidden + 1, 0}}, 1, 128, 1, 320, 0, 128, 3, 0, 256, 320, 7},
+    {0, 0, 1, 0, {{33, 34}, {35, 36}}, {{kDzHidden, 0}, {kDzHidden + 1, 0}}, 1, 128, 1, 320, 0, 128, 3, 0, 256, 320, MVIP_SMALL_COST},
     // views_linears.0, PE(viewdir) part + bias
-    {0, 0, 0, 1, {{kDzHidden, kDzHidden + 1}, {kDzHidden, kDzHidden + 1}}, {{37, 0}, {37, 0}}, 1, 128, 0, 320, 256, 64, 1, 1, 0, 256, 7},
+    {0, 0, 0, 1, {{kDzHidden, kDzHidden + 1}, {kDzHidden, kDzHidden + 1}}, {{37, 0}, {37, 0}}, 1, 128, 0, 320, 256, 64, 1, 1, 0, 256, MVIP_SMALL_COST},
 };
 struct FusedPlan {          // host-computed: which item each CTA pair works on, as the k-th of n pairs on that item
   unsigned char item[kFusedSlots], k[kFusedSlots], n[kFusedSlots];
