@@ -79,4 +79,24 @@ with open(os.path.join(P, tag + "_kernels_ncu.md"), "w") as f:
     f.write("| kernel | duration us | dram read GB | dram write GB | dram % peak | tensor pipe active % | L2 % | smem wavefronts % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
     for v in seen.values():
         f.write("| `%s` | %.1f | %.3f | %.3f | %.1f | %.1f | %.1f | %.1f | %d |\n" % v)
-print("wrote profiles/%s_*" % tag)
+# ---- DRAM traffic per launch of the MLP kernels inside one cfg-2 step: what bench.py reports as roofline.traffic ----
+import json
+traffic = {}
+for r in rows:
+    name = short(r[2][r[0]["Kernel Name"]]).split("(")[0].split("<")[0]
+    if name not in ("mlp_forward_pair_kernel", "backward_fused_kernel", "head_grads_kernel"):
+        continue
+    b = (g(r, "dram__bytes_read.sum") + g(r, "dram__bytes_write.sum")) * 1e9
+    if b != b or g(r, "gpu__time_duration.sum") > 3000:      # the render-sized launches of scripts/prof_hbm_stages.py are not part of a step
+        continue
+    traffic.setdefault(name, []).append(b)
+out = {"source": "profiles/%s_ncu_full_raw.csv (ncu --set full, one cfg-2 step: coarse 262,144 + fine 524,288 points; mean of the two launches)" % tag,
+       "rays_per_gpu": 4096, "kernels": {}}
+for k, v in traffic.items():
+    v = v[:2]
+    out["kernels"][k] = {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v)}
+    label = {"mlp_forward_pair_kernel": "mvip_mlp_forward"}.get(k)
+    if label:
+        out["kernels"][label] = out["kernels"][k]
+json.dump(out, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+print("wrote profiles/%s_* and profiles/ncu_traffic.json" % tag)
