@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_train_parity.py -q -x -p no:cacheprovider 2>&1 | tail -3
-for v in "" variants/mc11/libmvip_nerf.so variants/mc15/libmvip_nerf.so; do echo "=== $v"; for i in 1 2; do MVIP_LIB=$v python scripts/prof_fused.py 524288 2>&1 | grep "backward_fused"; done; MVIP_LIB=$v python scripts/prof_fused.py 262144 2>&1 | grep "backward_fused"; MVIP_LIB=$v python scripts/bwd_timeline.py 524288 2>&1 | grep "span\|mean"; done
+mkdir -p gpurun_out
+timeout 600 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:'pair_kernel<\(bool\)1' -s 1 -c 1 -o gpurun_out/fwd_src python scripts/prof_fwd.py > gpurun_out/fwd_src.log 2>&1
+ls -la gpurun_out/fwd_src.ncu-rep; tail -3 gpurun_out/fwd_src.log

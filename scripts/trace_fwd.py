@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from mvip_nerf_b200 import ops, _lib
 from oracle import nerf_oracle as orc
+if os.environ.get("MVIP_LIB"):
+    _lib.LIB_PATH = os.path.abspath(os.environ["MVIP_LIB"])
 dev = "cuda"
 p = orc.init_params(1)
 blob = ops.mlp_pack([torch.from_numpy(p[n]).to(dev) for n in ops.PARAM_ORDER])
