@@ -297,28 +297,19 @@ __device__ __forceinline__ void ts_epilogue(const Params& p, uint8_t* smem, uint
     // behind two 256-thread barriers and a wait on the previous 36 KB store - cost ~1,700 cycles per accumulator half).
     // mask_layer >= 0: this warp's 512 B of ReLU mask words of that layer ([row][h][2 words]) go out with it.
     auto stage_out = [&](int chunk, const uint32_t (&pk)[32], int h, const uint32_t (&mw)[2], bool with_mask, int mask_layer) {
-#ifdef MVIP_EXP_NOSTAGE
-      return;
-#endif
       if (lane == 0) tma_store_wait_read0();    // this warp's previous bulk stores have finished reading its staging pieces
       __syncwarp();
-#ifndef MVIP_EXP_NOSTS
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq)
         *reinterpret_cast<uint4*>(stg + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
       if (with_mask) *reinterpret_cast<uint2*>(mstg + lane * 16 + h * 8) = make_uint2(mw[0], mw[1]);
-#endif
-#ifndef MVIP_EXP_NOFENCE
       fence_proxy_async_smem();
-#endif
       __syncwarp();
-#ifndef MVIP_EXP_NOSTORE
       if (lane == 0 && tile_valid) {
         tma_store_1d(stash_tile + (size_t)chunk * kActChunk + q * 4096, stg, 4096);
         if (mask_layer >= 0) tma_store_1d(stash_tile + kStashMaskOff + (size_t)mask_layer * 4096 + ch * 2048 + q * 512, mstg, 512);
         tma_store_commit();
       }
-#endif
     };
 
     float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;

@@ -274,6 +274,17 @@ class GradAllReducer:
         self.flat = view if self.in_place else torch.cat([g.reshape(-1) for g in grads])
         self.handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
 
+    def start_if_contiguous(self):
+        """Starts the collective only if it can run in place on one contiguous buffer; -> whether it did."""
+        if world() == 1 or any(p.grad is None for p in self.params):
+            return False
+        view = _flat_view([p.grad for p in self.params])
+        if view is None:
+            return False
+        self.in_place, self.flat = True, view
+        self.handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
+        return True
+
     def finish(self):
         if self.handle is None:
             return
@@ -308,6 +319,7 @@ class GradSync:
         self.overlap = bool(overlap)
         self.groups = [list(ps) for ps in param_groups]
         self.reducers = [GradAllReducer(ps) for ps in self.groups]
+        self._all = GradAllReducer([p for ps in self.groups for p in ps])
         self.count = [0] * len(self.groups)
         self.started = [False] * len(self.groups)
         self.hooks = []
@@ -325,11 +337,14 @@ class GradSync:
 
     def finish(self):
         if world() > 1:
-            for gi, r in enumerate(self.reducers):
-                if not self.started[gi]:
-                    r.start()
-            for r in self.reducers:
-                r.finish()
+            if not any(self.started) and self._all.start_if_contiguous():
+                self._all.finish()          # the gradients of all networks are one contiguous range: ONE collective
+            else:
+                for gi, r in enumerate(self.reducers):
+                    if not self.started[gi]:
+                        r.start()
+                for r in self.reducers:
+                    r.finish()
         self.count = [0] * len(self.groups)
         self.started = [False] * len(self.groups)
 

@@ -70,10 +70,20 @@ class GraphedTrainStep:
         self.loss = None
         self.one_graph = bool(nccl_in_graph) or mdist.world() == 1
         self.sync = mdist.GradSync(self.groups, overlap=overlap_allreduce) if (self.one_graph and mdist.world() > 1) else None
+        n_grad = sum(p.numel() for ps in self.groups for p in ps)
+        self.grad_arena = torch.empty(n_grad, device=self.dev, dtype=torch.float32) if mdist.world() > 1 else None
 
     # -- the two halves of the step, exactly as the eager loop runs them -----------------------------------------------
     def _forward_backward(self):
         self.opt.zero_grad(set_to_none=True)
+        if self.grad_arena is not None:       # both networks' gradients back to back: one allreduce (dist.GradSync.finish)
+            ops.grad_arena.begin(self.grad_arena)
+        try:
+            return self._forward_backward_body()
+        finally:
+            ops.grad_arena.end()
+
+    def _forward_backward_body(self):
         H, W, focal = self.args
         mse = {"_mse": (self.target, None)} if self.fused_loss else {}
         rgb, disp, acc, depth, extras = run.render(H, W, focal, chunk=self.chunk, rays=self.rays, near=self.near, far=self.far,

@@ -368,6 +368,33 @@ def mlp_forward(packed, rays=None, z_vals=None, viewdir_offset=8, pts=None, dirs
     return (raw, stash) if want_stash else raw
 
 
+class _GradArena:
+    """Optional caller-owned buffer the flat gradient buffers of successive mlp_backward calls are carved from, back to back
+    (fine network first, then coarse: autograd's order), so that the gradients of BOTH networks are one contiguous fp32 range
+    and the data-parallel step needs ONE allreduce (dist.GradSync).  graph.GraphedTrainStep installs one per step."""
+
+    def __init__(self):
+        self.buf, self.off = None, 0
+
+    def begin(self, buf):
+        self.buf, self.off = buf, 0
+
+    def end(self):
+        self.buf, self.off = None, 0
+
+    def take(self, n, dev, zero):
+        if self.buf is None or self.buf.device != dev or self.off + n > self.buf.numel():
+            return (torch.zeros if zero else torch.empty)((n,), device=dev, dtype=torch.float32)
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        if zero:
+            out.zero_()
+        return out
+
+
+grad_arena = _GradArena()
+
+
 def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
     """-> list of 24 fp32 gradient tensors in PARAM_ORDER"""
     lib = _lib.load()
@@ -378,7 +405,7 @@ def mlp_backward(packed, d_raw, stash, grads=None, accumulate=False):
         # one flat buffer, 24 views
         sizes = [int(torch.Size(shp).numel()) for shp in PARAM_SHAPES]
         # the reduce kernel overwrites every element — except for an empty batch, which launches nothing
-        flat = (torch.zeros if P == 0 else torch.empty)((sum(sizes),), device=dev, dtype=torch.float32)
+        flat = grad_arena.take(sum(sizes), dev, zero=(P == 0))
         grads, off = [], 0
         for shp, n in zip(PARAM_SHAPES, sizes):
             grads.append(flat[off:off + n].view(shp))

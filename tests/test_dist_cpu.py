@@ -181,6 +181,66 @@ def test_world2_gloo_gradsync_overlapped_buckets():
     mp.spawn(_gradsync_worker, args=(2, _free_port()), nprocs=2, join=True)
 
 
+def _gradsync_single_bucket_worker(rank, world, port):
+    """overlap=False + the gradients of both networks back to back in one buffer (what graph.GraphedTrainStep arranges through
+    ops.grad_arena): finish() must issue ONE in-place collective over the whole range; a gap in the layout falls back to
+    one bucket per network."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from mvip_nerf_b200 import dist as md
+    md.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    fine, coarse = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    groups = [list(fine.parameters()), list(coarse.parameters())]
+    params = groups[0] + groups[1]
+    sync = md.GradSync(groups, overlap=False)
+    calls = []
+    real = dist.all_reduce
+
+    def counting(t, *a, **k):
+        calls.append(t.numel())
+        return real(t, *a, **k)
+    md.dist.all_reduce = counting
+    n = sum(p.numel() for p in params)
+    for gap in (0, 3):
+        arena = torch.zeros(n + gap)
+        off = 0
+        for i, p in enumerate(params):
+            if i == len(groups[0]):
+                off += gap                      # gap > 0: the two networks are not adjacent
+            p.grad = arena[off:off + p.numel()].view_as(p)
+            p.grad.fill_(float(rank + 1) * (i + 1))
+            off += p.numel()
+        del calls[:]
+        sync.finish()
+        assert not any(sync.started)
+        assert calls == ([n] if gap == 0 else [sum(p.numel() for p in groups[0]), sum(p.numel() for p in groups[1])]), calls
+        for i, p in enumerate(params):
+            assert float((p.grad - 3.0 * (i + 1)).abs().max()) == 0.0          # 1 + 2 = sum over the two ranks
+            assert p.grad.untyped_storage().data_ptr() == arena.untyped_storage().data_ptr()      # in place
+    md.dist.all_reduce = real
+    sync.remove()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_gradsync_single_bucket():
+    mp.spawn(_gradsync_single_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_grad_arena_carves_consecutive_buffers():
+    from mvip_nerf_b200 import ops
+    buf = torch.zeros(10)
+    ops.grad_arena.begin(buf)
+    a = ops.grad_arena.take(4, buf.device, zero=False)
+    b = ops.grad_arena.take(6, buf.device, zero=True)
+    c = ops.grad_arena.take(1, buf.device, zero=True)          # exhausted: falls back to a fresh tensor
+    ops.grad_arena.end()
+    assert a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf.data_ptr() + 16
+    assert c.untyped_storage().data_ptr() != buf.untyped_storage().data_ptr()
+    d = ops.grad_arena.take(3, buf.device, zero=False)         # no arena installed
+    assert d.untyped_storage().data_ptr() != buf.untyped_storage().data_ptr()
+
+
 def test_world2_gloo_sharded_guidance_views_with_gradients():
     mp.spawn(_guidance_worker, args=(2, _free_port()), nprocs=2, join=True)
 
