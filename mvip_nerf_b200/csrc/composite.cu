@@ -426,17 +426,39 @@ composite_bwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ 
     }
     float excl = __shfl_down_sync(FULL_MASK, incl, 1, G);
     if (sub == G - 1) excl = 0.f;
-    if (live_ray) {
+    // d_raw of this lane's 4 consecutive samples ...
+    float4 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float dalpha = Gk[k] * f.T[k] - (Gw[k] + excl) * rcp_ftz(f.q[k]) + gav[k];
+      o[k].x = f.w[k] * gR * f.cr[k] * (1.f - f.cr[k]);
+      o[k].y = f.w[k] * gG * f.cg[k] * (1.f - f.cg[k]);
+      o[k].z = f.w[k] * gB * f.cb[k] * (1.f - f.cb[k]);
+      o[k].w = (f.sig[k] > 0.f) ? dalpha * f.delta[k] * f.e[k] : 0.f;
+    }
+    // ... transposed inside each quad of lanes (lane 4m + j ends up with samples 16m + 4k + j, k = 0..3), so that every store
+    // instruction writes 64 contiguous bytes per quad = full 32-byte sectors (16 bytes per lane at a 64-byte stride wrote half
+    // sectors: twice the L2 write transactions)
+    const int j = lane & 3;
+#pragma unroll
+    for (int d = 1; d <= 2; d <<= 1) {        // exchange with lane ^ d the elements whose index differs from ours in bit d
+      const bool up = (j & d) != 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float dalpha = Gk[k] * f.T[k] - (Gw[k] + excl) * rcp_ftz(f.q[k]) + gav[k];
-        float4 o;
-        o.x = f.w[k] * gR * f.cr[k] * (1.f - f.cr[k]);
-        o.y = f.w[k] * gG * f.cg[k] * (1.f - f.cg[k]);
-        o.z = f.w[k] * gB * f.cb[k] * (1.f - f.cb[k]);
-        o.w = (f.sig[k] > 0.f) ? dalpha * f.delta[k] * f.e[k] : 0.f;
-        d_raw[off + k] = o;
+        if (k & d) continue;                  // pairs (k, k | d)
+        const float4 mine = up ? o[k] : o[k | d];
+        float4 got;
+        got.x = __shfl_xor_sync(FULL_MASK, mine.x, d);
+        got.y = __shfl_xor_sync(FULL_MASK, mine.y, d);
+        got.z = __shfl_xor_sync(FULL_MASK, mine.z, d);
+        got.w = __shfl_xor_sync(FULL_MASK, mine.w, d);
+        if (up) o[k] = got; else o[k | d] = got;
       }
+    }
+    if (live_ray) {
+      const int64_t qoff = ray * S + (sub & ~3) * 4 + j;      // first sample of the quad + our column
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d_raw[qoff + 4 * k] = o[k];
     }
   }
 }
