@@ -71,43 +71,62 @@ sample_coarse_warp_kernel(const float* __restrict__ rays, int ray_stride, int64_
     omt[k] = __fsub_rn(1.0f, t[k]);
   }
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp0; r < n_rays; r += nwarps) {
-    float nf = __ldg(rays + r * ray_stride + 6 + (lane & 1));     // even lanes: near, odd lanes: far
-    if (lindisp) nf = __frcp_rn(nf);
-    const float a = __shfl_sync(FULL_MASK, nf, 0), b = __shfl_sync(FULL_MASK, nf, 1);
-    float z[C];
+  // kU rays per trip: all their loads (near / far, the C draws) are issued before the first use, so a warp keeps kU x (8 + 4 S)
+  // bytes in flight instead of one ray's (the stage is latency-bound: ~1.5 instructions per sample)
+  constexpr int kU = 4;
+  for (int64_t r0 = warp0; r0 < n_rays; r0 += kU * nwarps) {
+    float nf[kU], tr[kU][C];
 #pragma unroll
-    for (int k = 0; k < C; ++k) {
-      z[k] = __fadd_rn(__fmul_rn(a, omt[k]), __fmul_rn(b, t[k]));
-      if (lindisp) z[k] = __frcp_rn(z[k]);
-    }
-    if (t_rand != nullptr) {
-      const float prev = __shfl_up_sync(FULL_MASK, z[C - 1], 1), next = __shfl_down_sync(FULL_MASK, z[0], 1);
-      float tr[C];
-      if constexpr (C == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(t_rand + r * S) + lane);
-        tr[0] = v.x; tr[1] = v.y; tr[2] = v.z; tr[3] = v.w;
-      } else if constexpr (C == 2) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(t_rand + r * S) + lane);
-        tr[0] = v.x; tr[1] = v.y;
+    for (int u = 0; u < kU; ++u) {
+      const int64_t r = r0 + u * nwarps;
+      const bool live = r < n_rays;
+      nf[u] = live ? __ldg(rays + r * ray_stride + 6 + (lane & 1)) : 1.f;     // even lanes: near, odd lanes: far
+      if (t_rand != nullptr && live) {
+        if constexpr (C == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(t_rand + r * S) + lane);
+          tr[u][0] = v.x; tr[u][1] = v.y; tr[u][2] = v.z; tr[u][3] = v.w;
+        } else if constexpr (C == 2) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(t_rand + r * S) + lane);
+          tr[u][0] = v.x; tr[u][1] = v.y;
+        } else {
+          tr[u][0] = __ldg(t_rand + r * S + lane);
+        }
       } else {
-        tr[0] = __ldg(t_rand + r * S + lane);
+#pragma unroll
+        for (int k = 0; k < C; ++k) tr[u][k] = 0.f;
       }
-      float out[C];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t r = r0 + u * nwarps;
+      if (r >= n_rays) break;                                      // warp-uniform
+      float nfu = nf[u];
+      if (lindisp) nfu = __frcp_rn(nfu);
+      const float a = __shfl_sync(FULL_MASK, nfu, 0), b = __shfl_sync(FULL_MASK, nfu, 1);
+      float z[C];
 #pragma unroll
       for (int k = 0; k < C; ++k) {
-        const float zp = (k > 0) ? z[(k > 0) ? k - 1 : 0] : prev, zn = (k + 1 < C) ? z[(k + 1 < C) ? k + 1 : k] : next;
-        float lower = __fmul_rn(0.5f, __fadd_rn(z[k], zp)), upper = __fmul_rn(0.5f, __fadd_rn(zn, z[k]));
-        if (k == 0 && lane == 0) lower = z[k];
-        if (k == C - 1 && lane == 31) upper = z[k];
-        out[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[k]));
+        z[k] = __fadd_rn(__fmul_rn(a, omt[k]), __fmul_rn(b, t[k]));
+        if (lindisp) z[k] = __frcp_rn(z[k]);
       }
+      if (t_rand != nullptr) {
+        const float prev = __shfl_up_sync(FULL_MASK, z[C - 1], 1), next = __shfl_down_sync(FULL_MASK, z[0], 1);
+        float out[C];
 #pragma unroll
-      for (int k = 0; k < C; ++k) z[k] = out[k];
+        for (int k = 0; k < C; ++k) {
+          const float zp = (k > 0) ? z[(k > 0) ? k - 1 : 0] : prev, zn = (k + 1 < C) ? z[(k + 1 < C) ? k + 1 : k] : next;
+          float lower = __fmul_rn(0.5f, __fadd_rn(z[k], zp)), upper = __fmul_rn(0.5f, __fadd_rn(zn, z[k]));
+          if (k == 0 && lane == 0) lower = z[k];
+          if (k == C - 1 && lane == 31) upper = z[k];
+          out[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[u][k]));
+        }
+#pragma unroll
+        for (int k = 0; k < C; ++k) z[k] = out[k];
+      }
+      if constexpr (C == 4) reinterpret_cast<float4*>(z_out + r * S)[lane] = make_float4(z[0], z[1], z[2], z[3]);
+      else if constexpr (C == 2) reinterpret_cast<float2*>(z_out + r * S)[lane] = make_float2(z[0], z[1]);
+      else z_out[r * S + lane] = z[0];
     }
-    if constexpr (C == 4) reinterpret_cast<float4*>(z_out + r * S)[lane] = make_float4(z[0], z[1], z[2], z[3]);
-    else if constexpr (C == 2) reinterpret_cast<float2*>(z_out + r * S)[lane] = make_float2(z[0], z[1]);
-    else z_out[r * S + lane] = z[0];
   }
 }
 
