@@ -357,7 +357,7 @@ def run_ours(a):
         if a.no_graph:
             return None, "eager launches"
         from mvip_nerf_b200.graph import GraphedTrainStep
-        for in_graph, note in ((True, "one CUDA graph per step: render + loss + backward + per-network NCCL allreduce + Adam + bf16 re-pack"),
+        for in_graph, note in ((True, "one CUDA graph per step: render + loss + backward + ONE NCCL allreduce of both networks' gradients + Adam + bf16 re-pack"),
                                (False, "two CUDA graphs per step: (render + loss + backward) | eager NCCL allreduce | (Adam + bf16 re-pack)")):
             if not in_graph and world == 1:
                 break
