@@ -314,3 +314,45 @@ def test_fused_backward_is_deterministic_and_never_reads_stale_dz():
         outs.append(flat.clone())
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.gpu
+def test_fused_backward_does_not_depend_on_its_scheduling_knobs():
+    """Stagger of the chain starts and the credit throttle only change WHEN things happen inside backward_fused_kernel: every
+    wgrad pair still consumes its tiles in the same fixed order, so the gradients must be bit-identical for any setting
+    (no stagger / no throttle, the defaults, an absurdly tight throttle that stalls every tile, a huge stagger)."""
+    import ctypes
+    from mvip_nerf_b200 import _lib, ops
+    dev = "cuda"
+    p = orc.init_params(9)
+    blob = ops.mlp_pack([torch.from_numpy(p[n]).to(dev) for n in ops.PARAM_ORDER])
+    g = torch.Generator(device=dev).manual_seed(13)
+    P = 128 * 148 * 3 + 17
+    pts = torch.rand(P, 3, device=dev, generator=g) * 4 - 2
+    dirs = torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g), dim=-1)
+    raw, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
+    d = torch.randn(P, 4, device=dev, generator=g)
+    lib = _lib.load()
+    ws = ops._aligned_bytes(lib.mvip_mlp_backward_workspace_bytes(P), dev)
+    outs = []
+    try:
+        for stagger, throttle in ((0, (500, 0, 0)), (-1, (500, 60000, 20)), (-1, (1, 20000, 0)), (5000, (50, 60000, 200))):
+            lib.mvip_debug_set_bwd_stagger(stagger)
+            lib.mvip_debug_set_bwd_throttle(*throttle)
+            ws.fill_(0xFF)
+            flat = torch.full((595844,), float("nan"), device=dev)
+            grads, off = [], 0
+            for shp in ops.PARAM_SHAPES:
+                n = int(torch.Size(shp).numel())
+                grads.append(flat[off:off + n].view(shp)); off += n
+            arr = (ctypes.c_void_p * 24)(*[x.data_ptr() for x in grads])
+            rc = lib.mvip_mlp_backward(ops._ptr(blob), ops._ptr(d), P, ops._ptr(stash), ops._ptr(ws), arr, 0, ops._stream())
+            _lib.check(rc, "mvip_mlp_backward")
+            torch.cuda.synchronize()
+            outs.append(flat.clone())
+    finally:
+        lib.mvip_debug_set_bwd_stagger(-1)
+        lib.mvip_debug_set_bwd_throttle(500, 60000, 20)
+    assert torch.isfinite(outs[0]).all()
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
