@@ -193,6 +193,13 @@ __device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.b
 // all but the 5 most recent committed bulk stores are complete (their global writes performed)
 __device__ __forceinline__ void tma_store_wait_all5() { asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); }
 
+// 16-byte store to a 32-bit shared-window address (no generic-address arithmetic in the hot loops)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -287,7 +287,8 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     const uint32_t tD = tA + 128 + ch * 64;
     const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
     // staging: two 32 KB buffers (the two chunk images of one accumulator half); this warp writes rows [32 q, 32 q + 32) of image ch
-    uint8_t* stg = smem + kFSmemStg + ch * kActChunk + q * 4096;
+    const uint32_t stg_row = smem_u32(smem + kFSmemStg + ch * kActChunk + q * 4096) + (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u;
+    const uint32_t stg_x7 = (uint32_t)(lane & 7) << 4;
     uint32_t acc_phase = 0, so_n = 0;
     auto act_arrive = [&]() {
       __syncwarp();
@@ -327,15 +328,14 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       // bulk-group wait and no release fence on the epilogue warps (a red.release.gpu here cost 3,000 - 5,000 cycles).
       auto stage_out = [&](const uint32_t (&pk)[32]) {
         const uint32_t sb = so_n & 1u;
-        uint8_t* buf = stg;
         // ONE 32 KB staging buffer: the previous half-step's bulk store (issued ~2,900 cycles ago, ~1,300 cycles to read its
         // source) has finished with it.  The 32 KB a second buffer took are a fourth stage of the wgrad ring.
         if (so_n > 0) mbar_wait(&bar_sfree[sb ^ 1u], ((so_n - 1) >> 1) & 1u);
         ++so_n;
         BTR(tr_hs, 7);
 #pragma unroll
-        for (int gq = 0; gq < 8; ++gq)
-          *reinterpret_cast<uint4*>(buf + chunk_off16(lane, gq)) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+        for (int gq = 0; gq < 8; ++gq)     // chunk_off16(lane, gq) = row offset | ((gq ^ (lane & 7)) << 4)
+          sts128(stg_row | (((uint32_t)gq << 4) ^ stg_x7), pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
         BTR(tr_hs, 8);
         fence_proxy_async_smem();
         __syncwarp();
