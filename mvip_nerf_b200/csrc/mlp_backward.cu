@@ -125,19 +125,24 @@ struct WParams {
 //     the chain leaves the tensor pipe idle while its epilogue warps work (it is bound by their latency, not by HBM).
 //     Here every CTA pair runs
 //       * the chain on ONE tile slot per CTA (TMEM columns [0, 256): A operand + one accumulator half), tile pairs taken
-//         round-robin over the clusters.  The epilogue warps write packed bf16 rows into two 32 KB staging buffers; a
-//         dedicated store warp sends each buffer to the dZ stash as one bulk store and, three times per tile, waits for
-//         its stores to be complete, issues ONE gpu-scope release fence and sets the flags of the groups that went out
-//         (a red.release.gpu per group on the epilogue warps cost them 3,000 - 5,000 cycles each time);
+//         round-robin over the clusters, the chain of cluster c starting c x stagger cycles late.  The epilogue warps write
+//         packed bf16 rows into ONE 32 KB staging buffer; a dedicated store thread sends it to the dZ stash as one bulk
+//         store and publishes each of the 10 dZ UNITS of a tile (the output of one chain step) as soon as its stores are
+//         complete (st.release.gpu of a flag; only that thread pays for the fences: a red.release.gpu per group on the
+//         epilogue warps cost them 3,000 - 5,000 cycles each time);
 //       * a cta_group::2 wgrad (M = 256: 128 rows per CTA, N <= 256: B split over the CTAs, K = points) whose fp32
 //         accumulator lives in TMEM columns [256, 512) of both CTAs for the whole launch; the pair is bound to ONE work
-//         item (kFItems) and consumes its operands of every n-th tile as soon as the chain that produced the dZ group - on
-//         any SM - has published it: ld.acquire.gpu + fence.proxy.async, then TMA loads that hit L2.
-//     The chains work on a window of 148 consecutive tiles (90 MB of dZ) and every consumer follows the window, so HBM
-//     sees the forward stash once (read) and the dZ write-back; the wgrad MMAs fill the tensor pipe while the chain's
-//     epilogue runs (cluster 0: pipe busy ~82 % of the time).  The chain never waits for wgrad (dZ has its full-size
-//     buffer), wgrad only waits for flags, all CTAs are resident (grid <= #SMs): no deadlock.
-//     Shared memory per CTA: chain weight ring 8 x 8 KB, dZ staging 2 x 32 KB, wgrad ring 3 x 32 KB.
+//         item (kFItems) and consumes its operands of every n-th tile, in tile order (bitwise reproducible sums).  A
+//         watcher warp polls the flags of the pair's next 32 tiles (one ld.acquire.gpu round trip) and keeps the count of
+//         published tiles in shared memory; the converged TMA warp (lane l issues the l-th 8 KB load of a 64-point
+//         stage; 4 stages) issues one fence.proxy.async.global per batch of published tiles, prefetches the stash
+//         operands into L2 two tiles ahead and loads the dZ unit ~30 us after its publication: out of L2.
+//       * a soft credit throttle keeps the pairs that close: a chain delays the start of a tile by
+//         (units published - units picked up - throttle_units) x throttle_gain cycles (bounded: it can delay, never block).
+//     HBM sees the forward stash once (read), the dZ write-back, and the ~30 % of dZ reads that still miss L2
+//     (profiles/r02_backward_handover.md).  The chain never waits for wgrad (dZ has its full-size buffer), wgrad only
+//     waits for flags, all CTAs are resident (grid <= #SMs): no deadlock.
+//     Shared memory per CTA: chain weight ring 8 x 8 KB, dZ staging 32 KB, wgrad ring 4 x 32 KB.
 // =================================================================================================
 constexpr int kFThreads = 512;          // warps 0-7 chain epilogue (0-3 also drain the wgrad accumulator at the end), 8 chain TMA,
                                         // 9 TMEM alloc / chain relay, 10 chain MMA, 11 wgrad TMA, 12 wgrad MMA / relay, 13-14 bias sums,
@@ -286,7 +291,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     const uint32_t tA = tmem_base + lane_base;
     const uint32_t tD = tA + 128 + ch * 64;
     const float* small = reinterpret_cast<const float*>(p.packed + kSmallOff);
-    // staging: two 32 KB buffers (the two chunk images of one accumulator half); this warp writes rows [32 q, 32 q + 32) of image ch
+    // staging: one 32 KB buffer (the two chunk images of one accumulator half); this warp writes rows [32 q, 32 q + 32) of image ch
     const uint32_t stg_row = smem_u32(smem + kFSmemStg + ch * kActChunk + q * 4096) + (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u;
     const uint32_t stg_x7 = (uint32_t)(lane & 7) << 4;
     uint32_t acc_phase = 0, so_n = 0;
@@ -711,8 +716,8 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     // A unit (the output of one chain step of one tile: flag 0 = d hidden_pre, 1 + s = step s) is published as soon as its
     // stores are complete: the wgrad pair that consumes it picks it up out of L2 a few microseconds later, long before the
     // line would be evicted (measured with scripts/ubench/l2_handoff.cu: bulk-stored data is read back from L2 as long as
-    // less than ~70 MB are written between the store and the load; publishing three times per tile, with all chains in
-    // lock step, put a whole wave of tiles = 92 MB in between and every dZ byte was re-read from HBM).
+    // less than ~70 MB are written between the store and the load; the first version published three times per tile and its
+    // TMA thread needed 3,900 cycles per tile: the pairs fell ever further behind and every dZ byte was re-read from HBM).
     // The store of buffer c is given until buffer c + 2 has been issued to complete (cp.async.bulk.wait_group 2), then the
     // thread orders it (async proxy) before its generic-proxy flag store and releases the flag at gpu scope.
     // Only this thread ever pays for the fences.
