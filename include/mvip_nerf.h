@@ -217,8 +217,9 @@ int mvip_mlp_backward(const void* packed, const float* d_raw /* [n_points,4] */,
                       const void* stash, void* workspace, float* const* grads /* host array */,
                       int accumulate, void* stream);
 
-/* The same call split into its four launches (bit 0 dgrad chain, 1 wgrad, 2 head grads, 3 reduce) so a
- * caller can bracket each kernel with its own events; phases must run in order on the same workspace. */
+/* The same call split into its launches (bit 0: backward_fused_kernel = dgrad chain + all tensor-core weight gradients;
+ * bit 1: kept for ABI compatibility, launches nothing; bit 2: head grads; bit 3: reduce) so a caller can bracket each
+ * kernel with its own events; phases must run in order on the same workspace. */
 int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_points, const void* stash,
                              void* workspace, float* const* grads, int accumulate, int phase_mask, void* stream);
 
