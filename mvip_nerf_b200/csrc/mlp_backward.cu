@@ -31,6 +31,7 @@ struct ChainParams {
   int64_t n_tiles;
   uint32_t* flags;      // [n_tiles][kFlagsPerTile] "dZ unit is in the stash" flags, set by the chain's store warp
   uint32_t* cons_stamp; // [n_tiles][kFlagsPerTile] %globaltimer_lo when the consuming pair started on the unit (debug aid)
+  uint32_t* next_pair;  // [0] tile pairs handed out beyond the first one of every CTA pair; [16 + 4 c + (k & 3)]: rank 0 -> rank 1 of pair c
   uint32_t* credit;     // [0] 2 x dZ units published, [1] 2 x dZ units picked up (a unit read by two work items counts 1 per item)
   int throttle_units;   // a chain does not start a tile while more than this many units are published but not picked up ...
   int throttle_cycles;  // ... for at most this many cycles (a soft limit: it can delay, never block)
@@ -50,6 +51,9 @@ constexpr int kFusedSlots = 80;                          // partial slots: one p
 
 // cycle counters of cluster 0 (debug aid, mvip_debug_wgrad_profile): [0] chain issuer total, [1] waiting for the epilogue,
 // [2] waiting for weights, [3] wgrad issuer total, [4] waiting for operands, [5] wgrad producer: flag wait, [6] stage wait, [7] total
+#ifndef MVIP_PROF_CLUSTER
+#define MVIP_PROF_CLUSTER 0      // the CTA pair whose cycle counters are recorded
+#endif
 __device__ unsigned long long g_wprof[8];
 // hand-over lag of the dZ units (debug aid, mvip_debug_bwd_lag): per CTA pair [0] sum, [1] max of (consumer picks the unit up) -
 // (chain published it) in ns of %globaltimer, [2] units consumed, [3] units that were already published when the consumer asked
@@ -113,7 +117,7 @@ struct WParams {
   const uint8_t* dz;
   int64_t n_tiles;
   float* partials;        // [kFusedSlots] slots of kPartialSlotBytes
-  float* bias_partials;   // [kFusedSlots][256]
+  float* bias_partials;   // [kFusedSlots][2 bias warps][256]
   Segment* segs;          // [kFusedSlots]
 };
 
@@ -212,6 +216,12 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
   __shared__ uint64_t bar_wfull[kFStages], bar_wempty[kFStages], bar_wacc;              // wgrad
   __shared__ uint64_t bar_sfull[2], bar_sfree[2];                                        // dZ staging buffers: epilogue -> store warp
   __shared__ uint32_t tmem_base_s;
+  // Tile pairs are handed out DYNAMICALLY (an atomic counter): with a static round-robin the chains drift apart by several
+  // waves (some SM pairs are persistently faster), units are published up to +-40 us out of tile order, and the wgrad pairs,
+  // which consume in tile order, wait for the stragglers while everything else piles up.  it_q[k & 3] = the k-th tile pair of
+  // this CTA pair, published one iteration ahead by epilogue warp 0 (rank 1 receives it from rank 0 through global memory).
+  __shared__ uint32_t it_q[4];
+  __shared__ uint64_t bar_it[4];
   __shared__ uint32_t w_ready_s;                                                         // wgrad: leading tiles of this pair's sequence whose dZ unit is published
   volatile uint32_t* w_ready = &w_ready_s;
 
@@ -267,9 +277,12 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       mbar_init(&bar_wempty[i], 1 + 2);              // multicast tcgen05.commit + the two bias-sum warps
     }
     mbar_init(&bar_wacc, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_it[i], 1);
+    it_q[0] = (uint32_t)cluster;                     // the first tile pair is static
     w_ready_s = 0;
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_sfull[i], 8); mbar_init(&bar_sfree[i], 1); }
     mbar_fence_init();
+    mbar_arrive(&bar_it[0]);                         // it_q[0] is valid
     if (rank == 0) {
       Segment sg;
       sg.item = w_active ? fit.slot_item : -1; sg.t0 = wk; sg.t1 = w_active ? (int)p.n_tiles : wk; sg.stride = wn;
@@ -282,6 +295,11 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // k-th tile pair of this CTA pair's chain (>= n_pairs: none left)
+  auto get_it = [&](uint32_t k) -> int64_t {
+    mbar_wait(&bar_it[k & 3u], (k >> 2) & 1u);
+    return (int64_t)reinterpret_cast<volatile uint32_t*>(it_q)[k & 3u];
+  };
 
   if (warp < 8) {
     // ===================== chain epilogue: TMEM lane quarter q = warp%4, column half ch of every N-half =====================
@@ -317,14 +335,19 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       const long long t0 = clock64(), delay = (long long)cluster * p.stagger;
       while (clock64() - t0 < delay) __nanosleep(200);
     }
-    for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+    for (uint32_t kq = 0;; ++kq) {
+      const int64_t it = get_it(kq);
+      if (it >= n_pairs) break;
+      // the next tile pair: rank 0 draws it now (the atomic's latency hides behind the first chain steps) ...
+      uint32_t nxt = 0;
+      if (warp == 0 && lane == 0 && rank == 0) nxt = (uint32_t)n_clusters + atom_add_relaxed_gpu(p.next_pair, 1u);
       const int64_t tile = 2 * it + (int64_t)rank;
       const bool tile_valid = tile < p.n_tiles;
       const int64_t g = tile * kTile + r;
       const bool valid = tile_valid && g < p.n_points;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(p.stash + (size_t)(tile_valid ? tile : 0) * kStashTileBytes + kStashMaskOff);
 #ifdef MVIP_TRACE_BWD
-      const bool tr_on = cluster == 0 && rank == 0 && warp == 0 && lane == 0 && it == cluster + 3 * (int64_t)n_clusters;
+      const bool tr_on = cluster == 0 && rank == 0 && warp == 0 && lane == 0 && kq == 3;
       int tr_hs = 0;
 #endif
 
@@ -387,6 +410,25 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       uint2 mw_next = load_mask(0, 0);
 #pragma unroll 1
       for (int s = 0; s < kCSteps; ++s) {
+        // ... and publishes it half-way through the tile: to the peer CTA through global memory (tagged with the iteration
+        // number), to the other warps of this CTA through it_q / bar_it
+        if (warp == 0 && lane == 0 && ((rank == 0 && s == 4) || (rank == 1 && s == 6))) {
+          uint32_t* slot = p.next_pair + 16 + 4 * cluster + ((kq + 1) & 3u);
+          if (rank == 0) {
+            if (nxt > 0xFFFFFu) nxt = 0xFFFFFu;                  // (>= n_pairs either way: n_pairs < 2^20 is checked on the host)
+            st_relaxed_gpu(slot, ((kq + 1) << 20) | nxt);
+          } else {
+            uint32_t v = ld_relaxed_gpu(slot);
+            const long long t0 = clock64();
+            while ((v >> 20) != ((kq + 1) & 0xFFFu)) {
+              if (clock64() - t0 > 8000000000LL) { printf("mvip: fused backward tile hand-out timeout cluster %d\n", cluster); __trap(); }
+              v = ld_relaxed_gpu(slot);
+            }
+            nxt = v & 0xFFFFFu;
+          }
+          reinterpret_cast<volatile uint32_t*>(it_q)[(kq + 1) & 3u] = nxt;
+          mbar_arrive(&bar_it[(kq + 1) & 3u]);
+        }
         // s == 0: d feature (no activation).  s >= 1: dZ_{8-s} = acc [+ d_alpha * w_alpha] masked by h_{9-s} > 0
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -476,7 +518,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     // ===================== chain TMA producer: this CTA's 64 rows of every (step, N-half, K chunk), once per tile pair =====================
     if (lane == 0) {
       uint32_t j = 0; int slot = 0;
-      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+      for (uint32_t kq = 0; get_it(kq) < n_pairs; ++kq) {
         int cbase = 0;
         for (int s = 0; s < kCSteps; ++s) {
           const int n = chain_nchunks(s);
@@ -498,7 +540,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     // ===================== chain relay (peer CTA): "my part of the weight group has landed" =====================
     if (rank == 1 && lane == 0) {
       uint32_t j = 0;
-      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+      for (uint32_t kq = 0; get_it(kq) < n_pairs; ++kq) {
         for (int c = 0; c < 2 * kCSteps; ++c, ++j) {
           mbar_wait(&bar_gfull[j % kG], (j / kG) & 1u);
           mbar_arrive_cluster(mapa_u32(smem_u32(&bar_gfull[j % kG]), 0));
@@ -519,7 +561,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       const uint32_t w_end = w_lo + kFSlots * (kSlotBytes2 >> 4);
       uint32_t bpos = w_lo;
       auto next_slot = [&](uint32_t b) { b += (kSlotBytes2 >> 4); return b == w_end ? w_lo : b; };
-      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+      for (uint32_t kq = 0; get_it(kq) < n_pairs; ++kq) {
 #pragma unroll 1
         for (int s = 0; s < kCSteps; ++s) {
 #pragma unroll 1
@@ -566,7 +608,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           }
         }
       }
-      if (cluster == 0 && lane == 0) { g_wprof[0] = clock64() - c_t0; g_wprof[1] = c_act; g_wprof[2] = c_full; }
+      if (cluster == MVIP_PROF_CLUSTER && lane == 0) { g_wprof[0] = clock64() - c_t0; g_wprof[1] = c_act; g_wprof[2] = c_full; }
     } else {
       watch_flags();
     }
@@ -630,7 +672,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (cluster == 0 && rank == 0 && lane == 0) { g_wprof[5] = p_flag; g_wprof[6] = p_empty; g_wprof[7] = clock64() - p_t0; }
+      if (cluster == MVIP_PROF_CLUSTER && rank == 0 && lane == 0) { g_wprof[5] = p_flag; g_wprof[6] = p_empty; g_wprof[7] = clock64() - p_t0; }
       if (rank == 0 && lane == 0) { g_lag[cluster][2] = n_my; g_lag[cluster][3] = l_ready; }
     }
   } else if (warp == 12) {
@@ -665,7 +707,7 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
         }
         if (elect_one_sync()) umma_commit_2cta(&bar_wacc, 3);
         __syncwarp();
-        if (cluster == 0 && lane == 0) { g_wprof[3] = clock64() - w_t0; g_wprof[4] = w_full; }
+        if (cluster == MVIP_PROF_CLUSTER && lane == 0) { g_wprof[3] = clock64() - w_t0; g_wprof[4] = w_full; }
       } else if (lane == 0) {
         for (int t = wk; t < p.n_tiles; t += wn) {
           for (int h = 0; h < kSubStages; ++h) {
@@ -678,29 +720,31 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
     }
   } else if ((warp == 13 || warp == 14) && w_active) {
     // ===================== bias column sums of this CTA's 128 dZ features, from the staged A operand =====================
-    // thread t4 (0..63) owns features 2 t4, 2 t4 + 1: half chunk t4 / 32, 16-byte group (t4 % 32) / 4, word t4 % 4
+    // thread t4 (0..63): 8-feature group fg = t4 % 16 (piece fg / 8, 16-byte group fg % 8), rows [16 rg, 16 rg + 16) of the stage with
+    // rg = t4 / 16: sixteen 16-byte loads per stage (the first version read 64 words per thread and took as long as the four MMAs
+    // of a full item - longer than those of a small one - before it released the stage)
+    static_assert(kStagePts == 64, "the bias warps assume 64-point stages");
     const int t4 = (warp - 13) * 32 + lane;
-    const uint32_t boff = (uint32_t)(t4 >> 5) * kHalf;
-    const int bg = (t4 & 31) >> 2;
-    const uint32_t bw = (uint32_t)(t4 & 3) * 4;
-    float b0 = 0.f, b1 = 0.f;
+    const int fg = t4 & 15, rg = t4 >> 4;
+    const uint32_t boff = (uint32_t)(fg >> 3) * kHalf + (uint32_t)rg * 16u * 128u;
+    const uint32_t g7 = (uint32_t)(fg & 7);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool do_bias = (fit.bias_ranks >> rank) & 1;
     int stage = 0; uint32_t phase = 0;
     for (int t = wk; t < p.n_tiles; t += wn) {
       for (int h = 0; h < kSubStages; ++h) {
         mbar_wait(&bar_wfull[stage], phase);
         if (do_bias) {
-          const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff + bw;
+          const uint32_t a32 = smem_u32(smem) + kFSmemWg + stage * kFStageBytes + boff;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t ak = a32 + k * 128 + (((uint32_t)bg ^ (uint32_t)k) << 4);
-#pragma unroll
-            for (int i = 0; i < kStagePts / 8; ++i) {
-              uint32_t pr;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pr) : "r"(ak + i * 1024));
-              b0 += __uint_as_float(pr << 16);
-              b1 += __uint_as_float(pr & 0xffff0000u);
-            }
+          for (int i = 0; i < 16; ++i) {          // row 16 rg + i: (row & 7) = i & 7
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(a32 + (uint32_t)i * 128u + ((g7 ^ (uint32_t)(i & 7)) << 4)));
+            acc[0] += __uint_as_float(w0 << 16); acc[1] += __uint_as_float(w0 & 0xffff0000u);
+            acc[2] += __uint_as_float(w1 << 16); acc[3] += __uint_as_float(w1 & 0xffff0000u);
+            acc[4] += __uint_as_float(w2 << 16); acc[5] += __uint_as_float(w2 & 0xffff0000u);
+            acc[6] += __uint_as_float(w3 << 16); acc[7] += __uint_as_float(w3 & 0xffff0000u);
           }
         }
         __syncwarp();
@@ -708,9 +752,14 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
     }
-    float* bias_out = wp.bias_partials + (size_t)cluster * 256 + 128 * rank;      // zeros where this CTA contributes nothing
-    bias_out[2 * t4] = b0;
-    bias_out[2 * t4 + 1] = b1;
+    // the two row groups of a warp meet by shuffle; the two warps write separate partials (the reduce kernel adds them)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    if (lane < 16) {
+      float* bias_out = wp.bias_partials + (size_t)cluster * 512 + (size_t)(warp - 13) * 256 + 128 * rank + 8 * fg;     // zeros where this CTA contributes nothing
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bias_out[e] = acc[e];
+    }
   } else if (warp == 15) {
     // ===================== dZ store warp: one 32 KB bulk store per staging buffer; publication of every dZ unit =====================
     // A unit (the output of one chain step of one tile: flag 0 = d hidden_pre, 1 + s = step s) is published as soon as its
@@ -727,7 +776,9 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
       auto publish = [&](uint32_t*& f) {
         if (f) { fence_proxy_async_global(); st_release_gpu(f, globaltimer_lo() | 1u); red_add_relaxed_gpu(p.credit, 2u); f = nullptr; }   // non-zero; the value is a time stamp (debug)
       };
-      for (int64_t it = cluster; it < n_pairs; it += n_clusters) {
+      for (uint32_t kq = 0;; ++kq) {
+        const int64_t it = get_it(kq);
+        if (it >= n_pairs) break;
         const int64_t tile = 2 * it + (int64_t)rank;
         const bool tile_valid = tile < p.n_tiles;
         uint8_t* dz_tile = p.dz + (size_t)(tile_valid ? tile : 0) * kDzTileBytes;
@@ -954,11 +1005,11 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
       for (; k + 8 <= nslots; k += 8) {
         float a[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = p.bias_partials[(size_t)slots[k + q] * 256 + e];
+        for (int q = 0; q < 8; ++q) a[q] = p.bias_partials[(size_t)slots[k + q] * 512 + e] + p.bias_partials[(size_t)slots[k + q] * 512 + 256 + e];
 #pragma unroll
         for (int q = 0; q < 8; ++q) s += a[q];
       }
-      for (; k < nslots; ++k) s += p.bias_partials[(size_t)slots[k] * 256 + e];
+      for (; k < nslots; ++k) s += p.bias_partials[(size_t)slots[k] * 512 + e] + p.bias_partials[(size_t)slots[k] * 512 + 256 + e];
       float* dst = p.grads.p[itm.bias] + e;
       *dst = p.accumulate ? *dst + s : s;
     }
@@ -975,10 +1026,10 @@ Workspace carve(int64_t n_points) {
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
   w.dz = take((size_t)num_tiles(n_points) * kDzTileBytes);
   w.partials = take((size_t)kFusedSlots * kPartialSlotBytes);
-  w.bias = take((size_t)kFusedSlots * 256 * sizeof(float));
+  w.bias = take((size_t)kFusedSlots * 512 * sizeof(float));
   w.segs = take((size_t)kFusedSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
-  w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t) + 64);      // + the two credit counters
+  w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t) + 64 + (16 + 4 * kFusedSlots) * sizeof(uint32_t));   // + credit counters + tile hand-out
   w.stamps = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
   return w;
@@ -1062,6 +1113,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   cp.flags = reinterpret_cast<uint32_t*>(wsb + ws.flags);
   cp.cons_stamp = reinterpret_cast<uint32_t*>(wsb + ws.stamps);
   cp.credit = cp.flags + (size_t)n_tiles * kFlagsPerTile;
+  cp.next_pair = cp.credit + 16;
   cp.throttle_units = g_throttle_units;
   cp.throttle_cycles = g_throttle_cycles;
   cp.throttle_gain = g_throttle_gain;
@@ -1076,6 +1128,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
   // one tile pair takes a chain ~53,000 cycles (profiles/r02_bwd_trace.md): spread the chain starts over one such period;
   // pointless when there is a single wave of tile pairs
   cp.stagger = ((n_tiles + 1) / 2 > clusters) ? (g_stagger >= 0 ? g_stagger : 53000 / clusters) : 0;
+  MVIP_REQUIRE((n_tiles + 1) / 2 + clusters < (1 << 20), MVIP_E_UNSUPPORTED, "mvip_mlp_backward: more than 2^20 tile pairs (268 M points) per call");
   MVIP_REQUIRE(clusters >= kFusedItems, MVIP_E_UNSUPPORTED, "mvip_mlp_backward: needs at least %d SM pairs", kFusedItems);
 
   // 1. fused dgrad chain + weight gradients (phase bit 1; bit 2 is kept for ABI compatibility and launches nothing)
@@ -1110,7 +1163,7 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
           if (given[i] < n_i[i]) { plan.item[c] = (unsigned char)i; plan.k[c] = (unsigned char)given[i]; plan.n[c] = (unsigned char)n_i[i]; ++given[i]; ++c; }
       plan_clusters = clusters;
     }
-    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t) + 64, st));
+    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t) + 64 + (16 + 4 * kFusedSlots) * sizeof(uint32_t), st));
     MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0xff, (size_t)kFusedSlots * sizeof(Segment), st));      // item = -1: unused slot
     const size_t smem = kFSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
