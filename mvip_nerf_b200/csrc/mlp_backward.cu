@@ -107,7 +107,7 @@ __constant__ WItem kItems[kNumItems] = {
 constexpr int kRealItems = kNumItems;
 
 struct Segment {
-  int item;       // kItems index of the slot, -1 = empty
+  int item;       // kItems index of the slot; -1 or t1 == t0 (the zeroed table) = empty
   int t0, t1;     // tiles t0, t0 + stride, ... < t1
   int stride;
 };
@@ -828,7 +828,13 @@ backward_fused_kernel(const ChainParams p, const WParams wp, const FusedPlan pla
 // 3. alpha / rgb head grads on CUDA cores
 // =================================================================================================
 constexpr int kHeadFloats = 256 + 4 + 384 + 4;   // dW_alpha, db_alpha(+pad), dW_rgb, db_rgb(+pad)
-constexpr int kHeadMaxBlocks = 1184;             // 8 per SM
+constexpr int kHeadMaxBlocks = 1184;             // partial slots in the workspace (one per block; the grid is one block per SM)
+constexpr int kHgRows = 64;                      // points per pipeline stage (half a tile)
+constexpr int kHgStages = 4;
+constexpr uint32_t kHgPiece = kHgRows * 128;     // 64 rows of one chunk image (rows 0-63 / 64-127 of a chunk are contiguous)
+constexpr uint32_t kHgStageBytes = 6 * kHgPiece + kHgRows * 16;   // h8 (4 chunks) + hidden (2 chunks) + d_raw
+constexpr int kHgThreads = 288;                  // 8 consumer warps + 1 bulk-copy warp
+constexpr size_t kHgSmemBytes = (size_t)kHgStages * kHgStageBytes + 1024;
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4 v, float (&f)[8]) {
   f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
@@ -838,59 +844,93 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 v, float (&f)[8]) {
 }
 
 // dW_alpha[j] = sum_p d_alpha[p] h8[p][j];  dW_rgb[c][j] = sum_p d_rgb[p][c] hidden[p][j];  db = sum_p d_raw[p].
-// Thread (cg = tid%32, rg = tid/32) owns the 8 features [8cg, 8cg+8) of rows [16rg, 16rg+16) of every tile of
-// its block: one 16-byte load per (row, operand), eight lanes covering one 128-byte row segment.
-__global__ void __launch_bounds__(256, 2) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
-                                                         int64_t n_points, int64_t n_tiles, float* __restrict__ out) {
+// One block per SM walks half tiles (64 points) in a fixed order.  Warp 8 streams the operands of a half tile - the h8 and
+// hidden rows of the stash (six 8 KB pieces) and 1 KB of d_raw - into a four-stage shared-memory ring with bulk copies
+// (evict-first: this is the last reader of the stash); consumer warp w owns rows [8w, 8w+8) of every stage.  h8: lane l
+// holds the 8 features [8l, 8l+8) of a row; hidden (128 features): lane l holds features [8(l&15), +8) of the rows of
+// parity l>>4, the two half warps are added at the end.  Fixed summation order => bitwise reproducible.
+__global__ void __launch_bounds__(kHgThreads, 1) head_grads_kernel(const float4* __restrict__ d_raw, const uint8_t* __restrict__ stash,
+                                                                int64_t n_points, int64_t n_half, float* __restrict__ out) {
+  extern __shared__ uint8_t hg_smem_raw[];
   __shared__ float red[8][kHeadFloats];
-  const int tid = threadIdx.x, cg = tid & 31, rg = tid >> 5;
-  float aa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float ar[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
-  const uint32_t h8_off = (uint32_t)(kStashH + 28 + (cg >> 3)) * kActChunk;
-  const uint32_t hid_off = (uint32_t)(kStashHidden + ((cg & 15) >> 3)) * kActChunk;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const uint8_t* tile = stash + (size_t)t * kStashTileBytes;
-    // all loads of the tile first (32 independent 16-byte requests per thread), then the FMAs
-    uint4 hv[16], xv[16];
-    float4 dv[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int row = rg * 16 + i;
-      const uint32_t o = chunk_off16(row, cg & 7);
-      hv[i] = __ldg(reinterpret_cast<const uint4*>(tile + h8_off + o));
-      xv[i] = (cg < 16) ? __ldg(reinterpret_cast<const uint4*>(tile + hid_off + o)) : make_uint4(0u, 0u, 0u, 0u);
-      const int64_t g = t * kTile + row;
-      dv[i] = g < n_points ? __ldg(d_raw + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ uint64_t full[kHgStages], empty[kHgStages];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hg_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kHgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    const uint64_t pol = l2_policy_evict_first();
+    int it = 0;
+    for (int64_t h = blockIdx.x; h < n_half; h += gridDim.x, ++it) {
+      const int s = it % kHgStages;
+      if (it >= kHgStages) mbar_wait(&empty[s], ((it / kHgStages) & 1) ^ 1);
+      uint8_t* dst = ring + (size_t)s * kHgStageBytes;
+      const uint8_t* tile = stash + (size_t)(h >> 1) * kStashTileBytes + (size_t)(h & 1) * kHgPiece;
+      const int64_t left = n_points - h * kHgRows;                       // >= 1: n_half = ceil(n_points / 64)
+      const uint32_t d_bytes = (uint32_t)(left < kHgRows ? left : kHgRows) * 16u;
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], 6 * kHgPiece + d_bytes);
+      __syncwarp();
+      if (lane < 4) tma_load_1d_hint(dst + lane * kHgPiece, tile + (size_t)(kStashH + 28 + lane) * kActChunk, kHgPiece, &full[s], pol);
+      else if (lane < 6) tma_load_1d_hint(dst + lane * kHgPiece, tile + (size_t)(kStashHidden + lane - 4) * kActChunk, kHgPiece, &full[s], pol);
+      else if (lane == 6) tma_load_1d(dst + 6 * kHgPiece, d_raw + h * kHgRows, d_bytes, &full[s]);
     }
+  } else {
+    float aa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ar[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t h8_piece = (uint32_t)(lane >> 3) * kHgPiece, hid_piece = (uint32_t)(4 + ((lane & 15) >> 3)) * kHgPiece;
+    const int g8 = lane & 7, par = lane >> 4;
+    int it = 0;
+    for (int64_t h = blockIdx.x; h < n_half; h += gridDim.x, ++it) {
+      const int s = it % kHgStages;
+      mbar_wait(&full[s], (it / kHgStages) & 1);
+      const uint8_t* st = ring + (size_t)s * kHgStageBytes;
+      const float4* dsm = reinterpret_cast<const float4*>(st + 6 * kHgPiece);
+      const int64_t left = n_points - h * kHgRows;
+      const int valid = (int)(left < kHgRows ? left : kHgRows);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 d = dv[i];
-      float h[8], x[8];
-      unpack_bf16x8(hv[i], h);
-      unpack_bf16x8(xv[i], x);
+      for (int i = 0; i < 8; ++i) {
+        const int row = warp * 8 + i;
+        const float4 d = row < valid ? dsm[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float f[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(st + h8_piece + chunk_off16(row, g8)), f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        aa[e] += d.w * h[e];
-        ar[e] += d.x * x[e]; ag[e] += d.y * x[e]; ab[e] += d.z * x[e];
+        for (int e = 0; e < 8; ++e) aa[e] += d.w * f[e];
+        ds.x += d.x; ds.y += d.y; ds.z += d.z; ds.w += d.w;
       }
-      ds.x += d.x; ds.y += d.y; ds.z += d.z; ds.w += d.w;
-    }
-  }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    red[rg][cg * 8 + e] = aa[e];
-    if (cg < 16) {
-      red[rg][260 + cg * 8 + e] = ar[e];
-      red[rg][260 + 128 + cg * 8 + e] = ag[e];
-      red[rg][260 + 256 + cg * 8 + e] = ab[e];
+      for (int i = 0; i < 4; ++i) {
+        const int row = warp * 8 + 2 * i + par;
+        const float4 d = row < valid ? dsm[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float f[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(st + hid_piece + chunk_off16(row, g8)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ar[e] += d.x * f[e]; ag[e] += d.y * f[e]; ab[e] += d.z * f[e]; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ar[e] += __shfl_xor_sync(FULL_MASK, ar[e], 16);
+      ag[e] += __shfl_xor_sync(FULL_MASK, ag[e], 16);
+      ab[e] += __shfl_xor_sync(FULL_MASK, ab[e], 16);
+      red[warp][lane * 8 + e] = aa[e];
+      if (lane < 16) {
+        red[warp][260 + lane * 8 + e] = ar[e];
+        red[warp][260 + 128 + lane * 8 + e] = ag[e];
+        red[warp][260 + 256 + lane * 8 + e] = ab[e];
+      }
+    }
+    if (lane == 31) { red[warp][256] = ds.w; red[warp][644] = ds.x; red[warp][645] = ds.y; red[warp][646] = ds.z; }
+    if (lane == 30) { red[warp][257] = red[warp][258] = red[warp][259] = 0.f; red[warp][647] = 0.f; }
   }
-  if (cg == 31) { red[rg][256] = ds.w; red[rg][644] = ds.x; red[rg][645] = ds.y; red[rg][646] = ds.z; }
-  if (cg == 30) { red[rg][257] = red[rg][258] = red[rg][259] = 0.f; red[rg][647] = 0.f; }
   __syncthreads();
   float* o = out + (size_t)blockIdx.x * kHeadFloats;
-  for (int e = tid; e < kHeadFloats; e += 256) {
+  for (int e = tid; e < kHeadFloats; e += kHgThreads) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][e];
@@ -1027,8 +1067,8 @@ Workspace carve(int64_t n_points) {
   w.dz = take((size_t)num_tiles(n_points) * kDzTileBytes);
   w.partials = take((size_t)kFusedSlots * kPartialSlotBytes);
   w.bias = take((size_t)kFusedSlots * 512 * sizeof(float));
-  w.segs = take((size_t)kFusedSlots * sizeof(Segment));
   w.heads = take((size_t)kHeadMaxBlocks * kHeadFloats * sizeof(float));
+  w.segs = take((size_t)kFusedSlots * sizeof(Segment));      // segs and flags are adjacent: one memset clears both
   w.flags = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t) + 64 + (16 + 4 * kFusedSlots) * sizeof(uint32_t));   // + credit counters + tile hand-out
   w.stamps = take((size_t)num_tiles(n_points) * kFlagsPerTile * sizeof(uint32_t));
   w.total = off;
@@ -1065,7 +1105,7 @@ int mvip_debug_bwd_trace(long long* out240) {
 
 // cycles between the chain starts of consecutive CTA pairs (tuning aid; < 0 restores the default)
 static int g_stagger = -1;
-static int g_throttle_units = 500, g_throttle_cycles = 60000, g_throttle_gain = 20;   // measured: 1.42 ms (best = median) at P = 524,288; waiting for the excess to clear: best 1.34, median 1.43 - 1.6
+static int g_throttle_units = 150, g_throttle_cycles = 60000, g_throttle_gain = 40;   // swept at P = 524,288 (units, gain): (150, 40) median 1.249 ms, (500, 20) 1.266, (200, 20) 1.257, no throttle 1.263
 int mvip_debug_set_bwd_throttle(int units, int cycles, int gain) { g_throttle_units = units; g_throttle_cycles = cycles; g_throttle_gain = gain; return MVIP_OK; }
 int mvip_debug_set_bwd_stagger(int cycles) { g_stagger = cycles; return MVIP_OK; }
 
@@ -1163,19 +1203,21 @@ int mvip_mlp_backward_phases(const void* packed, const float* d_raw, int64_t n_p
           if (given[i] < n_i[i]) { plan.item[c] = (unsigned char)i; plan.k[c] = (unsigned char)given[i]; plan.n[c] = (unsigned char)n_i[i]; ++given[i]; ++c; }
       plan_clusters = clusters;
     }
-    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.flags, 0, (size_t)n_tiles * kFlagsPerTile * sizeof(uint32_t) + 64 + (16 + 4 * kFusedSlots) * sizeof(uint32_t), st));
-    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0xff, (size_t)kFusedSlots * sizeof(Segment), st));      // item = -1: unused slot
+    // flags, credit counters, tile hand-out and the segment table (all-zero segment = unused slot: t1 == t0) in one memset
+    MVIP_CUDA_OK(cudaMemsetAsync(wsb + ws.segs, 0, ws.stamps - ws.segs, st));
     const size_t smem = kFSmemBytes + 1024;
     MVIP_SMEM_OPT_IN(backward_fused_kernel, smem);
     backward_fused_kernel<<<2 * clusters, kFThreads, smem, st>>>(cp, wp, plan);
     MVIP_LAUNCH_OK("backward_fused_kernel");
   }
   // 3. heads
-  const int head_cap = sms * 8 < kHeadMaxBlocks ? sms * 8 : kHeadMaxBlocks;
-  const int head_grid = (int)(n_tiles < head_cap ? n_tiles : head_cap);
+  const int64_t n_half = (n_points + kHgRows - 1) / kHgRows;
+  const int head_cap = sms < kHeadMaxBlocks ? sms : kHeadMaxBlocks;
+  const int head_grid = (int)(n_half < head_cap ? n_half : head_cap);
   if (phase_mask & 4) {
-    head_grads_kernel<<<head_grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_raw), static_cast<const uint8_t*>(stash),
-                                                 n_points, n_tiles, reinterpret_cast<float*>(wsb + ws.heads));
+    MVIP_SMEM_OPT_IN(head_grads_kernel, kHgSmemBytes);
+    head_grads_kernel<<<head_grid, kHgThreads, kHgSmemBytes, st>>>(reinterpret_cast<const float4*>(d_raw), static_cast<const uint8_t*>(stash),
+                                                                   n_points, n_half, reinterpret_cast<float*>(wsb + ws.heads));
     MVIP_LAUNCH_OK("head_grads_kernel");
   }
   // 4. reduce
