@@ -345,160 +345,296 @@ sample_fine_kernel(const float* __restrict__ z_g, const float* __restrict__ weig
 }
 
 // ---------------------------------------------------------------------------------------------
-// sample_fine for the shape render_rays uses (N_samples = 64 coarse depths, N_importance = 64): one warp per ray, lane l
-// owns z[2l..2l+1], the two pdf entries p[2l..2l+1] and the two draws u[2l..2l+1].  Compared with the generic kernel:
-//   * rows move as 8-byte vectors, the weights never round-trip through shared memory except for the ATen-order row sum;
-//   * the fp64 cdf scan works on register values; only cdf / bins (the binary-search tables) live in shared memory;
-//   * the searches are the branch-free 6-step form (no bounds test: 32+16+8+4+2+1-1 = 62 is the last cdf index);
-//   * unsorted draws are ordered by a REGISTER bitonic network (15 shuffle stages on 2 values per lane) instead of a
-//     shared-memory one, and the sorted run is merged with the coarse depths by a 7-stage bitonic MERGE (reverse the
-//     samples, then compare-exchange at distances 64..1) instead of 128 binary searches.
+// sample_fine for the shape render_rays uses (N_samples = 64 coarse depths, N_importance = 64): FOUR rays per warp, eight
+// lanes per ray, lane t of a group owns the eight consecutive elements [8t, 8t+8) of every row (z, weights, draws), moved
+// as 16-byte vectors.  Compared with the generic kernel:
+//   * the weights go through shared memory once, for the ATen-order row sum (a transposed access); the fp64 cdf scan works
+//     on register values (three shuffle steps inside the group); only cdf / bins (the search tables) live in shared memory,
+//     72 floats apart per ray so that the four groups of a warp hit different banks;
+//   * the searches are the branch-free 6-step form; the first three levels (cdf[31], cdf[15|47], cdf[7|23|39|55]) are
+//     held in registers and shared by the lane's eight draws, the last three and the interpolation operands are loads;
+//   * unsorted draws are ordered by a REGISTER bitonic network: 21 stages, 15 of them inside the lane (plain min / max on
+//     registers), 6 across lanes (8 shuffles each, for four rays at once); the sorted run is merged with the coarse depths
+//     by a 7-stage bitonic MERGE (reverse the samples, compare-exchange at distances 64..1: three of them across lanes).
+//   A ray costs ~31 shuffle and ~25 shared-memory instructions (the two-elements-per-lane version: ~85 and ~40; the
+//   shuffle / shared-memory pipe is what bounds this stage, profiles/r02_hbm_stages.md).
 // Every value written is bit-identical to the generic kernel's (same roundings; sort / merge only permute values).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float invert_cdf64(const float* cdf, const float* bins, float u, int* ind_out) {
-  int pos = 0;
-#pragma unroll
-  for (int step = 32; step > 0; step >>= 1)
-    if (cdf[pos + step - 1] <= u) pos += step;      // #{i < 63 : cdf[i] <= u} == upper_bound
-  *ind_out = pos;
-  const int below = max(0, pos - 1), above = min(62, pos);
-  const float cb = cdf[below];
-  float denom = __fsub_rn(cdf[above], cb);
-  if (denom < 1e-5f) denom = 1.0f;
-  const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
-  const float bb = bins[below];
-  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bins[above], bb)));
-}
+constexpr int kF8Stride = 72;   // floats between the W1 / bins rows of neighbouring rays (64 + 8: a bank shift of 8 per group)
+constexpr int kCdfStride = 65;  // ... and between their cdf rows
 
 __device__ __forceinline__ void cmpx(float& lo, float& hi) {
   const float a = fminf(lo, hi), b = fmaxf(lo, hi);
   lo = a; hi = b;
 }
+// shared-memory load at a 32-bit shared address plus an immediate byte offset (ordered like a volatile access)
+template <int OFF>
+__device__ __forceinline__ float lds_off(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
 
+#ifndef MVIP_SF_MINB
+#define MVIP_SF_MINB 4
+#endif
 template <bool U_ROW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MVIP_SF_MINB)
 sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ weights_g, const float* __restrict__ u_g,
                      int64_t n_rays, float* __restrict__ samples_g, int64_t* __restrict__ inds_g,
                      float* __restrict__ merged_g, float* __restrict__ std_g) {
-  __shared__ float sm[8][3][64];
+  // per warp: W1[j] = weights[j] + 1e-5 (w[i] = W1[i+1]; later the pdf for the sequential fallback), bins, and the cdf.
+  // W1 / bins rows are 72 floats apart (16-byte vector stores; the transposed reads of the row sum are conflict-free);
+  // the cdf rows - the table the searches probe - are 65 apart: the probes of a search level sit at equal positions
+  // modulo 8 / 4 / 2, so a row offset that is a multiple of 8 banks puts the four rays of a warp on the same few
+  // banks (simulated: 31.8 shared-memory cycles per draw at 72, 21.7 at 65; one dimension of scalar stores pays it).
+  __shared__ __align__(16) float sm[8][3][4 * kF8Stride + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* w = sm[warp][0];
-  float* cdf = sm[warp][1];
-  float* bins = sm[warp][2];
-  float2 u2 = make_float2(0.f, 0.f);
-  if (U_ROW) u2 = __ldg(reinterpret_cast<const float2*>(u_g) + lane);
-  for (int64_t ray = (int64_t)blockIdx.x * 8 + warp; ray < n_rays; ray += (int64_t)gridDim.x * 8) {
-    const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_g + ray * 64) + lane);
-    const float2 w2 = __ldg(reinterpret_cast<const float2*>(weights_g + ray * 64) + lane);
-    if (!U_ROW) u2 = __ldg(reinterpret_cast<const float2*>(u_g + ray * 64) + lane);
-    // w[i] = weights[i+1] + 1e-5 (i < 62): weights[2l] is w[2l-1], weights[2l+1] is w[2l]
-    const float wa = __fadd_rn(w2.x, 1e-5f), wb = __fadd_rn(w2.y, 1e-5f);
-    if (lane > 0) w[2 * lane - 1] = wa;
-    if (lane < 31) w[2 * lane] = wb;
-    const float z_next = __shfl_down_sync(FULL_MASK, z2.x, 1);
-    bins[2 * lane] = __fmul_rn(0.5f, __fadd_rn(z2.y, z2.x));
-    if (lane < 31) bins[2 * lane + 1] = __fmul_rn(0.5f, __fadd_rn(z_next, z2.y));
+  const int t = lane & 7, q = lane >> 3;
+  float* W1 = sm[warp][0] + kF8Stride * q;
+  float* CT = sm[warp][1] + kCdfStride * q;        // cdf[i] = CT[i], i = 0..62
+  float* BN = sm[warp][2] + kF8Stride * q;
+  float u[8];
+  if (U_ROW) ldg8(u_g + 8 * t, u);
+  for (int64_t ray0 = ((int64_t)blockIdx.x * 8 + warp) * 4; ray0 < n_rays; ray0 += (int64_t)gridDim.x * 32) {
+    const bool active = ray0 + q < n_rays;
+    const int64_t ray = active ? ray0 + q : n_rays - 1;     // idle groups shadow the last ray (nothing is stored)
+    float z[8], wv[8];
+    ldg8(z_g + ray * 64 + 8 * t, z);
+    ldg8(weights_g + ray * 64 + 8 * t, wv);
+    if (!U_ROW) ldg8(u_g + ray * 64 + 8 * t, u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wv[k] = __fadd_rn(wv[k], 1e-5f);
+    st8(W1 + 8 * t, wv);
+    {
+      const float z_next = __shfl_down_sync(FULL_MASK, z[0], 1, 8);
+      float b[8];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) b[k] = __fmul_rn(0.5f, __fadd_rn(z[k + 1], z[k]));
+      b[7] = __fmul_rn(0.5f, __fadd_rn(z_next, z[7]));      // bins[63] (t = 7) does not exist and is never read
+      st8(BN + 8 * t, b);
+    }
     __syncwarp();
     // torch.sum in ATen's CPU order for K = 62: 7 vectors of 8 lanes (4 accumulators, vectors 4..6 fold into the first),
     // then the 6-element tail, then the 8 lanes of the combined vector, all sequential fp32 adds
-    float t = 0.f;
-    if (lane < 8) {
-      float ps0 = w[lane];
-      const float ps1 = w[8 + lane], ps2 = w[16 + lane], ps3 = w[24 + lane];
-      ps0 = __fadd_rn(ps0, w[32 + lane]);
-      ps0 = __fadd_rn(ps0, w[40 + lane]);
-      ps0 = __fadd_rn(ps0, w[48 + lane]);
-      t = __fadd_rn(__fadd_rn(__fadd_rn(ps0, ps1), ps2), ps3);
+    float s;
+    {
+      float ps0 = W1[1 + t];
+      const float ps1 = W1[9 + t], ps2 = W1[17 + t], ps3 = W1[25 + t];
+      ps0 = __fadd_rn(ps0, W1[33 + t]);
+      ps0 = __fadd_rn(ps0, W1[41 + t]);
+      ps0 = __fadd_rn(ps0, W1[49 + t]);
+      const float tv = __fadd_rn(__fadd_rn(__fadd_rn(ps0, ps1), ps2), ps3);
+      s = 0.f;
+#pragma unroll
+      for (int k = 57; k < 63; ++k) s = __fadd_rn(s, W1[k]);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(FULL_MASK, tv, l, 8));
     }
-    float s = 0.f;
+    // pdf entries of this lane: p[8t + k] = w[8t + k] / s = W1[8t + k + 1] / s, k = 0..7 (62 entries: t = 7 has six).
+    // IEEE division: the eight quotients share the divisor, so the reciprocal refinement of the compiler's own div.rn
+    // sequence (MUFU.RCP, two FFMAs) is done once and each quotient takes its three remaining FFMAs - the same
+    // operations on the same values, hence the same bits.  That sequence is only valid away from the exponent limits
+    // (the compiler guards it with FCHK); outside a generous safe range the plain __fdiv_rn is used.
+    float p[8];
+    {
+      const float w_next = __shfl_down_sync(FULL_MASK, wv[0], 1, 8);
+      float num[8];
 #pragma unroll
-    for (int k = 56; k < 62; ++k) s = __fadd_rn(s, w[k]);
+      for (int k = 0; k < 7; ++k) num[k] = wv[k + 1];
+      num[7] = w_next;
+      bool safe = (s >= 1e-30f) && (s <= 1e30f);
 #pragma unroll
-    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(FULL_MASK, t, l));
-    // pdf entries of this lane: p[2l] = w[2l] / s (own wb), p[2l+1] = w[2l+1] / s (next lane's wa); lane 31 has none
-    const float wa_next = __shfl_down_sync(FULL_MASK, wa, 1);
-    const float p0 = __fdiv_rn(wb, s), p1 = __fdiv_rn(wa_next, s);
-    bool ok = (lane == 31) || ((p0 >= 7.450580596923828e-09f) && (p0 <= 1.0f) && (p1 >= 7.450580596923828e-09f) && (p1 <= 1.0f));
-    ok = __all_sync(FULL_MASK, ok);
-    __syncwarp();                                   // all reads of w[] are done before the fallback may overwrite it
-    if (ok) {                                       // exact fp64 scan == the sequential CPU cumsum (see warp_build_cdf)
-      const double d0 = (lane < 31) ? (double)p0 : 0.0, d1 = (lane < 31) ? (double)p1 : 0.0;
-      const double local = d0 + d1;
+      for (int k = 0; k < 8; ++k) safe = safe && (num[k] >= 1e-30f) && (num[k] <= 1e30f);
+      if (__all_sync(FULL_MASK, safe)) {
+        float r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s));
+        const float r = __fmaf_rn(r0, __fmaf_rn(r0, -s, 1.0f), r0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float q0 = __fmaf_rn(num[k], r, 0.0f);
+          p[k] = __fmaf_rn(r, __fmaf_rn(q0, -s, num[k]), q0);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = __fdiv_rn(num[k], s);
+      }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (8 * t + k < 62) ok = ok && (p[k] >= 7.450580596923828e-09f) && (p[k] <= 1.0f);
+    const unsigned okb = __ballot_sync(FULL_MASK, ok);
+    const bool gok = ((okb >> (8 * q)) & 0xffu) == 0xffu;
+    {   // exact fp64 scan == the sequential CPU cumsum (see warp_build_cdf)
+      double d[8], local = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k] = (8 * t + k < 62) ? (double)p[k] : 0.0; local += d[k]; }
       double incl = local;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double v = __shfl_up_sync(FULL_MASK, incl, o);
-        if (lane >= o) incl += v;
+      for (int o = 1; o < 8; o <<= 1) {
+        const double v = __shfl_up_sync(FULL_MASK, incl, o, 8);
+        if (t >= o) incl += v;
       }
       double run = incl - local;
-      run += d0;
-      if (lane < 31) cdf[2 * lane + 1] = (float)run;
-      run += d1;
-      if (lane < 31) cdf[2 * lane + 2] = (float)run;
-      if (lane == 0) cdf[0] = 0.f;
-    } else {
-      if (lane < 31) { w[2 * lane] = p0; w[2 * lane + 1] = p1; }
+      float c[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { run += d[k]; c[k] = (float)run; }
+      if (gok) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) CT[8 * t + k + 1] = c[k];   // (t = 7: slots 63, 64 are padding)
+      }
+      if (t == 0) CT[0] = 0.f;
+    }
+    if (okb != 0xffffffffu) {   // a pdf entry below 2^-27 somewhere in the warp: that ray's cdf by the sequential scan
+      __syncwarp();             // all reads of W1 are done
+      st8(W1 + 8 * t, p);       // W1[i] = p[i] now
       __syncwarp();
-      if (lane == 0) {
+      if (!gok && t == 0) {
         double run = 0.0;
-        cdf[0] = 0.f;
         for (int i = 0; i < 62; ++i) {
-          run += (double)w[i];
-          cdf[i + 1] = (float)run;
+          run += (double)W1[i];
+          CT[i + 1] = (float)run;
         }
       }
     }
     __syncwarp();
-    int i0, i1;
-    float s0 = invert_cdf64(cdf, bins, u2.x, &i0);
-    float s1 = invert_cdf64(cdf, bins, u2.y, &i1);
-    if (samples_g) reinterpret_cast<float2*>(samples_g + ray * 64)[lane] = make_float2(s0, s1);
-    if (inds_g) reinterpret_cast<longlong2*>(inds_g + ray * 64)[lane] = make_longlong2((long long)i0, (long long)i1);
-    if (std_g) {  // torch.std(unbiased=False), run.py:1836: fp32 two-pass like the reference's (tolerance-checked, not bit-exact)
-      const float mean = warp_sum(s0 + s1) * (1.0f / 64.0f);
-      const float e0 = s0 - mean, e1 = s1 - mean;
-      const float sq = warp_sum(e0 * e0 + e1 * e1);
-      if (lane == 0) std_g[ray] = sqrtf(sq * (1.0f / 64.0f));
-    }
-    // ---- order the 64 samples (element e = 2 lane + r) if the draws were not sorted
-    const float s_next = __shfl_down_sync(FULL_MASK, s0, 1);
-    const bool sorted = (s0 <= s1) && (lane == 31 || s1 <= s_next);
-    if (!__all_sync(FULL_MASK, sorted)) {
+    // ---- the draws: upper_bound(cdf, u) with the first three levels in registers, then the lerp (no FMA)
+    float sv[8];
+    {
+      // Shared-memory addresses are kept as 32-bit byte addresses and every probe is a load with an immediate offset
+      // (the compiler's own index arithmetic costs 30 instructions per draw instead of 17).
+      const uint32_t cdf0 = smem_u32(CT);                   // address of cdf[0]
+      const uint32_t to_bins = smem_u32(BN) - cdf0;         // bytes from cdf[i] to bins[i] of this ray
+      const float c31 = lds_off<31 * 4>(cdf0), c15 = lds_off<15 * 4>(cdf0), c47 = lds_off<47 * 4>(cdf0);
+      uint32_t pa[8];                                       // address of cdf[pos]; the probe of a step is cdf[pos + step - 1]
 #pragma unroll
-      for (int k = 2; k <= 64; k <<= 1) {
-        const bool up = ((2 * lane) & k) == 0;
+      for (int k = 0; k < 8; ++k) {                         // the first two levels from registers
+        const bool hi = c31 <= u[k];
+        pa[k] = cdf0 + (hi ? 128u : 0u) + (((hi ? c47 : c15) <= u[k]) ? 64u : 0u);
+      }
 #pragma unroll
-        for (int j = k >> 1; j > 1; j >>= 1) {
-          const bool keep_min = ((((2 * lane) & j) == 0) == up);
-          const float o0 = __shfl_xor_sync(FULL_MASK, s0, j >> 1), o1 = __shfl_xor_sync(FULL_MASK, s1, j >> 1);
-          s0 = keep_min ? fminf(s0, o0) : fmaxf(s0, o0);
-          s1 = keep_min ? fminf(s1, o1) : fmaxf(s1, o1);
+      for (int k = 0; k < 8; ++k) pa[k] += (lds_off<7 * 4>(pa[k]) <= u[k]) ? 32u : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pa[k] += (lds_off<3 * 4>(pa[k]) <= u[k]) ? 16u : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pa[k] += (lds_off<1 * 4>(pa[k]) <= u[k]) ? 8u : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pa[k] += (lds_off<0>(pa[k]) <= u[k]) ? 4u : 0u;
+      float mean_acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float uu = u[k];
+        const uint32_t pl = pa[k] - (pa[k] != cdf0 ? 4u : 0u);              // &cdf[below], below = max(0, pos - 1)
+        const uint32_t ph = pa[k] - (pa[k] == cdf0 + 63u * 4u ? 4u : 0u);   // &cdf[above], above = min(62, pos)
+        const float cb = lds_off<0>(pl);
+        float denom = __fsub_rn(lds_off<0>(ph), cb);
+        if (denom < 1e-5f) denom = 1.0f;
+        const float tt = __fdiv_rn(__fsub_rn(uu, cb), denom);
+        const float bb = lds_off<0>(pl + to_bins);
+        sv[k] = __fadd_rn(bb, __fmul_rn(tt, __fsub_rn(lds_off<0>(ph + to_bins), bb)));
+        mean_acc += sv[k];
+      }
+      if (active) {
+        if (samples_g) st8(samples_g + ray * 64 + 8 * t, sv);
+        if (inds_g) {
+          longlong2* dst = reinterpret_cast<longlong2*>(inds_g + ray * 64 + 8 * t);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_longlong2((long long)((pa[2 * k] - cdf0) >> 2), (long long)((pa[2 * k + 1] - cdf0) >> 2));
         }
-        const float a = fminf(s0, s1), b = fmaxf(s0, s1);   // j == 1: the pair inside the lane
-        s0 = up ? a : b;
-        s1 = up ? b : a;
+      }
+      if (std_g) {  // torch.std(unbiased=False), run.py:1836: fp32 two-pass like the reference's (tolerance-checked, not bit-exact)
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) mean_acc += __shfl_xor_sync(FULL_MASK, mean_acc, o);
+        const float mean = mean_acc * (1.0f / 64.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float e = sv[k] - mean; sq += e * e; }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(FULL_MASK, sq, o);
+        if (t == 0 && active) std_g[ray] = sqrtf(sq * (1.0f / 64.0f));
       }
     }
-    // ---- bitonic merge of (z ascending, samples descending): element E = 2 lane + r for z, 64 + 2 lane + r for samples
-    float a0 = z2.x, a1 = z2.y;
-    float b0 = __shfl_sync(FULL_MASK, s1, 31 - lane), b1 = __shfl_sync(FULL_MASK, s0, 31 - lane);
-    cmpx(a0, b0);
-    cmpx(a1, b1);
+    // ---- order the 64 samples (element e = 8t + k) if the draws were not sorted
+    {
+      const float s_next = __shfl_down_sync(FULL_MASK, sv[0], 1, 8);
+      bool sorted = (t == 7) || (sv[7] <= s_next);
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const bool keep_min = (lane & m) == 0;
-      const float o0 = __shfl_xor_sync(FULL_MASK, a0, m), o1 = __shfl_xor_sync(FULL_MASK, a1, m);
-      const float o2 = __shfl_xor_sync(FULL_MASK, b0, m), o3 = __shfl_xor_sync(FULL_MASK, b1, m);
-      a0 = keep_min ? fminf(a0, o0) : fmaxf(a0, o0);
-      a1 = keep_min ? fminf(a1, o1) : fmaxf(a1, o1);
-      b0 = keep_min ? fminf(b0, o2) : fmaxf(b0, o2);
-      b1 = keep_min ? fminf(b1, o3) : fmaxf(b1, o3);
+      for (int k = 0; k < 7; ++k) sorted = sorted && (sv[k] <= sv[k + 1]);
+      if (!__all_sync(FULL_MASK, sorted)) {
+#pragma unroll
+        for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+          // merge of sorted runs of k2 / 2 elements: first stage e <-> e ^ (k2 - 1) (the second run taken backwards),
+          // then e <-> e ^ j for j = k2 / 4 .. 1; every comparator leaves the minimum at the lower element
+          if (k2 <= 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((k & (k2 >> 1)) == 0) cmpx(sv[k], sv[k ^ (k2 - 1)]);
+          } else {
+            const int lm = (k2 >> 3) - 1;                   // lane t <-> t ^ lm, element k <-> 7 - k
+            const bool keep_min = (t & (k2 >> 4)) == 0;
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = __shfl_xor_sync(FULL_MASK, sv[7 - k], lm);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sv[k] = keep_min ? fminf(sv[k], o[k]) : fmaxf(sv[k], o[k]);
+          }
+#pragma unroll
+          for (int j = k2 >> 2; j >= 8; j >>= 1) {
+            const bool keep_min = (t & (j >> 3)) == 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float o = __shfl_xor_sync(FULL_MASK, sv[k], j >> 3);
+              sv[k] = keep_min ? fminf(sv[k], o) : fmaxf(sv[k], o);
+            }
+          }
+#pragma unroll
+          for (int j = (k2 >> 2) < 4 ? (k2 >> 2) : 4; j >= 1; j >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if ((k & j) == 0) cmpx(sv[k], sv[k | j]);
+          }
+        }
+      }
     }
-    cmpx(a0, a1);
-    cmpx(b0, b1);
-    reinterpret_cast<float2*>(merged_g + ray * 128)[lane] = make_float2(a0, a1);
-    reinterpret_cast<float2*>(merged_g + ray * 128 + 64)[lane] = make_float2(b0, b1);
-    __syncwarp();                                   // the next ray overwrites w / cdf / bins
+    // ---- bitonic merge of (z ascending, samples descending): elements 8t + k (a) and 64 + 8t + k (b)
+    {
+      float b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[k] = __shfl_sync(FULL_MASK, sv[7 - k], 7 - t, 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cmpx(z[k], b[k]);
+#pragma unroll
+      for (int m = 4; m > 0; m >>= 1) {
+        const bool keep_min = (t & m) == 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float oa = __shfl_xor_sync(FULL_MASK, z[k], m), ob = __shfl_xor_sync(FULL_MASK, b[k], m);
+          z[k] = keep_min ? fminf(z[k], oa) : fmaxf(z[k], oa);
+          b[k] = keep_min ? fminf(b[k], ob) : fmaxf(b[k], ob);
+        }
+      }
+#pragma unroll
+      for (int j = 4; j >= 1; j >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((k & j) == 0) { cmpx(z[k], z[k | j]); cmpx(b[k], b[k | j]); }
+      }
+      if (active) {
+        st8(merged_g + ray * 128 + 8 * t, z);
+        st8(merged_g + ray * 128 + 64 + 8 * t, b);
+      }
+    }
+    __syncwarp();                                   // the next rays overwrite W1 / cdf / bins
   }
 }
 
@@ -563,9 +699,9 @@ int mvip_sample_fine(const float* z_vals, const float* weights, const float* u, 
                "mvip_sample_fine: need 10 <= n_samples <= %d and n_out <= %d (got %d, %d)", kMaxBins + 1, kMaxOut,
                n_samples, n_out);
   if (n_rays == 0) return MVIP_OK;
-  if (n_samples == 64 && n_out == 64 && mvip_aligned(z_vals, 8) && mvip_aligned(weights, 8) && mvip_aligned(u, 8) &&
-      mvip_aligned(z_merged, 8) && (!z_samples || mvip_aligned(z_samples, 8)) && (!inds || mvip_aligned(inds, 16))) {
-    int64_t blocks = (n_rays + 7) / 8;
+  if (n_samples == 64 && n_out == 64 && mvip_aligned(z_vals, 16) && mvip_aligned(weights, 16) && mvip_aligned(u, 16) &&
+      mvip_aligned(z_merged, 16) && (!z_samples || mvip_aligned(z_samples, 16)) && (!inds || mvip_aligned(inds, 16))) {
+    int64_t blocks = (n_rays + 31) / 32;            // 8 warps x 4 rays
     const int64_t cap = (int64_t)mvip_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (u_is_row)

@@ -7,9 +7,10 @@ A cfg-2 step is ~45 kernel launches, 16 of them ours; the three MLP kernels take
 
     rays -> render() -> loss -> backward      (fresh random draws on every replay: torch registers the CUDA generator with
                                                the graph and advances its offset)
-         -> gradient allreduce (N > 1)        one NCCL bucket per network, issued by dist.GradSync from a post-accumulate-grad
-                                               hook the moment a network's gradients exist: the fine network's bucket runs on
-                                               NCCL's stream while the coarse network's backward is still computing
+         -> gradient allreduce (N > 1)        ONE NCCL bucket for both networks (their flat gradient buffers are carved from
+                                               one arena), issued after the backward: the fused backward owns every SM, an
+                                               overlapped collective only delays its CTAs (dist.GradSync(overlap=True) exists
+                                               and measured slower)
          -> Adam (lr and step number read from device memory) -> re-pack of the bf16 weight blobs
 
 as ONE graph, once, after warm-up, and replays it.  (`nccl_in_graph=False` keeps the collectives out of the capture: graph A =

@@ -112,6 +112,11 @@ def test_sample_fine_64x64_fast_path_vs_oracle(ops, mode):
     assert np.array_equal(npy(out["z_samples"]), want["z_samples"])
     assert np.array_equal(npy(out["z_merged"]), want["z_merged"])
     np.testing.assert_allclose(npy(out["z_std"]), want["z_std"], rtol=2e-5, atol=1e-6)
+    # ragged row counts: the kernel carries four rays per warp, the last warp may hold 1 - 3
+    for n in (1, 2, 3, 5, 37, 255):
+        part = ops.sample_fine(cu(z[:n]), cu(w[:n]), cu(u if mode == "det" else u[:n]), want_inds=True)
+        for key in ("inds", "z_samples", "z_merged", "z_std"):
+            assert torch.equal(part[key], out[key][:n]), (n, key)
     # the generic kernel (taken for any other shape) on an embedding of the same problem: 64 draws -> 65 with a duplicate
     if mode != "det":
         u65 = np.concatenate([u, u[:, -1:]], -1)
