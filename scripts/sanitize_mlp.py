@@ -1,4 +1,4 @@
-"""Small forward(+stash) / backward of the tcgen05 MLP kernels for compute-sanitizer (racecheck / synccheck / memcheck):
+"""Small forward(+stash) / backward of the tcgen05 MLP kernels (+ head grads, fine sampler) for compute-sanitizer (racecheck / synccheck / memcheck):
 
     compute-sanitizer --tool racecheck python scripts/sanitize_mlp.py
 """
@@ -23,3 +23,12 @@ raw2, stash = ops.mlp_forward(blob, pts=pts, dirs=dirs, want_stash=True)
 grads = ops.mlp_backward(blob, torch.randn(P, 4, device=dev, generator=g), stash)
 torch.cuda.synchronize()
 print("sanitize_mlp: P=%d raw diff %.3e grad0 norm %.4f" % (P, float((raw - raw2).abs().max()), float(grads[0].norm())))
+# the four-rays-per-warp fine sampler (ragged row count: the last warp holds 1 - 3 rays) and the coarse sampler
+N = 4 * 37 + 3
+z = torch.sort(1.2 + 6.5 * torch.rand(N, 64, device=dev, generator=g), -1).values
+w = torch.rand(N, 64, device=dev, generator=g) ** 8
+w[::5] *= 1e-12                                   # sequential-scan fallback rows
+u = torch.rand(N, 64, device=dev, generator=g)
+fs = ops.sample_fine(z, w, u, want_inds=True)
+torch.cuda.synchronize()
+print("sanitize_mlp: sample_fine N=%d merged sorted %s" % (N, bool((fs["z_merged"][:, 1:] >= fs["z_merged"][:, :-1]).all())))
