@@ -1,6 +1,2 @@
-mkdir -p gpurun_out
-for tool in memcheck racecheck; do
-  timeout 300 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_mlp.py > gpurun_out/r02_$tool.log 2>&1
-  echo "exit $?" >> gpurun_out/r02_$tool.log
-  grep -c "Race reported\|Error:" gpurun_out/r02_$tool.log; grep "Race reported\|Error" gpurun_out/r02_$tool.log | sed 's/.*\(Race reported[^.]*\).*/\1/' | cut -c1-200 | sort | uniq -c | head -12; tail -3 gpurun_out/r02_$tool.log
-done
+timeout 300 python -m pytest tests/test_gpu_mlp.py -q -x -p no:cacheprovider 2>&1 | tail -2
+for v in "" variants/wl/libmvip_nerf.so "" variants/wl/libmvip_nerf.so; do echo "== $v"; MVIP_LIB=$v python scripts/prof_fwd.py 2>&1 | grep "stash="; MVIP_LIB=$v python scripts/prof_fused.py 524288 2>&1 | grep "backward_fused"; done
