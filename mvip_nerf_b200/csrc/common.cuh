@@ -191,11 +191,6 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
                : "memory");
 }
 // same with an L2 eviction-priority hint
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 __device__ __forceinline__ void tma_store_1d_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t policy) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
                "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
