@@ -1,2 +1,9 @@
-timeout 300 python -m pytest tests/test_gpu_mlp.py -q -x -p no:cacheprovider 2>&1 | tail -2
-for v in "" variants/wl/libmvip_nerf.so "" variants/wl/libmvip_nerf.so; do echo "== $v"; MVIP_LIB=$v python scripts/prof_fwd.py 2>&1 | grep "stash="; MVIP_LIB=$v python scripts/prof_fused.py 524288 2>&1 | grep "backward_fused"; done
+mkdir -p gpurun_out
+date +%s > gpurun_out/t0
+timeout 420 bash scripts/profile.sh > gpurun_out/profile.log 2>&1
+echo "profile.sh done after $(( $(date +%s) - $(cat gpurun_out/t0) )) s"
+python scripts/prof_fused.py 524288 > gpurun_out/r02_prof_fused.txt 2>&1
+python scripts/prof_fused.py 262144 >> gpurun_out/r02_prof_fused.txt 2>&1
+python scripts/bwd_timeline.py 524288 > gpurun_out/r02_bwd_timeline.txt 2>&1
+python scripts/hbm_stages.py > gpurun_out/r02_hbm_stages.txt 2>&1; grep -v "^{" gpurun_out/r02_hbm_stages.txt | tail -9
+echo "all done after $(( $(date +%s) - $(cat gpurun_out/t0) )) s"; ls -la gpurun_out | head -30
