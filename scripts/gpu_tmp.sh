@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-date +%s > gpurun_out/t0
-timeout 420 bash scripts/profile.sh > gpurun_out/profile.log 2>&1
-echo "profile.sh done after $(( $(date +%s) - $(cat gpurun_out/t0) )) s"
-python scripts/prof_fused.py 524288 > gpurun_out/r02_prof_fused.txt 2>&1
-python scripts/prof_fused.py 262144 >> gpurun_out/r02_prof_fused.txt 2>&1
-python scripts/bwd_timeline.py 524288 > gpurun_out/r02_bwd_timeline.txt 2>&1
-python scripts/hbm_stages.py > gpurun_out/r02_hbm_stages.txt 2>&1; grep -v "^{" gpurun_out/r02_hbm_stages.txt | tail -9
-echo "all done after $(( $(date +%s) - $(cat gpurun_out/t0) )) s"; ls -la gpurun_out | head -30
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
+python - <<'PY'
+import json
+d = json.loads([l for l in open('gpurun_out/final_bench.json') if l.startswith('{')][-1])
+print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'launches', d['gpu_launches'], 'steps', d['steps'])
+for k, v in d['kernels'].items(): print(k, round(v['ms_per_step'], 4), {a: round(b, 3) for a, b in v.items() if a.startswith('frac') or a in ('tflops', 'hbm_gbs')})
+r = d['roofline']; print({k: r[k] for k in ('kernel', 'bound', 'achieved', 'peak', 'frac', 'frac_burst', 'frac_sustained', 'traffic', 'share_of_step')}); print(r['step']); print(r['secondary'])
+print(d['clocks']); print(d.get('cpu_baseline')); print(d['render'], d['guidance'], d['guidance_train'])
+PY
