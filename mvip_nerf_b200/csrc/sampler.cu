@@ -53,44 +53,37 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, int ray_str
   z_out[idx] = z;
 }
 
-// Warp-per-ray form for S = 32 C (C = 1, 2, 4): lane l owns samples [l C, l C + C).  The per-sample table values
-// (t, 1 - t) live in registers across rays, 1/near and 1/far are ONE reciprocal instruction (lane parity picks the
-// operand), every stratum is evaluated once and its neighbours' values arrive by shuffle, t_rand / z move as 4C-byte
-// vectors.  ~1.5 instructions per sample instead of ~120 (three stratum evaluations with five IEEE divisions each).
+// Register form for S = 4 G (G = 8, 16, 32 lanes per ray, 32 / G rays per warp): lane `sub` of a ray's group owns the FOUR
+// samples [4 sub, 4 sub + 4), so t_rand / z always move as 16-byte vectors.  The per-sample table values (t, 1 - t) live in
+// registers across rays, 1/near and 1/far are ONE reciprocal instruction (lane parity picks the operand), every stratum is
+// evaluated once and its neighbours' values arrive by shuffle inside the group.  ~1.5 instructions per sample instead of
+// ~120 (three stratum evaluations with five IEEE divisions each).
 // __frcp_rn is the correctly rounded reciprocal == IEEE 1/x == torch's reciprocal.
-template <int C>
+template <int G>
 __global__ void __launch_bounds__(256)
 sample_coarse_warp_kernel(const float* __restrict__ rays, int ray_stride, int64_t n_rays, const float* __restrict__ t_vals,
                           const float* __restrict__ t_rand, int lindisp, float* __restrict__ z_out) {
-  constexpr int S = 32 * C;
-  const int lane = threadIdx.x & 31;
+  constexpr int C = 4, S = C * G, RPW = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
   float t[C], omt[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) {
-    t[k] = __ldg(t_vals + lane * C + k);
+    t[k] = __ldg(t_vals + sub * C + k);
     omt[k] = __fsub_rn(1.0f, t[k]);
   }
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  // kU rays per trip: all their loads (near / far, the C draws) are issued before the first use, so a warp keeps kU x (8 + 4 S)
-  // bytes in flight instead of one ray's (the stage is latency-bound: ~1.5 instructions per sample)
-  constexpr int kU = 4;
-  for (int64_t r0 = warp0; r0 < n_rays; r0 += kU * nwarps) {
+  // kU ray groups per trip: all their loads (near / far, the draws) are issued before the first use
+  constexpr int kU = (G == 32) ? 4 : 1;      // S = 64 (two rays per warp), 262,144 rays: kU = 1 / 2 / 4 / 8 -> 65.9 / 58.3 / 52.3 / 47.4 % of the copy peak
+  for (int64_t r0 = warp0 * RPW; r0 < n_rays; r0 += kU * nwarps * RPW) {
     float nf[kU], tr[kU][C];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t r = r0 + u * nwarps;
+      const int64_t r = r0 + u * nwarps * RPW + grp;
       const bool live = r < n_rays;
-      nf[u] = live ? __ldg(rays + r * ray_stride + 6 + (lane & 1)) : 1.f;     // even lanes: near, odd lanes: far
+      nf[u] = live ? __ldg(rays + r * ray_stride + 6 + (sub & 1)) : 1.f;     // even lanes: near, odd lanes: far
       if (t_rand != nullptr && live) {
-        if constexpr (C == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(t_rand + r * S) + lane);
-          tr[u][0] = v.x; tr[u][1] = v.y; tr[u][2] = v.z; tr[u][3] = v.w;
-        } else if constexpr (C == 2) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(t_rand + r * S) + lane);
-          tr[u][0] = v.x; tr[u][1] = v.y;
-        } else {
-          tr[u][0] = __ldg(t_rand + r * S + lane);
-        }
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(t_rand + r * S) + sub);
+        tr[u][0] = v.x; tr[u][1] = v.y; tr[u][2] = v.z; tr[u][3] = v.w;
       } else {
 #pragma unroll
         for (int k = 0; k < C; ++k) tr[u][k] = 0.f;
@@ -98,11 +91,12 @@ sample_coarse_warp_kernel(const float* __restrict__ rays, int ray_stride, int64_
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t r = r0 + u * nwarps;
-      if (r >= n_rays) break;                                      // warp-uniform
+      const int64_t rg0 = r0 + u * nwarps * RPW;
+      if (rg0 >= n_rays) break;                                    // warp-uniform
+      const int64_t r = rg0 + grp;
       float nfu = nf[u];
       if (lindisp) nfu = __frcp_rn(nfu);
-      const float a = __shfl_sync(FULL_MASK, nfu, 0), b = __shfl_sync(FULL_MASK, nfu, 1);
+      const float a = __shfl_sync(FULL_MASK, nfu, 0, G), b = __shfl_sync(FULL_MASK, nfu, 1, G);
       float z[C];
 #pragma unroll
       for (int k = 0; k < C; ++k) {
@@ -110,22 +104,20 @@ sample_coarse_warp_kernel(const float* __restrict__ rays, int ray_stride, int64_
         if (lindisp) z[k] = __frcp_rn(z[k]);
       }
       if (t_rand != nullptr) {
-        const float prev = __shfl_up_sync(FULL_MASK, z[C - 1], 1), next = __shfl_down_sync(FULL_MASK, z[0], 1);
+        const float prev = __shfl_up_sync(FULL_MASK, z[C - 1], 1, G), next = __shfl_down_sync(FULL_MASK, z[0], 1, G);
         float out[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) {
           const float zp = (k > 0) ? z[(k > 0) ? k - 1 : 0] : prev, zn = (k + 1 < C) ? z[(k + 1 < C) ? k + 1 : k] : next;
           float lower = __fmul_rn(0.5f, __fadd_rn(z[k], zp)), upper = __fmul_rn(0.5f, __fadd_rn(zn, z[k]));
-          if (k == 0 && lane == 0) lower = z[k];
-          if (k == C - 1 && lane == 31) upper = z[k];
+          if (k == 0 && sub == 0) lower = z[k];
+          if (k == C - 1 && sub == G - 1) upper = z[k];
           out[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[u][k]));
         }
 #pragma unroll
         for (int k = 0; k < C; ++k) z[k] = out[k];
       }
-      if constexpr (C == 4) reinterpret_cast<float4*>(z_out + r * S)[lane] = make_float4(z[0], z[1], z[2], z[3]);
-      else if constexpr (C == 2) reinterpret_cast<float2*>(z_out + r * S)[lane] = make_float2(z[0], z[1]);
-      else z_out[r * S + lane] = z[0];
+      if (r < n_rays) __stcs(reinterpret_cast<float4*>(z_out + r * S) + sub, make_float4(z[0], z[1], z[2], z[3]));
     }
   }
 }
@@ -655,13 +647,14 @@ int mvip_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const 
   if (n_rays == 0) return MVIP_OK;  // empty batch: nothing to do (pointers may be null)
   MVIP_REQUIRE(rays && t_vals && z_out, MVIP_E_INVALID, "mvip_sample_coarse: null pointer");
   if ((n_samples == 32 || n_samples == 64 || n_samples == 128) && mvip_aligned(z_out, 16) && (!t_rand || mvip_aligned(t_rand, 16))) {
-    int64_t blocks = (n_rays + 7) / 8;
-    const int64_t cap = (int64_t)mvip_num_sms() * 8;
+    const int rpw = 128 / n_samples;                 // rays per warp: 4 samples per lane
+    int64_t blocks = (n_rays + 8 * rpw - 1) / (8 * rpw);
+    const int64_t cap = (int64_t)mvip_num_sms() * 8;       // (16 blocks per SM: the same; uncapped: 43 %)
     if (blocks > cap) blocks = cap;
     auto st = (cudaStream_t)stream;
-    if (n_samples == 32) sample_coarse_warp_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
-    else if (n_samples == 64) sample_coarse_warp_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
-    else sample_coarse_warp_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    if (n_samples == 32) sample_coarse_warp_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    else if (n_samples == 64) sample_coarse_warp_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
+    else sample_coarse_warp_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(rays, ray_stride, n_rays, t_vals, t_rand, lindisp, z_out);
     MVIP_LAUNCH_OK("sample_coarse_warp_kernel");
     return MVIP_OK;
   }
