@@ -297,8 +297,10 @@ struct MseArgs {
   const float* g_sq;          // backward: [2] (device)
 };
 
+// four resident blocks per SM (61 registers): 83 % / 87 % of the copy peak at S = 64 / 128 (five blocks, 48 registers: 81 % / 82 %;
+// three: 83 % / 77 %; six, with spills: 72 % / 75 %)
 template <int G>
-__global__ void __launch_bounds__(kWarps * 32, 5)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 composite_fwd4_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                       int d_stride, const float* __restrict__ noise, int64_t n_rays, int white,
                       float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
