@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -4
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/val_ref.json 2> gpurun_out/val_ref.err
-timeout 900 python bench.py > gpurun_out/val_bench.json 2> gpurun_out/val_bench.err
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/val_bench.json 2> gpurun_out/val_bench.err
 python - <<'PY'
 import json
 try:
