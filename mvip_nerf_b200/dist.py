@@ -312,7 +312,7 @@ class GradSync:
     overlap=False: finish() starts and joins all buckets after the backward pass.  The fused MLP backward is a persistent
     kernel that needs every SM (its CTA pairs wait for each other's tiles): an NCCL kernel that gets SMs first keeps part of its
     grid from becoming resident until the collective (and the peer it waits for) is done, so the graphed train step does not
-    overlap (measured on 2 B200: 4.00 ms per step overlapped).
+    overlap (measured on 2 B200: 3.74 - 4.00 ms per step overlapped against 3.64 ms with one bucket after the backward).
 
         sync = GradSync([fine_params, coarse_params])
         loss.backward(); sync.finish(); optimizer.step()
