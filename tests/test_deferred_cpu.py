@@ -2,6 +2,7 @@
 render_rays is replaced by a small differentiable torch stand-in (the real one needs the CUDA library), so what is checked
 is the chunk loop, the gradient slicing / accumulation and the replay of the random streams."""
 import numpy as np
+import pytest
 import torch
 
 from mvip_nerf_b200 import run
@@ -112,3 +113,28 @@ def test_render_path_4view_pose_selection(monkeypatch):
     seen.clear()
     run.render_path_4view(127, masks, poses, [8, 12, 10.0], 64, {})
     assert seen == [3.0, 5.0, 7.0, 9.0, 11.0]                                                          # iter = 7
+
+
+def test_patch_is_clipped_like_the_reference_slicing():
+    """render(patch=...) past the image border: the reference slices rays_o[i:i+len1, j:j+len2] (run.py:1174), which clips
+    silently; run._clip_patch must give the same extent (the first version raised)."""
+    from mvip_nerf_b200 import run
+    rng = np.random.RandomState(0)
+    H, W = 37, 53
+    img = np.zeros((H, W))
+    for _ in range(200):
+        i, j = int(rng.randint(0, H)), int(rng.randint(0, W))
+        l1, l2 = int(rng.randint(1, 64)), int(rng.randint(1, 64))
+        ci, cj, c1, c2 = run._clip_patch((i, j, l1, l2), H, W)
+        assert (ci, cj) == (i, j)
+        assert (c1, c2) == img[i:i + l1, j:j + l2].shape
+
+
+def test_graphed_adam_refuses_several_param_groups():
+    """FusedAdam's CUDA-graph form keeps one device-resident (lr, step) pair: more than one group must raise
+    before anything is captured, not silently train every group with group 0's learning rate."""
+    from mvip_nerf_b200.optim import FusedAdam
+    a, b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2))
+    opt = FusedAdam([{"params": [a]}, {"params": [b], "lr": 1e-2}], lr=5e-4)
+    with pytest.raises(RuntimeError, match="single param group"):
+        opt.graph_begin(torch.device("cpu"))

@@ -356,3 +356,35 @@ def test_fused_backward_does_not_depend_on_its_scheduling_knobs():
     assert torch.isfinite(outs[0]).all()
     for o in outs[1:]:
         assert torch.equal(outs[0], o)
+
+
+def test_backward_after_a_repack_raises(ops):
+    """The packed bf16 blob is shared and re-packed in place: a backward that runs after the parameters changed would use the
+    NEW weights for dgrad.  NeRF records the pack generation at forward and refuses such a backward; an in-place
+    parameter write followed by invalidate_packed() is picked up by the next forward."""
+    from mvip_nerf_b200.run_nerf_helpers import NeRF
+    torch.manual_seed(0)
+    net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True).cuda()
+    pts = torch.rand(300, 3, device="cuda") * 2 - 1
+    dirs = torch.nn.functional.normalize(torch.randn(300, 3, device="cuda"), dim=-1)
+    raw0 = net.query_points(pts, dirs)
+    raw0.sum().backward()                                           # the normal order works
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    raw1 = net.query_points(pts, dirs)
+    with torch.no_grad():
+        net.rgb_linear.bias.data.add_(0.25)                          # a raw .data write bumps no version counter ...
+    net.invalidate_packed()                                          # ... so the contract is an explicit invalidation
+    raw2 = net.query_points(pts, dirs)                               # re-packs: the new bias is visible
+    assert float((raw2[:, :3] - raw1[:, :3] - 0.25).detach().abs().max()) < 1e-5
+    with pytest.raises(RuntimeError, match="re-packed"):
+        raw1.sum().backward()
+
+
+def test_empty_batch_gives_zero_gradients(ops):
+    """N_rays == 0 under grad (reachable from dist.shard_rows when rays < world): the backward launches nothing, so the 24
+    gradients must come back as zeros, not as uninitialised memory that a sum-allreduce would spread."""
+    p = orc.init_params(2)
+    blob = pack(ops, p)
+    stash = torch.empty(0, dtype=torch.uint8, device="cuda")
+    grads = ops.mlp_backward(blob, torch.empty(0, 4, device="cuda"), stash)
+    assert len(grads) == 24 and all(float(g.abs().max()) == 0.0 for g in grads)
