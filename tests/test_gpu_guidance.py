@@ -76,6 +76,29 @@ def test_deferred_rays_entry_and_loss_backward(nerf):
     assert any(float(p.grad.abs().max()) > 0.0 for p in fine)
 
 
+def test_deferred_accepts_what_render_accepts(nerf):
+    """render_deferred shares render()'s ray-batch assembly: per-ray near / far tensors (the reference allows them,
+    run.py:1201-1203) and a static camera with view directions take the torch route instead of raising, and give render()'s
+    numbers."""
+    run, kw_train, kw_test, grad_vars, opt = nerf
+    g = torch.Generator().manual_seed(1)
+    ro = torch.zeros(200, 3).cuda()
+    rd = torch.nn.functional.normalize(torch.randn(200, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.]), dim=-1).cuda()
+    rays = torch.stack([ro, rd], 0)
+    near = (1.0 + 0.4 * torch.rand(200, 1, generator=g)).cuda()
+    far = (7.0 + torch.rand(200, 1, generator=g)).cuda()
+    with torch.no_grad():
+        want = run.render(756, 1008, 767.2935, chunk=128, rays=rays, near=near, far=far, **kw_test)
+    got = run.render_deferred(756, 1008, 767.2935, chunk=128, rays=rays, near=near, far=far, **kw_test)
+    assert torch.equal(got[0].detach(), want[0]) and torch.equal(got[3].detach(), want[3])
+    c2w, cam = pose(0.1, 0.05), pose(-0.2, 0.0)
+    with torch.no_grad():
+        want = run.render(12, 16, 20.0, chunk=128, c2w=c2w, c2w_staticcam=cam, near=1.2, far=7.7, **kw_test)
+    got = run.render_deferred(12, 16, 20.0, chunk=128, c2w=c2w, c2w_staticcam=cam, near=1.2, far=7.7, **kw_test)
+    assert torch.equal(got[0].detach(), want[0])
+    got[0].mean().backward()
+
+
 def test_render_path_writes_reference_layout(nerf, tmp_path):
     run, kw_train, kw_test, grad_vars, opt = nerf
     poses = torch.stack([pose(0.0), pose(0.2, 0.1)], 0)
