@@ -519,16 +519,24 @@ sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ we
       for (int k = 0; k < 8; ++k) pa[k] += (lds_off<3 * 4>(pa[k]) <= u[k]) ? 16u : 0u;
 #pragma unroll
       for (int k = 0; k < 8; ++k) pa[k] += (lds_off<1 * 4>(pa[k]) <= u[k]) ? 8u : 0u;
+      float v6[8];                                          // the last probe, cdf[pos6] (pos6 even): it IS one of the two lerp operands
+      bool inc[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) pa[k] += (lds_off<0>(pa[k]) <= u[k]) ? 4u : 0u;
+      for (int k = 0; k < 8; ++k) {
+        v6[k] = lds_off<0>(pa[k]);
+        inc[k] = v6[k] <= u[k];
+        pa[k] += inc[k] ? 4u : 0u;
+      }
       float mean_acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float uu = u[k];
         const uint32_t pl = pa[k] - (pa[k] != cdf0 ? 4u : 0u);              // &cdf[below], below = max(0, pos - 1)
         const uint32_t ph = pa[k] - (pa[k] == cdf0 + 63u * 4u ? 4u : 0u);   // &cdf[above], above = min(62, pos)
-        const float cb = lds_off<0>(pl);
-        float denom = __fsub_rn(lds_off<0>(ph), cb);
+        // pos = pos6 + 1: cdf[below] is the probe, cdf[above] is loaded; pos = pos6: cdf[above] is the probe, cdf[below] is loaded
+        const float other = lds_off<0>(inc[k] ? ph : pl);
+        const float cb = inc[k] ? v6[k] : other;
+        float denom = __fsub_rn(inc[k] ? other : v6[k], cb);
         if (denom < 1e-5f) denom = 1.0f;
         const float tt = __fdiv_rn(__fsub_rn(uu, cb), denom);
         const float bb = lds_off<0>(pl + to_bins);
@@ -556,21 +564,26 @@ sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ we
         if (t == 0 && active) std_g[ray] = sqrtf(sq * (1.0f / 64.0f));
       }
     }
-    // ---- order the 64 samples (element e = 8t + k) if the draws were not sorted
+    // ---- the samples in DESCENDING order (element e = 8t + k holds the (63 - e)-th smallest): the second half of the bitonic
+    //      sequence the merge below starts from.  Unsorted draws: a descending sort network; ascending draws: reversed by shuffle.
+    float b[8];
     {
       const float s_next = __shfl_down_sync(FULL_MASK, sv[0], 1, 8);
       bool sorted = (t == 7) || (sv[7] <= s_next);
 #pragma unroll
       for (int k = 0; k < 7; ++k) sorted = sorted && (sv[k] <= sv[k + 1]);
-      if (!__all_sync(FULL_MASK, sorted)) {
+      if (__all_sync(FULL_MASK, sorted)) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[k] = __shfl_sync(FULL_MASK, sv[7 - k], 7 - t, 8);
+      } else {
 #pragma unroll
         for (int k2 = 2; k2 <= 64; k2 <<= 1) {
           // merge of sorted runs of k2 / 2 elements: first stage e <-> e ^ (k2 - 1) (the second run taken backwards),
-          // then e <-> e ^ j for j = k2 / 4 .. 1; every comparator leaves the minimum at the lower element
+          // then e <-> e ^ j for j = k2 / 4 .. 1; every comparator leaves the MAXIMUM at the lower element
           if (k2 <= 8) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if ((k & (k2 >> 1)) == 0) cmpx(sv[k], sv[k ^ (k2 - 1)]);
+              if ((k & (k2 >> 1)) == 0) cmpx(sv[k ^ (k2 - 1)], sv[k]);
           } else {
             const int lm = (k2 >> 3) - 1;                   // lane t <-> t ^ lm, element k <-> 7 - k
             const bool keep_min = (t & (k2 >> 4)) == 0;
@@ -578,7 +591,7 @@ sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ we
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = __shfl_xor_sync(FULL_MASK, sv[7 - k], lm);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sv[k] = keep_min ? fminf(sv[k], o[k]) : fmaxf(sv[k], o[k]);
+            for (int k = 0; k < 8; ++k) sv[k] = keep_min ? fmaxf(sv[k], o[k]) : fminf(sv[k], o[k]);   // keep_min = lower element: it keeps the max
           }
 #pragma unroll
           for (int j = k2 >> 2; j >= 8; j >>= 1) {
@@ -586,23 +599,22 @@ sample_fine64_kernel(const float* __restrict__ z_g, const float* __restrict__ we
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float o = __shfl_xor_sync(FULL_MASK, sv[k], j >> 3);
-              sv[k] = keep_min ? fminf(sv[k], o) : fmaxf(sv[k], o);
+              sv[k] = keep_min ? fmaxf(sv[k], o) : fminf(sv[k], o);
             }
           }
 #pragma unroll
           for (int j = (k2 >> 2) < 4 ? (k2 >> 2) : 4; j >= 1; j >>= 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if ((k & j) == 0) cmpx(sv[k], sv[k | j]);
+              if ((k & j) == 0) cmpx(sv[k | j], sv[k]);
           }
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[k] = sv[k];
       }
     }
     // ---- bitonic merge of (z ascending, samples descending): elements 8t + k (a) and 64 + 8t + k (b)
     {
-      float b[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) b[k] = __shfl_sync(FULL_MASK, sv[7 - k], 7 - t, 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) cmpx(z[k], b[k]);
 #pragma unroll
