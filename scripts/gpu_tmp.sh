@@ -1,2 +1,3 @@
-timeout 200 python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovider -k "sample_fine or sample_pdf" 2>&1 | tail -3
-timeout 100 python scripts/hbm_stages.py 2>&1 | grep "sample_fine" | grep -v "^{"
+# scratch: the command of the last one-off GPU check of the round (final build: smoke + end-to-end render tests)
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 60 python -m pytest tests/test_gpu_render.py -q -x -p no:cacheprovider 2>&1 | tail -2
